@@ -1,0 +1,192 @@
+/* hmpc.h -- C ABI of the B200-native hybrid-MPC hot path (libhmpc.so, sm_100a).
+ *
+ * Every entry point replaces one step of michchr/pyhybridcontrol's per-step hybrid-MPC solve; the
+ * reference interface each one stands in for is cited as file:line (relative to the reference root).
+ * The reference is pure Python, so "what its FFI would bind" is the ctypes stub shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types.
+ *   - *_f64 functions take DEVICE pointers and a cudaStream_t passed as void* (NULL = default stream);
+ *     they enqueue work and return without synchronising.  *_host_f64 functions take HOST pointers, do the
+ *     host<->device copies themselves on an internal stream and return after the result is on the host.
+ *   - all matrices are FP64, row-major, batch-major: agent b's block starts at base + b*stride_b elements;
+ *     stride_b == 0 broadcasts one block to the whole batch.
+ *   - the library never allocates or frees caller buffers; scratch comes in through (workspace, bytes),
+ *     sized by the matching *_workspace_bytes query.
+ *   - return value: HMPC_OK or a negative hmpc_status; per-problem solver outcomes are in status arrays.
+ *   - thread-compatible: no global mutable state; concurrent calls must use distinct workspaces/streams.
+ */
+#ifndef HMPC_H_
+#define HMPC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    HMPC_OK = 0,
+    HMPC_ERR_ARG = -1,        /* bad dimension / null pointer / unsupported size           */
+    HMPC_ERR_CUDA = -2,       /* a CUDA runtime call failed (see hmpc_last_cuda_error)      */
+    HMPC_ERR_WORKSPACE = -3,  /* workspace too small                                        */
+    HMPC_ERR_NO_DEVICE = -4   /* no sm_100 device visible                                   */
+} hmpc_status;
+
+/* per-problem outcome of hmpc_milp_solve_f64 (status[b]) */
+typedef enum {
+    HMPC_SOLVE_OPTIMAL = 0,     /* proven optimal (within mip_rel_gap)                      */
+    HMPC_SOLVE_INFEASIBLE = 1,
+    HMPC_SOLVE_NODE_LIMIT = 2,  /* best incumbent returned, not proven                      */
+    HMPC_SOLVE_ITER_LIMIT = 3,
+    HMPC_SOLVE_NUMERIC = 4,     /* lost dual feasibility / artificial bound active          */
+    HMPC_SOLVE_UNSUPPORTED = 5
+} hmpc_solve_status;
+
+/* MLD dimensions (reference: models/mld_model.py:149-168) + horizon (controllers/controller_base.py:159-160) */
+typedef struct {
+    int32_t B;        /* agents in the batch                     */
+    int32_t Nt;       /* N_tilde, number of stacked steps        */
+    int32_t nx, nu, ndelta, nz, nmu, nomega, ny, nc;
+} hmpc_dims;
+
+/* index of each system matrix in the mats[] / mat_stride_b[] arrays of hmpc_condense_f64 */
+enum { HMPC_A = 0, HMPC_B1, HMPC_B2, HMPC_B3, HMPC_B4, HMPC_b5,
+       HMPC_C, HMPC_D1, HMPC_D2, HMPC_D3, HMPC_D4, HMPC_d5,
+       HMPC_E, HMPC_F1, HMPC_F2, HMPC_F3, HMPC_F4, HMPC_f5, HMPC_G, HMPC_Psi, HMPC_NUM_MATS };
+
+/* index of each condensed matrix in out[] */
+enum { HMPC_PHI_X = 0, HMPC_GAMMA_V, HMPC_GAMMA_OMEGA, HMPC_GAMMA_5,
+       HMPC_L_X, HMPC_L_V, HMPC_L_OMEGA, HMPC_L_5,
+       HMPC_H_X, HMPC_H_V, HMPC_H_OMEGA, HMPC_H_5, HMPC_NUM_EVO };
+
+/* ---- library ------------------------------------------------------------------------------------ */
+int hmpc_version(void);
+const char* hmpc_last_cuda_error(void);           /* message of the last CUDA failure in this thread */
+int hmpc_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* smem_optin_bytes);
+
+/* ---- K1 condense: replaces MldEvoMatrices.gen_mld_evo_matrices
+ *      (controllers/components/mld_evolution_matrices.py:108-134; formulas :237-240, :253-332, :467-527).
+ *  mats[i]   : [B or 1, rows_i, cols_i]; NULL = all-zero block (C must be given explicitly).
+ *  out[i]    : [B, rows*Nt, cols*Nt] dense row-major, NULL = skip.  Shapes: Phi_x (nx*Nt, nx), Gamma_v
+ *              (nx*Nt, nv*Nt), Gamma_omega (nx*Nt, nomega*Nt), Gamma_5 (nx*Nt, 1), L_* with ny rows/step,
+ *              H_* with nc rows/step; nv = nu+ndelta+nz+nmu, v(k) = [u; delta; z; mu].
+ *  The *_N_p variants of the reference are row-prefix views of these (:246-250).                     */
+int hmpc_condense_f64(const hmpc_dims* dims, const double* const mats[HMPC_NUM_MATS],
+                      const int64_t mat_stride_b[HMPC_NUM_MATS], double* const out[HMPC_NUM_EVO], void* stream);
+/* algorithmic bytes one agent's 12 matrices occupy (roofline numerator of K1) */
+int64_t hmpc_condense_bytes_per_agent(const hmpc_dims* dims);
+
+/* ---- K2 constraint right-hand side: replaces ConstraintSolvedController.gen_evo_constraints
+ *      (controllers/controller_base.py:440-452):  rhs = H_x x0 + H_omega w + H_5        (S == 0)
+ *                                                rhs = H_x x0 + rowmin_s(H_omega W) + H_5 (S  > 0)
+ *  rows <= nc*Nt selects the reduced-horizon prefix (mld_evolution_matrices.py:89-105).
+ *  x0 [B,nx]; w [B, nomega*Nt] or scenarios W [B, nomega*Nt, S]; rhs [B, rows].                       */
+int hmpc_constraint_rhs_f64(const hmpc_dims* dims, int32_t rows, const double* H_x, const double* H_omega,
+                            const double* H_5, const double* x0, const double* w, int32_t S,
+                            double* rhs, void* stream);
+
+/* ---- affine prediction: x~ = Phi x0 + Gamma_v v + Gamma_w w + Gamma_5  (or y~ with the L matrices);
+ *      replaces EvoVariables.gen_state_output_vars (controllers/components/variables.py:245-286).
+ *  M_x [B,R,nx], M_v [B,R,nvt], M_w [B,R,nwt], M_5 [B,R]; v [B,nvt] may be NULL (constant part only).  */
+int hmpc_predict_f64(int32_t B, int32_t R, int32_t nx, int32_t nvt, int32_t nwt, const double* M_x,
+                     const double* M_v, const double* M_w, const double* M_5, const double* x0,
+                     const double* v, const double* w, double* out, void* stream);
+
+/* ---- linear cost in v-space from Linear atoms on v and on the affine predictions
+ *      (controllers/components/objective_atoms.py:308-318, 523-532):
+ *        c   = w_v + Gamma_v' w_x + L_v' w_y                       [B, nvt]
+ *        c0  = w_x'(x~ at v=0) + w_y'(y~ at v=0)                   [B]
+ *  any of w_x / w_y may be NULL.  xc / yc are the constant parts from hmpc_predict_f64(v = NULL).       */
+int hmpc_linear_cost_f64(int32_t B, int32_t nvt, int32_t nxt, int32_t nyt, const double* w_v, int64_t w_v_stride_b,
+                         const double* w_x, const double* Gamma_v, const double* xc,
+                         const double* w_y, const double* L_v, const double* yc,
+                         double* c, double* c0, void* stream);
+
+/* ---- K3/K4 mixed-integer solve: replaces cvx.Problem.solve -> Gurobi/CPLEX inside
+ *      ConstraintSolvedController.solve (controllers/controller_base.py:509-512).
+ *      minimise c'v (+c0)  s.t.  H v <= rhs,  lb <= v <= ub,  v[j] in {0,1} where is_bin[j] != 0.
+ *  One CTA per problem: row-generating bounded dual simplex on a shared-memory tableau, c-MIR cuts,
+ *  depth-first branch and bound.                                               */
+typedef struct {
+    double  mip_rel_gap;     /* 0 = prove optimality (reference ran MIPGap=1e-2)                        */
+    double  int_tol;         /* integrality tolerance, default 1e-6                                     */
+    double  feas_tol;        /* primal feasibility tolerance, default 1e-9                              */
+    double  big_bound;       /* artificial box for free columns, default 1e7                            */
+    int32_t max_nodes;       /* per problem, default 200000                                             */
+    int32_t max_pivots;      /* per problem, default 2000000                                            */
+    int32_t max_cuts;        /* cut-pool capacity per problem, default 512                              */
+    int32_t max_rows;        /* active tableau rows (0 = as many as shared memory allows)               */
+    int32_t cut_rounds_root; /* default 30                                                              */
+    int32_t cut_rounds_node; /* default 2                                                               */
+    int32_t cuts_per_round;  /* default 8                                                               */
+    int32_t reserved;
+} hmpc_milp_opts;
+
+void hmpc_milp_default_opts(hmpc_milp_opts* opts);
+int  hmpc_milp_workspace_bytes(int32_t B, int32_t n, int32_t m, const hmpc_milp_opts* opts, size_t* bytes);
+/*  c [B,n] (stride_c_b), H [B,m,n] (stride_H_b), rhs [B,m], lb/ub [B,n] (stride_bnd_b; +-inf allowed),
+ *  is_bin [n] bytes shared by the batch.  Outputs: v [B,n], obj [B] (= c'v, caller adds c0),
+ *  status [B] (hmpc_solve_status), stats [B,8] = {nodes, pivots, cuts, rows_added, max_rows, lp_solves,
+ *  purges, reserved}.                                                                                 */
+int  hmpc_milp_solve_f64(int32_t B, int32_t n, int32_t m,
+                         const double* c, int64_t stride_c_b, const double* H, int64_t stride_H_b,
+                         const double* rhs, const double* lb, const double* ub, int64_t stride_bnd_b,
+                         const uint8_t* is_bin, const hmpc_milp_opts* opts,
+                         void* workspace, size_t workspace_bytes,
+                         double* v, double* obj, int32_t* status, int32_t* stats, void* stream);
+
+/* ---- K5 simulation step: replaces MldModel.lsim_k (models/mld_model.py:647-699): mu ignored in cons
+ *      (:694), tolerance cons_tol (default 1e-6, :648).  mats as in hmpc_condense_f64.
+ *  x [B,nx], u [B,nu], delta [B,ndelta], z [B,nz], w [B,nomega] -> x1 [B,nx], y [B,ny], cons [B,nc] bytes */
+int hmpc_lsim_step_f64(const hmpc_dims* dims, const double* const mats[HMPC_NUM_MATS],
+                       const int64_t mat_stride_b[HMPC_NUM_MATS], const double* x, const double* u,
+                       const double* delta, const double* z, const double* w, double cons_tol,
+                       double* x1, double* y, uint8_t* cons, void* stream);
+
+/* ---- DEWH simulation model re-parametrisation + step: replaces DewhAgentMpc.sim_step_k
+ *      (examples/residential_mg_with_pv_and_dewhs/modelling/micro_grid_agents.py:389-408) and the
+ *      const_heat=False model (micro_grid_models.py:45-57).  params [B,12] =
+ *      {C_w, A_h, U_h, m_h, T_w, T_inf, P_h_Nom, T_h_min, T_h_max, T_h_Nom, ts, reserved}.
+ *  T [B] is clamped to T_w+0.1 first; outputs T1 [B], model [B,4] = {A, B1, B4, b5} (may be NULL),
+ *  cons [B,2] bytes (may be NULL).                                                                     */
+int hmpc_dewh_sim_step_f64(int32_t B, const double* params, const double* T, const double* u,
+                           const double* D_h, double* T1, double* model, uint8_t* cons, void* stream);
+/* control model (const_heat=True): model [B,4] = {A, B1, B4, b5} */
+int hmpc_dewh_control_model_f64(int32_t B, const double* params, double* model, void* stream);
+
+/* ---- K6 aggregate power: replaces GridAgentMpc.get_grid_device_powers_N_tilde + GridModel D4 = ones
+ *      (micro_grid_agents.py:625-646, micro_grid_models.py:143):  P_agg[k] = sum_b P_nom[b] * u[b,k].
+ *  Deterministic two-pass tree; partial [ceil(B/256), Nt] scratch from the caller.                     */
+int hmpc_aggregate_power_f64(int32_t B, int32_t Nt, const double* u, int64_t u_stride_b, int32_t u_stride_k,
+                             const double* P_nom, double* partial, double* P_agg, void* stream);
+
+/* ---- host-buffer front door: one whole control step for a batch (what a ctypes/cgo/JNI caller binds).
+ *      Replaces, for every agent of the batch, MpcController.build() + solve()
+ *      (controllers/mpc_controller.py:76-101, controllers/controller_base.py:491-540) with Linear cost atoms.
+ *  All pointers are HOST memory.  The plan owns the device buffers, pinned staging and a stream; the call
+ *  copies the inputs host->device, runs K1 (only when `recondense` != 0) -> K2 -> K3/K4, copies the results
+ *  device->host and returns after they have landed.
+ *    mats/strides : as hmpc_condense_f64 (ignored when recondense == 0)
+ *    x0 [B,nx], w [B,nomega*Nt], cost_v [B or 1, nv*Nt] (stride 0 = broadcast): linear cost on v~
+ *    lb_v, ub_v [nv*Nt] (+-inf allowed), is_bin_v [nv*Nt]: shared by the batch
+ *    outputs: v [B,nv*Nt], obj [B], status [B], stats [B,8]; timing_ms[4] = {h2d, kernels, d2h, total} (may be NULL)  */
+typedef struct hmpc_step_plan hmpc_step_plan;
+int hmpc_step_plan_create(const hmpc_dims* dims, const hmpc_milp_opts* opts, hmpc_step_plan** plan);
+int hmpc_step_plan_destroy(hmpc_step_plan* plan);
+int hmpc_mpc_step_host_f64(hmpc_step_plan* plan, int32_t recondense, const double* const mats[HMPC_NUM_MATS],
+                           const int64_t mat_stride_b[HMPC_NUM_MATS], const double* x0, const double* w,
+                           const double* cost_v, int64_t cost_v_stride_b, const double* lb_v, const double* ub_v,
+                           const uint8_t* is_bin_v, double* v, double* obj, int32_t* status, int32_t* stats,
+                           float* timing_ms);
+/* bytes moved per step by the call above: {host->device, device->host} */
+int hmpc_mpc_step_host_bytes(const hmpc_step_plan* plan, int32_t recondense, int64_t* h2d, int64_t* d2h);
+
+/* ---- measured FP64 FMA peak of this device (roofline denominator for the solver), TFLOP/s ---------- */
+int hmpc_fp64_peak_probe(double* tflops, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HMPC_H_ */

@@ -1,0 +1,29 @@
+"""oracle/ -- TEST INFRASTRUCTURE ONLY.  CPU (numpy) restatement of the reference's hybrid-MPC hot path.
+
+Who may import this package: ``tests/``, ``__graft_entry__.smoke()`` (as the checker) and ``bench.py``'s
+``cpu_baseline`` leg / ``--impl reference`` arm.  Nothing under ``pyhybridcontrol_b200/`` imports it; the
+product path fails loudly when the CUDA library is missing.
+
+What it restates (all citations relative to /root/reference):
+
+* ``oracle.mld``       -- MLD dimension rules + default blocks   (models/mld_model.py:149-168, 515-520, 910-928)
+* ``oracle.condense``  -- horizon condensing Phi/Gamma/L/H        (controllers/components/mld_evolution_matrices.py:237-332, 467-527)
+* ``oracle.assemble``  -- variable layout, cost atoms, constraints (controllers/components/variables.py:189-243,
+                          objective_atoms.py:308-363,453-496, controllers/controller_base.py:440-452,467-472)
+* ``oracle.lsim``      -- one-step MLD simulation + DEWH sim model (models/mld_model.py:647-699,
+                          examples/.../micro_grid_models.py:27-100, micro_grid_agents.py:389-408)
+* ``oracle.solve``     -- the MI(Q)P solve the reference hands to cvxpy -> Gurobi/CPLEX
+                          (controllers/controller_base.py:509-512).  Those solvers are third-party,
+                          unpinned and not installed; the offline backend is HiGHS 1.12.0 as vendored by
+                          scipy 1.18.1 (``scipy.optimize.milp``), plus exhaustive enumeration for <= ~18
+                          binaries and a Python B&B over HiGHS QPs for quadratic costs.
+
+Pinning status.  The reference has NO tests, golden vectors or fixtures for this path,
+so per the task rules:
+
+* condensing + lsim_k: **pinned** against outputs of the unmodified reference itself, run in the build
+  container under ``oracle/ref_shim.py``; vectors committed in ``tests/golden/`` together with the
+  generating script ``tests/golden/make_golden.py``.
+* problem assembly + MI(Q)P solve: **parity unpinned** -- cvxpy/Gurobi cannot run here; the restatement is
+  anchored on the reference's call sites (cited per function) and cross-checked HiGHS vs enumeration.
+"""

@@ -1,0 +1,155 @@
+"""TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
+
+The MI(Q)P solve the reference delegates to ``cvx.Problem.solve`` -> Gurobi / CPLEX
+(controllers/controller_base.py:509-512; models/mld_model.py:750,753).  Neither cvxpy nor those solvers is
+installed or pinned by the reference; the offline backend here is **HiGHS 1.12.0 vendored in scipy 1.18.1**:
+
+* ``solve_milp``      -- linear cost: ``scipy.optimize.milp`` with ``mip_rel_gap=0`` (what the reference example
+                         poses: all its atoms are Linear, SURVEY.md section 7 hard part 2).
+* ``solve_enumerate`` -- exhaustive enumeration over the binaries (<= ~18) with an LP/QP in the continuous
+                         variables; independent cross-check of both HiGHS and the GPU solver.
+* ``solve_miqp``      -- quadratic cost: depth-first branch-and-bound over HiGHS QP relaxations
+                         (private ``scipy.optimize._highspy._core``; HiGHS itself has no MIQP mode).
+
+Parity status: UNPINNED by the reference (it has no tests); HiGHS and enumeration are checked against each
+other in tests/test_oracle_solve.py.
+"""
+import itertools
+
+import numpy as np
+from scipy.optimize import Bounds, LinearConstraint, linprog, milp
+
+OPTIMAL, INFEASIBLE, LIMIT = 0, 1, 2
+
+
+def solve_milp(prob, mip_rel_gap=0.0, time_limit=None):
+    """-> (status, objective, v).  Requires prob.P is None."""
+    assert prob.P is None or not np.any(prob.P)
+    cons = [LinearConstraint(prob.H, -np.inf, prob.rhs)] if prob.H.shape[0] else []
+    opts = {"mip_rel_gap": mip_rel_gap, "presolve": True}
+    if time_limit:
+        opts["time_limit"] = time_limit
+    res = milp(prob.c, constraints=cons, integrality=prob.is_bin.astype(int),
+               bounds=Bounds(prob.lb, prob.ub), options=opts)
+    if res.status == 0:
+        v = np.array(res.x)
+        v[prob.is_bin] = np.round(v[prob.is_bin])
+        return OPTIMAL, float(res.fun + prob.c0), v
+    if res.status == 2:
+        return INFEASIBLE, np.inf, None
+    return LIMIT, (float(res.fun + prob.c0) if res.x is not None else np.inf), (None if res.x is None else np.array(res.x))
+
+
+def _continuous_subproblem(prob, bin_vals):
+    """Fix the binaries, solve the remaining LP/QP exactly."""
+    lb, ub = prob.lb.copy(), prob.ub.copy()
+    lb[prob.is_bin] = bin_vals
+    ub[prob.is_bin] = bin_vals
+    if prob.P is None or not np.any(prob.P):
+        res = linprog(prob.c, A_ub=prob.H if prob.H.shape[0] else None, b_ub=prob.rhs if prob.H.shape[0] else None,
+                      bounds=np.c_[lb, ub], method="highs")
+        if res.status != 0:
+            return np.inf, None
+        return float(res.fun + prob.c0), np.array(res.x)
+    st, obj, v = solve_qp(prob, lb, ub)
+    return (obj, v) if st == OPTIMAL else (np.inf, None)
+
+
+def solve_enumerate(prob, max_bin=18):
+    """Brute force over all binary assignments -> (status, objective, v, runner_up_objective)."""
+    nb = int(prob.is_bin.sum())
+    if nb > max_bin:
+        raise ValueError("too many binaries for enumeration: %d" % nb)
+    best, best_v, second = np.inf, None, np.inf
+    for bits in itertools.product((0.0, 1.0), repeat=nb):
+        obj, v = _continuous_subproblem(prob, np.array(bits))
+        if obj < best:
+            second, best, best_v = best, obj, v
+        elif obj < second:
+            second = obj
+    if best_v is None:
+        return INFEASIBLE, np.inf, None, np.inf
+    return OPTIMAL, best, best_v, second
+
+
+def solve_qp(prob, lb=None, ub=None):
+    """Convex QP relaxation through HiGHS' QP solver (private scipy binding)."""
+    from scipy.optimize._highspy import _core as hs
+    lb = prob.lb if lb is None else lb
+    ub = prob.ub if ub is None else ub
+    n, m = prob.n, prob.H.shape[0]
+    inf = hs.kHighsInf
+    h = hs._Highs()
+    h.setOptionValue("output_flag", False)
+    model = hs.HighsModel()
+    lp = model.lp_
+    lp.num_col_, lp.num_row_ = n, m
+    lp.col_cost_ = prob.c.astype(float)
+    lp.col_lower_ = np.where(np.isfinite(lb), lb, -inf)
+    lp.col_upper_ = np.where(np.isfinite(ub), ub, inf)
+    lp.row_lower_ = np.full(m, -inf)
+    lp.row_upper_ = prob.rhs.astype(float)
+    lp.a_matrix_.format_ = hs.MatrixFormat.kRowwise
+    nz = prob.H != 0
+    lp.a_matrix_.start_ = np.concatenate([[0], np.cumsum(nz.sum(axis=1))]).astype(np.int32)
+    lp.a_matrix_.index_ = np.nonzero(nz)[1].astype(np.int32)
+    lp.a_matrix_.value_ = prob.H[nz].astype(float)
+    if prob.P is not None and np.any(prob.P):
+        P = 0.5 * (prob.P + prob.P.T)
+        tri = np.triu(np.ones_like(P, dtype=bool)) & (P != 0)   # upper triangle, column-wise == lower row-wise
+        hess = model.hessian_
+        hess.dim_ = n
+        hess.format_ = hs.HessianFormat.kTriangular
+        # HiGHS wants the lower triangle column-wise; by symmetry use P^T's upper triangle row by row
+        Pl = np.tril(P)
+        nzl = Pl.T != 0  # rows of Pl.T are columns of Pl
+        hess.start_ = np.concatenate([[0], np.cumsum(nzl.sum(axis=1))]).astype(np.int32)
+        hess.index_ = np.nonzero(nzl)[1].astype(np.int32)
+        hess.value_ = Pl.T[nzl].astype(float)
+    h.passModel(model)
+    h.run()
+    ms = h.getModelStatus()
+    if ms == hs.HighsModelStatus.kOptimal:
+        sol = h.getSolution()
+        v = np.array(sol.col_value)
+        return OPTIMAL, prob.objective(v), v
+    if ms == hs.HighsModelStatus.kInfeasible:
+        return INFEASIBLE, np.inf, None
+    return LIMIT, np.inf, None
+
+
+def solve_miqp(prob, tol=1e-9, int_tol=1e-6, max_nodes=200000):
+    """Depth-first B&B on HiGHS QP relaxations -> (status, objective, v, nodes)."""
+    bin_idx = np.nonzero(prob.is_bin)[0]
+    best, best_v, nodes = np.inf, None, 0
+    stack = [(prob.lb.copy(), prob.ub.copy())]
+    while stack and nodes < max_nodes:
+        lb, ub = stack.pop()
+        nodes += 1
+        st, obj, v = solve_qp(prob, lb, ub)
+        if st != OPTIMAL or obj >= best - tol * max(1.0, abs(best)):
+            continue
+        frac = np.abs(v[bin_idx] - np.round(v[bin_idx]))
+        if frac.max(initial=0.0) <= int_tol:
+            vv = v.copy()
+            vv[bin_idx] = np.round(vv[bin_idx])
+            o2, v2 = _continuous_subproblem(prob, vv[bin_idx])
+            if o2 < best:
+                best, best_v = o2, v2
+            continue
+        j = bin_idx[int(np.argmax(frac))]
+        for val in ((0.0, 1.0) if v[j] >= 0.5 else (1.0, 0.0)):  # pushed last is explored first
+            l2, u2 = lb.copy(), ub.copy()
+            l2[j] = u2[j] = val
+            stack.append((l2, u2))
+    if best_v is None:
+        return (INFEASIBLE if not stack else LIMIT), np.inf, None, nodes
+    return (OPTIMAL if not stack else LIMIT), best, best_v, nodes
+
+
+def solve(prob, **kw):
+    """Dispatch on the cost type -> (status, objective, v)."""
+    if prob.P is None or not np.any(prob.P):
+        return solve_milp(prob, **kw)
+    st, obj, v, _ = solve_miqp(prob)
+    return st, obj, v

@@ -1,0 +1,389 @@
+"""ctypes binding of ``csrc/libhmpc.so`` (C ABI declared in ``include/hmpc.h``).
+
+This is the only door between the Python host code and the CUDA kernels.  PyTorch tensors are used purely as
+device buffers (``tensor.data_ptr()``) and for the current stream.  There is NO CPU fallback: if the library
+has not been built, importing this module raises ``ImportError``.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libhmpc.so")
+
+MAT_NAMES = ("A", "B1", "B2", "B3", "B4", "b5", "C", "D1", "D2", "D3", "D4", "d5",
+             "E", "F1", "F2", "F3", "F4", "f5", "G", "Psi")
+EVO_NAMES = ("Phi_x", "Gamma_v", "Gamma_omega", "Gamma_5", "L_x", "L_v", "L_omega", "L_5",
+             "H_x", "H_v", "H_omega", "H_5")
+EXPORTS = ("hmpc_version", "hmpc_last_cuda_error", "hmpc_device_info", "hmpc_condense_f64",
+           "hmpc_condense_bytes_per_agent", "hmpc_constraint_rhs_f64", "hmpc_predict_f64", "hmpc_linear_cost_f64",
+           "hmpc_milp_default_opts", "hmpc_milp_workspace_bytes", "hmpc_milp_solve_f64", "hmpc_lsim_step_f64",
+           "hmpc_dewh_sim_step_f64", "hmpc_dewh_control_model_f64", "hmpc_aggregate_power_f64",
+           "hmpc_step_plan_create", "hmpc_step_plan_destroy", "hmpc_mpc_step_host_f64", "hmpc_mpc_step_host_bytes",
+           "hmpc_fp64_peak_probe")
+
+SOLVE_STATUS = {0: "optimal", 1: "infeasible", 2: "node_limit", 3: "iter_limit", 4: "numeric", 5: "unsupported"}
+STAT_NAMES = ("nodes", "pivots", "cuts", "rows_added", "max_rows", "lp_solves", "purges", "reserved")
+
+
+class HmpcError(RuntimeError):
+    pass
+
+
+class Dims(C.Structure):
+    _fields_ = [(k, C.c_int32) for k in ("B", "Nt", "nx", "nu", "ndelta", "nz", "nmu", "nomega", "ny", "nc")]
+
+    @property
+    def nv(self):
+        return self.nu + self.ndelta + self.nz + self.nmu
+
+
+class MilpOpts(C.Structure):
+    _fields_ = [("mip_rel_gap", C.c_double), ("int_tol", C.c_double), ("feas_tol", C.c_double),
+                ("big_bound", C.c_double), ("max_nodes", C.c_int32), ("max_pivots", C.c_int32),
+                ("max_cuts", C.c_int32), ("max_rows", C.c_int32), ("cut_rounds_root", C.c_int32),
+                ("cut_rounds_node", C.c_int32), ("cuts_per_round", C.c_int32), ("reserved", C.c_int32)]
+
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError("libhmpc.so is not built (%s).  Run `python -c 'import __graft_entry__ as g; g.build()'` or "
+                      "`make -C pyhybridcontrol_b200/csrc`.  There is no CPU fallback." % LIB_PATH)
+
+_lib = C.CDLL(LIB_PATH)
+_P = C.c_void_p
+_MatArr = _P * len(MAT_NAMES)
+_StrideArr = C.c_int64 * len(MAT_NAMES)
+_EvoArr = _P * len(EVO_NAMES)
+
+_lib.hmpc_version.restype = C.c_int
+_lib.hmpc_last_cuda_error.restype = C.c_char_p
+_lib.hmpc_device_info.argtypes = [C.POINTER(C.c_int)] * 3 + [C.POINTER(C.c_size_t)]
+_lib.hmpc_condense_f64.argtypes = [C.POINTER(Dims), _MatArr, _StrideArr, _EvoArr, _P]
+_lib.hmpc_condense_bytes_per_agent.argtypes = [C.POINTER(Dims)]
+_lib.hmpc_condense_bytes_per_agent.restype = C.c_int64
+_lib.hmpc_constraint_rhs_f64.argtypes = [C.POINTER(Dims), C.c_int32, _P, _P, _P, _P, _P, C.c_int32, _P, _P]
+_lib.hmpc_predict_f64.argtypes = [C.c_int32] * 5 + [_P] * 9
+_lib.hmpc_linear_cost_f64.argtypes = [C.c_int32] * 4 + [_P, C.c_int64] + [_P] * 9
+_lib.hmpc_milp_default_opts.argtypes = [C.POINTER(MilpOpts)]
+_lib.hmpc_milp_default_opts.restype = None
+_lib.hmpc_milp_workspace_bytes.argtypes = [C.c_int32] * 3 + [C.POINTER(MilpOpts), C.POINTER(C.c_size_t)]
+_lib.hmpc_milp_solve_f64.argtypes = [C.c_int32] * 3 + [_P, C.c_int64, _P, C.c_int64, _P, _P, _P, C.c_int64, _P,
+                                                       C.POINTER(MilpOpts), _P, C.c_size_t, _P, _P, _P, _P, _P]
+_lib.hmpc_lsim_step_f64.argtypes = [C.POINTER(Dims), _MatArr, _StrideArr] + [_P] * 5 + [C.c_double] + [_P] * 4
+_lib.hmpc_dewh_sim_step_f64.argtypes = [C.c_int32] + [_P] * 8
+_lib.hmpc_dewh_control_model_f64.argtypes = [C.c_int32, _P, _P, _P]
+_lib.hmpc_aggregate_power_f64.argtypes = [C.c_int32, C.c_int32, _P, C.c_int64, C.c_int32, _P, _P, _P, _P]
+_lib.hmpc_step_plan_create.argtypes = [C.POINTER(Dims), C.POINTER(MilpOpts), C.POINTER(_P)]
+_lib.hmpc_step_plan_destroy.argtypes = [_P]
+_lib.hmpc_mpc_step_host_f64.argtypes = [_P, C.c_int32, _MatArr, _StrideArr, _P, _P, _P, C.c_int64, _P, _P, _P,
+                                        _P, _P, _P, _P, _P]
+_lib.hmpc_mpc_step_host_bytes.argtypes = [_P, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+_lib.hmpc_fp64_peak_probe.argtypes = [C.POINTER(C.c_double), _P]
+
+# number of kernel launches issued through this binding (bench.py reports it as gpu_launches)
+launch_count = 0
+
+
+def lib():
+    return _lib
+
+
+def _check(rc, what):
+    if rc != 0:
+        msg = _lib.hmpc_last_cuda_error().decode() if rc == -2 else ""
+        raise HmpcError("%s failed with status %d %s" % (what, rc, msg))
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), "device buffers must be contiguous CUDA tensors"
+    return C.c_void_p(t.data_ptr())
+
+
+def default_opts(**kw):
+    o = MilpOpts()
+    _lib.hmpc_milp_default_opts(C.byref(o))
+    for k, v in kw.items():
+        setattr(o, k, v)
+    return o
+
+
+def make_dims(B, Nt, nx=0, nu=0, ndelta=0, nz=0, nmu=0, nomega=0, ny=0, nc=0):
+    return Dims(B, Nt, nx, nu, ndelta, nz, nmu, nomega, ny, nc)
+
+
+def _mat_shape(d, name):
+    rows = d.nx if name in MAT_NAMES[0:6] else (d.ny if name in MAT_NAMES[6:12] else d.nc)
+    cols = {"A": d.nx, "C": d.nx, "E": d.nx, "B1": d.nu, "D1": d.nu, "F1": d.nu, "B2": d.ndelta, "D2": d.ndelta,
+            "F2": d.ndelta, "B3": d.nz, "D3": d.nz, "F3": d.nz, "B4": d.nomega, "D4": d.nomega, "F4": d.nomega,
+            "G": d.ny, "Psi": d.nmu}.get(name, 1)
+    return rows, cols
+
+
+def _pack_mats(d, mats):
+    arr, strides, keep = _MatArr(), _StrideArr(), []
+    for i, name in enumerate(MAT_NAMES):
+        t = mats.get(name)
+        r, c = _mat_shape(d, name)
+        if t is None or r * c == 0:
+            arr[i], strides[i] = None, 0
+            continue
+        if t.dim() == 2:
+            t = t.unsqueeze(0)
+        if tuple(t.shape[1:]) != (r, c) or t.shape[0] not in (1, d.B) or t.dtype != torch.float64:
+            raise ValueError("matrix %s: expected [%d or 1, %d, %d] float64, got %s %s" % (name, d.B, r, c,
+                                                                                      tuple(t.shape), t.dtype))
+        t = t.contiguous()
+        keep.append(t)
+        arr[i] = t.data_ptr()
+        strides[i] = 0 if t.shape[0] == 1 and d.B != 1 else r * c
+    return arr, strides, keep
+
+
+def evo_shapes(d):
+    nvt, nwt = d.nv * d.Nt, d.nomega * d.Nt
+    out = {}
+    for grp, rows in (("Phi_x Gamma_v Gamma_omega Gamma_5", d.nx), ("L_x L_v L_omega L_5", d.ny),
+                      ("H_x H_v H_omega H_5", d.nc)):
+        for name, cols in zip(grp.split(), (d.nx, nvt, nwt, 1)):
+            out[name] = (d.B, rows * d.Nt, cols)
+    return out
+
+
+def condense(d, mats, want=EVO_NAMES, out=None):
+    """K1.  mats: name -> CUDA float64 tensor [B|1, r, c].  Returns name -> tensor [B, rows*Nt, cols]."""
+    global launch_count
+    arr, strides, keep = _pack_mats(d, mats)
+    dev = next(iter(keep)).device if keep else torch.device("cuda")
+    shapes = evo_shapes(d)
+    res = {} if out is None else out
+    evo = _EvoArr()
+    for i, name in enumerate(EVO_NAMES):
+        if name in want:
+            if name not in res:
+                res[name] = torch.empty(shapes[name], dtype=torch.float64, device=dev)
+            evo[i] = res[name].data_ptr() if res[name].numel() else None
+        else:
+            evo[i] = None
+    _check(_lib.hmpc_condense_f64(C.byref(d), arr, strides, evo, _stream()), "hmpc_condense_f64")
+    launch_count += 1
+    return res
+
+
+def condense_bytes_per_agent(d):
+    return int(_lib.hmpc_condense_bytes_per_agent(C.byref(d)))
+
+
+def constraint_rhs(d, evo, x0, w, scenarios=None, rows=None, out=None):
+    """K2.  w: [B, nomega*Nt]; scenarios: [B, nomega*Nt, S] (robust row-min form)."""
+    global launch_count
+    rows = d.nc * d.Nt if rows is None else rows
+    S = 0 if scenarios is None else scenarios.shape[2]
+    ww = w if scenarios is None else scenarios
+    if out is None:
+        out = torch.empty((d.B, rows), dtype=torch.float64, device=evo["H_5"].device)
+    _check(_lib.hmpc_constraint_rhs_f64(C.byref(d), rows, _ptr(evo["H_x"]) if d.nx else None,
+                                        _ptr(evo["H_omega"]) if d.nomega else None, _ptr(evo["H_5"]),
+                                        _ptr(x0) if d.nx else None, _ptr(ww) if d.nomega else None, S, _ptr(out),
+                                        _stream()), "hmpc_constraint_rhs_f64")
+    launch_count += 1
+    return out
+
+
+def predict(M_x, M_v, M_w, M_5, x0, v, w):
+    """Affine prediction rows: out[b] = M_x x0 + M_v v + M_w w + M_5."""
+    global launch_count
+    B, R = M_5.shape[0], M_5.shape[1]
+    nx = M_x.shape[2] if M_x is not None and M_x.numel() else 0
+    nvt = M_v.shape[2] if M_v is not None else 0
+    nwt = M_w.shape[2] if M_w is not None and M_w.numel() else 0
+    out = torch.empty((B, R), dtype=torch.float64, device=M_5.device)
+    _check(_lib.hmpc_predict_f64(B, R, nx, nvt, nwt, _ptr(M_x) if nx else None, _ptr(M_v), _ptr(M_w) if nwt else None,
+                                 _ptr(M_5), _ptr(x0) if nx else None, _ptr(v), _ptr(w) if nwt else None, _ptr(out),
+                                 _stream()), "hmpc_predict_f64")
+    launch_count += 1
+    return out
+
+
+def linear_cost(B, nvt, w_v=None, w_x=None, Gamma_v=None, xc=None, w_y=None, L_v=None, yc=None):
+    global launch_count
+    ref = next(t for t in (w_v, w_x, w_y) if t is not None)
+    c = torch.empty((B, nvt), dtype=torch.float64, device=ref.device)
+    c0 = torch.zeros((B,), dtype=torch.float64, device=ref.device)
+    stride = 0
+    if w_v is not None:
+        w_v = w_v.reshape(-1, nvt)
+        stride = nvt if w_v.shape[0] == B and B > 1 else (0 if w_v.shape[0] == 1 and B > 1 else nvt)
+    nxt = w_x.shape[1] if w_x is not None else 0
+    nyt = w_y.shape[1] if w_y is not None else 0
+    _check(_lib.hmpc_linear_cost_f64(B, nvt, nxt, nyt, _ptr(w_v), stride, _ptr(w_x), _ptr(Gamma_v), _ptr(xc),
+                                     _ptr(w_y), _ptr(L_v), _ptr(yc), _ptr(c), _ptr(c0), _stream()),
+           "hmpc_linear_cost_f64")
+    launch_count += 1
+    return c, c0
+
+
+def milp_solve(c, H, rhs, lb, ub, is_bin, opts=None):
+    """K3/K4.  c [B|1,n], H [B|1,m,n], rhs [B,m], lb/ub [B|1,n] (or [n]), is_bin uint8 [n]."""
+    global launch_count
+    B, m = rhs.shape
+    n = c.shape[-1]
+    c2 = c.reshape(-1, n)
+    H3 = H.reshape(-1, m, n) if m else H
+    lb2, ub2 = lb.reshape(-1, n), ub.reshape(-1, n)
+    dev = rhs.device
+    v = torch.empty((B, n), dtype=torch.float64, device=dev)
+    obj = torch.empty((B,), dtype=torch.float64, device=dev)
+    status = torch.empty((B,), dtype=torch.int32, device=dev)
+    stats = torch.empty((B, 8), dtype=torch.int32, device=dev)
+    o = opts if opts is not None else default_opts()
+    _check(_lib.hmpc_milp_solve_f64(B, n, m, _ptr(c2), n if c2.shape[0] == B and B > 1 or B == 1 else 0,
+                                    _ptr(H3) if m else None, (m * n) if (m and H3.shape[0] == B) else 0,
+                                    _ptr(rhs) if m else None, _ptr(lb2), _ptr(ub2),
+                                    n if lb2.shape[0] == B and B > 1 else 0, _ptr(is_bin), C.byref(o), None, 0,
+                                    _ptr(v), _ptr(obj), _ptr(status), _ptr(stats), _stream()), "hmpc_milp_solve_f64")
+    launch_count += 1
+    return v, obj, status, stats
+
+
+def lsim_step(d, mats, x, u, delta, z, w, cons_tol=1e-6):
+    """K5 generic MLD step -> (x1 [B,nx], y [B,ny], cons uint8 [B,nc])."""
+    global launch_count
+    arr, strides, keep = _pack_mats(d, mats)
+    dev = next(t for t in (x, u, delta, z, w) if t is not None).device
+    x1 = torch.empty((d.B, d.nx), dtype=torch.float64, device=dev)
+    y = torch.empty((d.B, d.ny), dtype=torch.float64, device=dev)
+    cons = torch.empty((d.B, d.nc), dtype=torch.uint8, device=dev)
+    _check(_lib.hmpc_lsim_step_f64(C.byref(d), arr, strides, _ptr(x) if d.nx else None, _ptr(u) if d.nu else None,
+                                   _ptr(delta) if d.ndelta else None, _ptr(z) if d.nz else None,
+                                   _ptr(w) if d.nomega else None, cons_tol, _ptr(x1) if d.nx else None,
+                                   _ptr(y) if d.ny else None, _ptr(cons) if d.nc else None, _stream()),
+           "hmpc_lsim_step_f64")
+    launch_count += (1 if d.nx + d.ny else 0) + (1 if d.nc else 0)
+    return x1, y, cons
+
+
+DEWH_PARAM_ORDER = ("C_w", "A_h", "U_h", "m_h", "T_w", "T_inf", "P_h_Nom", "T_h_min", "T_h_max", "T_h_Nom", "ts")
+
+
+def pack_dewh_params(param_list):
+    """list of param dicts -> float64 numpy [B,12] in the order hmpc_dewh_* expects."""
+    out = np.zeros((len(param_list), 12))
+    for b, p in enumerate(param_list):
+        out[b, :11] = [p[k] for k in DEWH_PARAM_ORDER]
+    return out
+
+
+def dewh_sim_step(params, T, u, D_h, want_model=False):
+    global launch_count
+    B = T.shape[0]
+    T1 = torch.empty_like(T)
+    model = torch.empty((B, 4), dtype=torch.float64, device=T.device) if want_model else None
+    cons = torch.empty((B, 2), dtype=torch.uint8, device=T.device)
+    _check(_lib.hmpc_dewh_sim_step_f64(B, _ptr(params), _ptr(T), _ptr(u), _ptr(D_h), _ptr(T1), _ptr(model),
+                                       _ptr(cons), _stream()), "hmpc_dewh_sim_step_f64")
+    launch_count += 1
+    return T1, model, cons
+
+
+def dewh_control_model(params):
+    global launch_count
+    B = params.shape[0]
+    model = torch.empty((B, 4), dtype=torch.float64, device=params.device)
+    _check(_lib.hmpc_dewh_control_model_f64(B, _ptr(params), _ptr(model), _stream()), "hmpc_dewh_control_model_f64")
+    launch_count += 1
+    return model
+
+
+def aggregate_power(u, P_nom=None):
+    """K6 local part: u [B, Nt] (any strides) -> P_agg [Nt] = sum_b P_nom[b] u[b,k]."""
+    global launch_count
+    B, Nt = u.shape
+    chunks = max(1, (B + 255) // 256)
+    partial = torch.empty((chunks, Nt), dtype=torch.float64, device=u.device)
+    out = torch.empty((Nt,), dtype=torch.float64, device=u.device)
+    _check(_lib.hmpc_aggregate_power_f64(B, Nt, C.c_void_p(u.data_ptr()), u.stride(0), u.stride(1), _ptr(P_nom),
+                                         _ptr(partial), _ptr(out), _stream()), "hmpc_aggregate_power_f64")
+    launch_count += 2
+    return out
+
+
+def fp64_peak_tflops():
+    v = C.c_double(0.0)
+    _check(_lib.hmpc_fp64_peak_probe(C.byref(v), _stream()), "hmpc_fp64_peak_probe")
+    return v.value
+
+
+def device_info():
+    sm, ma, mi, sh = C.c_int(), C.c_int(), C.c_int(), C.c_size_t()
+    rc = _lib.hmpc_device_info(C.byref(sm), C.byref(ma), C.byref(mi), C.byref(sh))
+    return dict(rc=rc, sm_count=sm.value, cc=(ma.value, mi.value), smem_optin=sh.value)
+
+
+class StepPlan(object):
+    """Host-buffer front door (hmpc_mpc_step_host_f64): numpy in, numpy out, copies inside the call."""
+
+    def __init__(self, d, opts=None):
+        self.d = d
+        self.opts = opts if opts is not None else default_opts()
+        self._h = _P()
+        _check(_lib.hmpc_step_plan_create(C.byref(d), C.byref(self.opts), C.byref(self._h)), "hmpc_step_plan_create")
+        nvt = d.nv * d.Nt
+        self.v = np.empty((d.B, nvt))
+        self.obj = np.empty((d.B,))
+        self.status = np.empty((d.B,), dtype=np.int32)
+        self.stats = np.empty((d.B, 8), dtype=np.int32)
+        self.timing = (C.c_float * 4)()
+
+    def bytes_per_step(self, recondense):
+        a, b = C.c_int64(), C.c_int64()
+        _check(_lib.hmpc_mpc_step_host_bytes(self._h, int(recondense), C.byref(a), C.byref(b)), "bytes")
+        return a.value, b.value
+
+    def step(self, mats, x0, w, cost_v, lb_v, ub_v, is_bin_v, recondense=True):
+        global launch_count
+        d = self.d
+        arr, strides, keep = _MatArr(), _StrideArr(), []
+        for i, name in enumerate(MAT_NAMES):
+            a = None if mats is None else mats.get(name)
+            r, c = _mat_shape(d, name)
+            if a is None or r * c == 0:
+                arr[i], strides[i] = None, 0
+                continue
+            a = np.ascontiguousarray(a, dtype=np.float64).reshape(-1, r, c)
+            keep.append(a)
+            arr[i] = a.ctypes.data
+            strides[i] = 0 if a.shape[0] == 1 and d.B != 1 else r * c
+        nvt = d.nv * d.Nt
+        x0 = np.ascontiguousarray(x0, dtype=np.float64)
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        cost_v = np.ascontiguousarray(cost_v, dtype=np.float64).reshape(-1, nvt)
+        lb_v = np.ascontiguousarray(lb_v, dtype=np.float64)
+        ub_v = np.ascontiguousarray(ub_v, dtype=np.float64)
+        is_bin_v = np.ascontiguousarray(is_bin_v, dtype=np.uint8)
+        cs = nvt if cost_v.shape[0] == d.B and d.B > 1 else (0 if d.B > 1 else nvt)
+        _check(_lib.hmpc_mpc_step_host_f64(self._h, int(recondense), arr, strides, x0.ctypes.data, w.ctypes.data,
+                                           cost_v.ctypes.data, cs, lb_v.ctypes.data, ub_v.ctypes.data,
+                                           is_bin_v.ctypes.data, self.v.ctypes.data, self.obj.ctypes.data,
+                                           self.status.ctypes.data, self.stats.ctypes.data, self.timing),
+               "hmpc_mpc_step_host_f64")
+        launch_count += 3 if recondense else 2
+        return self.v, self.obj, self.status, self.stats, tuple(self.timing)
+
+    def close(self):
+        if self._h:
+            _lib.hmpc_step_plan_destroy(self._h)
+            self._h = _P()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,314 @@
+// condense.cu -- K1: batched FP64 horizon condensing of an MLD model into the stacked prediction and
+// constraint matrices.  Replaces MldEvoMatrices.gen_mld_evo_matrices
+// (reference: controllers/components/mld_evolution_matrices.py:108-134).
+//
+// Every one of the 12 outputs is block lower-triangular Toeplitz over the horizon: block (i, j) of the
+// v / omega matrices only depends on the lag i-j-1, the x and "5" columns only on i.  A CTA therefore
+//   1. stages the agent's ~20 small matrices in shared memory,
+//   2. runs the horizon recurrence once (A^k by running products, like the reference :253-272; then the
+//      lag blocks A^k [B1 B2 B3 0], A^k B4, the running sum of A^k b5 and their images under C and E+G C),
+//   3. streams its slice of the dense outputs to HBM with fully coalesced stores straight out of the
+//      shared-memory lag table.
+// Step 3 is what the kernel costs: 8 (nx+ny+nc) Nt (nx + 1 + (nv+nomega) Nt) bytes per agent of pure
+// writes (310,464 B for a DEWH at N_p = 48), so the roofline is the HBM write bandwidth.  Each agent is
+// split over `gridDim.y` CTAs (row slices of every output) so that a 100-agent batch still fills 148 SMs;
+// the recurrence is recomputed per slice (a few kFLOP, negligible against the stores).
+#include "common.cuh"
+
+namespace hmpc {
+
+struct CondenseArgs {
+    hmpc_dims d;
+    const double* mats[HMPC_NUM_MATS];
+    int64_t stride[HMPC_NUM_MATS];
+    double* out[HMPC_NUM_EVO];
+};
+
+// shared-memory plan (doubles)
+struct CondensePlan {
+    int nv, nw;
+    int o_A, o_Bv, o_B4, o_b5, o_C, o_Dv, o_D4, o_d5, o_E, o_Fv, o_F4, o_f5, o_G;
+    int o_Ap;                 // [Nt][nx*nx]
+    int o_Gv, o_Gw, o_c5, o_g5;  // state lag tables  [Nt][nx*nv], [Nt][nx*nw], [Nt][nx], [Nt][nx]
+    int o_LGv, o_LGw, o_L5, o_LX;   // output tables [Nt][ny*nv], [Nt][ny*nw], [Nt][ny], [Nt][ny*nx]
+    int o_HGv, o_HGw, o_H5, o_HX;   // constraint tables [Nt][nc*nv], ...
+    int o_LDv, o_LDw, o_HDv, o_HDw; // diagonal blocks
+    int total;
+};
+
+__host__ __device__ inline CondensePlan make_plan(const hmpc_dims& d) {
+    CondensePlan p;
+    p.nv = d.nu + d.ndelta + d.nz + d.nmu;
+    p.nw = d.nomega;
+    int o = 0;
+    auto take = [&](int n) { int r = o; o += n; return r; };
+    p.o_A = take(d.nx * d.nx); p.o_Bv = take(d.nx * p.nv); p.o_B4 = take(d.nx * p.nw); p.o_b5 = take(d.nx);
+    p.o_C = take(d.ny * d.nx); p.o_Dv = take(d.ny * p.nv); p.o_D4 = take(d.ny * p.nw); p.o_d5 = take(d.ny);
+    p.o_E = take(d.nc * d.nx); p.o_Fv = take(d.nc * p.nv); p.o_F4 = take(d.nc * p.nw); p.o_f5 = take(d.nc);
+    p.o_G = take(d.nc * d.ny);
+    p.o_Ap = take(d.Nt * d.nx * d.nx);
+    p.o_Gv = take(d.Nt * d.nx * p.nv); p.o_Gw = take(d.Nt * d.nx * p.nw); p.o_c5 = take(d.Nt * d.nx);
+    p.o_g5 = take(d.Nt * d.nx);
+    p.o_LGv = take(d.Nt * d.ny * p.nv); p.o_LGw = take(d.Nt * d.ny * p.nw); p.o_L5 = take(d.Nt * d.ny);
+    p.o_LX = take(d.Nt * d.ny * d.nx);
+    p.o_HGv = take(d.Nt * d.nc * p.nv); p.o_HGw = take(d.Nt * d.nc * p.nw); p.o_H5 = take(d.Nt * d.nc);
+    p.o_HX = take(d.Nt * d.nc * d.nx);
+    p.o_LDv = take(d.ny * p.nv); p.o_LDw = take(d.ny * p.nw);
+    p.o_HDv = take(d.nc * p.nv); p.o_HDw = take(d.nc * p.nw);
+    p.total = o;
+    return p;
+}
+
+// dst[r][c0 + c] = src_b[r][c]  (src may be null -> zeros)
+__device__ inline void stage(double* dst, int ld, int c0, const double* src, int64_t stride, int b, int rows,
+                             int cols) {
+    for (int e = threadIdx.x; e < rows * cols; e += blockDim.x) {
+        int r = e / cols, c = e - r * cols;
+        dst[r * ld + c0 + c] = src ? src[(int64_t)b * stride + e] : 0.0;
+    }
+}
+
+// C[M x N] = A[M x K] * B[K x N]  (+ optional addend D[M x N]), one thread per element, K ascending
+__device__ inline void small_mm(double* C, const double* A, const double* B, int M, int K, int N) {
+    for (int e = threadIdx.x; e < M * N; e += blockDim.x) {
+        int r = e / N, c = e - r * N;
+        double acc = 0.0;
+        for (int k = 0; k < K; ++k) acc += A[r * K + k] * B[k * N + c];
+        C[e] = acc;
+    }
+}
+
+// Writes rows [row_lo, row_hi) of a dense block-Toeplitz output:
+//   block(i, j) = lag[i-j-1] (i > j), diag (i == j, may be null -> 0), 0 (i < j); value is multiplied by sgn.
+// rb x cb is the block shape, ncol = cb * Nt.  Thread <-> column so that a warp stores 256 contiguous bytes.
+__device__ inline void write_toeplitz(double* __restrict__ out, const double* __restrict__ lag,
+                                      const double* __restrict__ diag, int rb, int cb, int Nt, double sgn,
+                                      int row_lo, int row_hi) {
+    const int ncol = cb * Nt;
+    if (ncol == 0 || rb == 0) return;
+    for (int col = threadIdx.x; col < ncol; col += blockDim.x) {
+        const int j = col / cb, cj = col - j * cb;
+        int i = row_lo / rb, ri = row_lo - i * rb;
+        double* p = out + (int64_t)row_lo * ncol + col;
+        for (int row = row_lo; row < row_hi; ++row) {
+            double v = 0.0;
+            if (i > j) v = sgn * lag[((i - j - 1) * rb + ri) * cb + cj];
+            else if (i == j && diag) v = sgn * diag[ri * cb + cj];
+            *p = v;
+            p += ncol;
+            if (++ri == rb) { ri = 0; ++i; }
+        }
+    }
+}
+
+// column-type outputs: out[row][c] = tab[row*cb + c] (already stacked over the horizon)
+__device__ inline void write_stack(double* __restrict__ out, const double* __restrict__ tab, int cb, int row_lo,
+                                   int row_hi) {
+    for (int e = row_lo * cb + threadIdx.x; e < row_hi * cb; e += blockDim.x) out[e] = tab[e];
+}
+
+__global__ void __launch_bounds__(256) condense_kernel(const CondenseArgs args) {
+    extern __shared__ double sm[];
+    const hmpc_dims d = args.d;
+    const CondensePlan p = make_plan(d);
+    const int b = blockIdx.x;
+    const int nx = d.nx, ny = d.ny, nc = d.nc, nv = p.nv, nw = p.nw, Nt = d.Nt;
+
+    // ---- 1. stage the agent's matrices (v-columns = [u | delta | z | mu])
+    stage(sm + p.o_A, nx, 0, args.mats[HMPC_A], args.stride[HMPC_A], b, nx, nx);
+    stage(sm + p.o_Bv, nv, 0, args.mats[HMPC_B1], args.stride[HMPC_B1], b, nx, d.nu);
+    stage(sm + p.o_Bv, nv, d.nu, args.mats[HMPC_B2], args.stride[HMPC_B2], b, nx, d.ndelta);
+    stage(sm + p.o_Bv, nv, d.nu + d.ndelta, args.mats[HMPC_B3], args.stride[HMPC_B3], b, nx, d.nz);
+    stage(sm + p.o_Bv, nv, d.nu + d.ndelta + d.nz, nullptr, 0, b, nx, d.nmu);
+    stage(sm + p.o_B4, nw, 0, args.mats[HMPC_B4], args.stride[HMPC_B4], b, nx, nw);
+    stage(sm + p.o_b5, 1, 0, args.mats[HMPC_b5], args.stride[HMPC_b5], b, nx, 1);
+    stage(sm + p.o_C, nx, 0, args.mats[HMPC_C], args.stride[HMPC_C], b, ny, nx);
+    stage(sm + p.o_Dv, nv, 0, args.mats[HMPC_D1], args.stride[HMPC_D1], b, ny, d.nu);
+    stage(sm + p.o_Dv, nv, d.nu, args.mats[HMPC_D2], args.stride[HMPC_D2], b, ny, d.ndelta);
+    stage(sm + p.o_Dv, nv, d.nu + d.ndelta, args.mats[HMPC_D3], args.stride[HMPC_D3], b, ny, d.nz);
+    stage(sm + p.o_Dv, nv, d.nu + d.ndelta + d.nz, nullptr, 0, b, ny, d.nmu);
+    stage(sm + p.o_D4, nw, 0, args.mats[HMPC_D4], args.stride[HMPC_D4], b, ny, nw);
+    stage(sm + p.o_d5, 1, 0, args.mats[HMPC_d5], args.stride[HMPC_d5], b, ny, 1);
+    stage(sm + p.o_E, nx, 0, args.mats[HMPC_E], args.stride[HMPC_E], b, nc, nx);
+    stage(sm + p.o_Fv, nv, 0, args.mats[HMPC_F1], args.stride[HMPC_F1], b, nc, d.nu);
+    stage(sm + p.o_Fv, nv, d.nu, args.mats[HMPC_F2], args.stride[HMPC_F2], b, nc, d.ndelta);
+    stage(sm + p.o_Fv, nv, d.nu + d.ndelta, args.mats[HMPC_F3], args.stride[HMPC_F3], b, nc, d.nz);
+    stage(sm + p.o_Fv, nv, d.nu + d.ndelta + d.nz, args.mats[HMPC_Psi], args.stride[HMPC_Psi], b, nc, d.nmu);
+    stage(sm + p.o_F4, nw, 0, args.mats[HMPC_F4], args.stride[HMPC_F4], b, nc, nw);
+    stage(sm + p.o_f5, 1, 0, args.mats[HMPC_f5], args.stride[HMPC_f5], b, nc, 1);
+    stage(sm + p.o_G, ny, 0, args.mats[HMPC_G], args.stride[HMPC_G], b, nc, ny);
+    __syncthreads();
+
+    // ---- 2a. A^k by running products  Ap[k] = Ap[k-1] A   (reference :264-272)
+    double* Ap = sm + p.o_Ap;
+    for (int e = threadIdx.x; e < nx * nx; e += blockDim.x) Ap[e] = (e / nx == e % nx) ? 1.0 : 0.0;
+    __syncthreads();
+    for (int k = 1; k < Nt; ++k) {
+        small_mm(Ap + k * nx * nx, Ap + (k - 1) * nx * nx, sm + p.o_A, nx, nx, nx);
+        __syncthreads();
+    }
+    // ---- 2b. state lag tables: Gv[k] = A^k Bv, Gw[k] = A^k B4, g5[k] = A^k b5 (all k in parallel)
+    double* Gv = sm + p.o_Gv; double* Gw = sm + p.o_Gw; double* c5 = sm + p.o_c5;
+    double* g5 = sm + p.o_g5;
+    for (int e = threadIdx.x; e < Nt * nx * nv; e += blockDim.x) {
+        int k = e / (nx * nv), rc = e - k * nx * nv, r = rc / nv, c = rc - r * nv;
+        double acc = 0.0;
+        for (int l = 0; l < nx; ++l) acc += Ap[(k * nx + r) * nx + l] * sm[p.o_Bv + l * nv + c];
+        Gv[e] = acc;
+    }
+    for (int e = threadIdx.x; e < Nt * nx * nw; e += blockDim.x) {
+        int k = e / (nx * nw), rc = e - k * nx * nw, r = rc / nw, c = rc - r * nw;
+        double acc = 0.0;
+        for (int l = 0; l < nx; ++l) acc += Ap[(k * nx + r) * nx + l] * sm[p.o_B4 + l * nw + c];
+        Gw[e] = acc;
+    }
+    for (int e = threadIdx.x; e < Nt * nx; e += blockDim.x) {
+        int k = e / nx, r = e - k * nx;
+        double acc = 0.0;
+        for (int l = 0; l < nx; ++l) acc += Ap[(k * nx + r) * nx + l] * sm[p.o_b5 + l];
+        g5[e] = acc;
+    }
+    __syncthreads();
+    // Gamma_5 row i = sum_{j<i} A^{i-1-j} b5, summed over j ascending like `toeplitz @ ones` (:331-332)
+    for (int e = threadIdx.x; e < Nt * nx; e += blockDim.x) {
+        int i = e / nx, r = e - i * nx;
+        double acc = 0.0;
+        for (int j = 0; j < i; ++j) acc += g5[(i - 1 - j) * nx + r];
+        c5[e] = acc;
+    }
+    __syncthreads();
+    // ---- 2c. images under C (outputs) and E, G (constraints); same association as the reference:
+    //          L = C~ Gamma + D~ ;  H = (E~ Gamma + F~) + G~ L
+    double* LGv = sm + p.o_LGv; double* LGw = sm + p.o_LGw; double* L5 = sm + p.o_L5; double* LX = sm + p.o_LX;
+    const double* Cm = sm + p.o_C; const double* Em = sm + p.o_E; const double* Gm = sm + p.o_G;
+    for (int e = threadIdx.x; e < Nt * ny * nv; e += blockDim.x) {
+        int k = e / (ny * nv), rc = e - k * ny * nv, r = rc / nv, c = rc - r * nv;
+        double acc = 0.0;
+        for (int l = 0; l < nx; ++l) acc += Cm[r * nx + l] * Gv[(k * nx + l) * nv + c];
+        LGv[e] = acc;
+    }
+    for (int e = threadIdx.x; e < Nt * ny * nw; e += blockDim.x) {
+        int k = e / (ny * nw), rc = e - k * ny * nw, r = rc / nw, c = rc - r * nw;
+        double acc = 0.0;
+        for (int l = 0; l < nx; ++l) acc += Cm[r * nx + l] * Gw[(k * nx + l) * nw + c];
+        LGw[e] = acc;
+    }
+    for (int e = threadIdx.x; e < Nt * ny; e += blockDim.x) {
+        int i = e / ny, r = e - i * ny;
+        double acc = 0.0;
+        for (int l = 0; l < nx; ++l) acc += Cm[r * nx + l] * c5[i * nx + l];
+        L5[e] = acc + sm[p.o_d5 + r];
+    }
+    for (int e = threadIdx.x; e < Nt * ny * nx; e += blockDim.x) {
+        int i = e / (ny * nx), rc = e - i * ny * nx, r = rc / nx, c = rc - r * nx;
+        double acc = 0.0;
+        for (int l = 0; l < nx; ++l) acc += Cm[r * nx + l] * Ap[(i * nx + l) * nx + c];
+        LX[e] = acc;
+    }
+    for (int e = threadIdx.x; e < ny * nv; e += blockDim.x) sm[p.o_LDv + e] = sm[p.o_Dv + e];
+    for (int e = threadIdx.x; e < ny * nw; e += blockDim.x) sm[p.o_LDw + e] = sm[p.o_D4 + e];
+    __syncthreads();
+    double* HGv = sm + p.o_HGv; double* HGw = sm + p.o_HGw; double* HX = sm + p.o_HX;
+    for (int e = threadIdx.x; e < Nt * nc * nv; e += blockDim.x) {
+        int k = e / (nc * nv), rc = e - k * nc * nv, r = rc / nv, c = rc - r * nv;
+        double eg = 0.0, gl = 0.0;
+        for (int l = 0; l < nx; ++l) eg += Em[r * nx + l] * Gv[(k * nx + l) * nv + c];
+        for (int l = 0; l < ny; ++l) gl += Gm[r * ny + l] * LGv[(k * ny + l) * nv + c];
+        HGv[e] = eg + gl;
+    }
+    for (int e = threadIdx.x; e < Nt * nc * nw; e += blockDim.x) {
+        int k = e / (nc * nw), rc = e - k * nc * nw, r = rc / nw, c = rc - r * nw;
+        double eg = 0.0, gl = 0.0;
+        for (int l = 0; l < nx; ++l) eg += Em[r * nx + l] * Gw[(k * nx + l) * nw + c];
+        for (int l = 0; l < ny; ++l) gl += Gm[r * ny + l] * LGw[(k * ny + l) * nw + c];
+        HGw[e] = eg + gl;   // sign applied on store: H_omega = -(...)
+    }
+    for (int e = threadIdx.x; e < Nt * nc * nx; e += blockDim.x) {
+        int i = e / (nc * nx), rc = e - i * nc * nx, r = rc / nx, c = rc - r * nx;
+        double eg = 0.0, gl = 0.0;
+        for (int l = 0; l < nx; ++l) eg += Em[r * nx + l] * Ap[(i * nx + l) * nx + c];
+        for (int l = 0; l < ny; ++l) gl += Gm[r * ny + l] * LX[(i * ny + l) * nx + c];
+        HX[e] = -(eg + gl);
+    }
+    for (int e = threadIdx.x; e < nc * nv; e += blockDim.x) {
+        int r = e / nv, c = e - r * nv;
+        double gl = 0.0;
+        for (int l = 0; l < ny; ++l) gl += Gm[r * ny + l] * sm[p.o_Dv + l * nv + c];
+        sm[p.o_HDv + e] = sm[p.o_Fv + e] + gl;
+    }
+    for (int e = threadIdx.x; e < nc * nw; e += blockDim.x) {
+        int r = e / nw, c = e - r * nw;
+        double gl = 0.0;
+        for (int l = 0; l < ny; ++l) gl += Gm[r * ny + l] * sm[p.o_D4 + l * nw + c];
+        sm[p.o_HDw + e] = sm[p.o_F4 + e] + gl;
+    }
+    for (int e = threadIdx.x; e < Nt * nc; e += blockDim.x) {
+        int i = e / nc, r = e - i * nc;
+        double eg = 0.0, gl = 0.0;
+        for (int l = 0; l < nx; ++l) eg += Em[r * nx + l] * c5[i * nx + l];
+        for (int l = 0; l < ny; ++l) gl += Gm[r * ny + l] * L5[i * ny + l];
+        sm[p.o_H5 + e] = sm[p.o_f5 + r] - (eg + gl);
+    }
+    __syncthreads();
+
+    // ---- 3. stream this CTA's row slice of every requested output
+    const int S = gridDim.y, s = blockIdx.y;
+    auto slice = [&](int rows, int& lo, int& hi) { lo = (int)((int64_t)rows * s / S); hi = (int)((int64_t)rows * (s + 1) / S); };
+    int lo, hi;
+    const int64_t nvt = (int64_t)nv * Nt, nwt = (int64_t)nw * Nt;
+    // state-input
+    slice(nx * Nt, lo, hi);
+    if (args.out[HMPC_PHI_X]) write_stack(args.out[HMPC_PHI_X] + (int64_t)b * nx * Nt * nx, Ap, nx, lo, hi);
+    if (args.out[HMPC_GAMMA_V]) write_toeplitz(args.out[HMPC_GAMMA_V] + (int64_t)b * nx * Nt * nvt, Gv, nullptr, nx, nv, Nt, 1.0, lo, hi);
+    if (args.out[HMPC_GAMMA_OMEGA]) write_toeplitz(args.out[HMPC_GAMMA_OMEGA] + (int64_t)b * nx * Nt * nwt, Gw, nullptr, nx, nw, Nt, 1.0, lo, hi);
+    if (args.out[HMPC_GAMMA_5]) write_stack(args.out[HMPC_GAMMA_5] + (int64_t)b * nx * Nt, c5, 1, lo, hi);
+    // output
+    slice(ny * Nt, lo, hi);
+    if (args.out[HMPC_L_X]) write_stack(args.out[HMPC_L_X] + (int64_t)b * ny * Nt * nx, LX, nx, lo, hi);
+    if (args.out[HMPC_L_V]) write_toeplitz(args.out[HMPC_L_V] + (int64_t)b * ny * Nt * nvt, LGv, sm + p.o_LDv, ny, nv, Nt, 1.0, lo, hi);
+    if (args.out[HMPC_L_OMEGA]) write_toeplitz(args.out[HMPC_L_OMEGA] + (int64_t)b * ny * Nt * nwt, LGw, sm + p.o_LDw, ny, nw, Nt, 1.0, lo, hi);
+    if (args.out[HMPC_L_5]) write_stack(args.out[HMPC_L_5] + (int64_t)b * ny * Nt, L5, 1, lo, hi);
+    // constraint
+    slice(nc * Nt, lo, hi);
+    if (args.out[HMPC_H_X]) write_stack(args.out[HMPC_H_X] + (int64_t)b * nc * Nt * nx, HX, nx, lo, hi);
+    if (args.out[HMPC_H_V]) write_toeplitz(args.out[HMPC_H_V] + (int64_t)b * nc * Nt * nvt, HGv, sm + p.o_HDv, nc, nv, Nt, 1.0, lo, hi);
+    if (args.out[HMPC_H_OMEGA]) write_toeplitz(args.out[HMPC_H_OMEGA] + (int64_t)b * nc * Nt * nwt, HGw, sm + p.o_HDw, nc, nw, Nt, -1.0, lo, hi);
+    if (args.out[HMPC_H_5]) write_stack(args.out[HMPC_H_5] + (int64_t)b * nc * Nt, sm + p.o_H5, 1, lo, hi);
+}
+
+}  // namespace hmpc
+
+extern "C" int64_t hmpc_condense_bytes_per_agent(const hmpc_dims* d) {
+    if (!d) return 0;
+    const int64_t nv = d->nu + d->ndelta + d->nz + d->nmu;
+    const int64_t cols = d->nx + 1 + (nv + d->nomega) * (int64_t)d->Nt;
+    return 8 * (int64_t)(d->nx + d->ny + d->nc) * d->Nt * cols;
+}
+
+extern "C" int hmpc_condense_f64(const hmpc_dims* dims, const double* const mats[HMPC_NUM_MATS],
+                                 const int64_t mat_stride_b[HMPC_NUM_MATS], double* const out[HMPC_NUM_EVO],
+                                 void* stream) {
+    using namespace hmpc;
+    if (!dims || !mats || !mat_stride_b || !out) return HMPC_ERR_ARG;
+    const hmpc_dims d = *dims;
+    if (d.B < 0 || d.Nt < 1 || d.nx < 0 || d.nu < 0 || d.ndelta < 0 || d.nz < 0 || d.nmu < 0 || d.nomega < 0 ||
+        d.ny < 0 || d.nc < 0)
+        return HMPC_ERR_ARG;
+    if (d.B == 0) return HMPC_OK;
+    CondenseArgs a;
+    a.d = d;
+    for (int i = 0; i < HMPC_NUM_MATS; ++i) { a.mats[i] = mats[i]; a.stride[i] = mat_stride_b[i]; }
+    for (int i = 0; i < HMPC_NUM_EVO; ++i) a.out[i] = out[i];
+    const CondensePlan p = make_plan(d);
+    const size_t smem = (size_t)p.total * sizeof(double);
+    if (smem > 220 * 1024) return HMPC_ERR_ARG;  // model too large for the shared-memory lag table
+    HMPC_CUDA_TRY(cudaFuncSetAttribute(condense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // enough CTAs for >= 2 waves of the 148 SMs, at most one CTA per 4 output rows
+    int S = 1;
+    const int max_rows = max(1, (d.nx + d.ny + d.nc) * d.Nt / 3);
+    while (d.B * S < 4 * kNumSM && S * 2 * 4 <= max_rows) S *= 2;
+    dim3 grid(d.B, S);
+    condense_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(a);
+    HMPC_LAUNCH_CHECK("condense_kernel");
+    return HMPC_OK;
+}
