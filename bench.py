@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark: DEWH hybrid-MPC MILP solves/sec (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--agents B] [--np N_p]
+
+Workload (config.workload): BASELINE.json configs[1] -- a batch of 100 synthetic DEWH agents per GPU, N_p = 48
+(n = 147 variables of which 49 binary, m = 98 rows per agent), independent MILPs, solved to proven optimality
+(mip_rel_gap = 0).  One "step" = one pass of the hot path over the batch:
+    K1 condense -> K2 constraint rhs -> K3/K4 branch-and-cut solve -> K5 DEWH sim step -> K6 aggregate power
+                                                                               (+ NCCL all-reduce when N > 1).
+Every step uses a different control instant (new states, demand forecast and prices), so nothing is cached.
+
+* value  : whole-job solves/s with inputs resident in HBM, CUDA-event time of the K steps, max over ranks.
+* e2e    : same metric through the host-buffer C-ABI call (hmpc_mpc_step_host_f64): numpy in, numpy out,
+           host<->device copies inside the timed region.
+* roofline / cpu_baseline objects: see DESIGN.md section 6.
+* --impl reference : the reference's CPU path (oracle port: numpy condensing + HiGHS via scipy) on all host
+  cores, same workload, same metric.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "dewh_hybrid_mpc_milp_solves_per_sec"
+UNIT = "solves/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
+    ap.add_argument("--agents", type=int, default=100, help="agents per GPU (weak scaling)")
+    ap.add_argument("--np", dest="N_p", type=int, default=48)
+    ap.add_argument("--cpu-sample", type=int, default=64, help="agent-solves timed for cpu_baseline")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(args, n_gpus):
+    return {"workload": "configs[1]: batch of %d synthetic DEWH agents per GPU, N_p=%d, independent MILPs, gap 0"
+                        % (args.agents, args.N_p),
+            "agents_per_gpu": args.agents, "N_p": args.N_p, "n_vars": 3 * (args.N_p + 1), "n_binaries": args.N_p + 1,
+            "n_rows": 2 * (args.N_p + 1), "parallelism": "agents sharded x%d" % n_gpus,
+            "l2_policy": "L2 flushed (256 MiB write) before every timed step"}
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference
+def _cpu_solve_one(job):
+    """One agent's control step on the CPU: numpy condensing + assembly + HiGHS (the oracle port)."""
+    from oracle import mld as omld, condense as oc, assemble as oa, solve as osv
+    mats, Nt, x0, omega, q_u, q_mu = job
+    full, d, vt = omld.complete(mats, nu_l=1)
+    evo = oc.condense(full, d, Nt)
+    prob = oa.build_problem(evo, d, vt, Nt, x0, omega, atoms=dict(q_u=q_u, q_mu=q_mu))
+    st, obj, v = osv.solve_milp(prob)
+    return obj
+
+
+def cpu_jobs(args, step, first_agent=0, count=None):
+    from pyhybridcontrol_b200.examples.residential_mg_with_pv_and_dewhs import synthetic as syn
+    B = args.agents if count is None else count
+    wl = syn.dewh_batch(B, args.N_p, seed=1, k0=step, first_agent=first_agent)
+    return [({k: v[b] for k, v in wl["mats"].items()}, wl["Nt"], wl["x0"][b], wl["omega"][b], wl["q_u"][b],
+             wl["q_mu"][b]) for b in range(B)]
+
+
+def run_cpu(args, jobs_per_step, steps, warmup, cores):
+    import multiprocessing as mp
+    ctx = mp.get_context("fork")
+    times = []
+    with ctx.Pool(cores) as pool:
+        for s in range(warmup + steps):
+            jobs = jobs_per_step(s)
+            t0 = time.perf_counter()
+            pool.map(_cpu_solve_one, jobs, chunksize=max(1, len(jobs) // (4 * cores)))
+            dt = time.perf_counter() - t0
+            if s >= warmup:
+                times.append(dt)
+    return times
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    times = run_cpu(args, lambda s: cpu_jobs(args, s), args.steps, min(args.warmup, 1), cores)
+    total = sum(times)
+    value = args.agents * len(times) / total
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, args.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": "%d steps x %d agents, numpy condensing + HiGHS 1.12 (scipy.optimize.milp, "
+                                       "gap 0), multiprocessing pool on all host cores" % (len(times), args.agents)},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "latency_p50_ms": 1e3 * float(np.median(times)), "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ clocks sampler
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super(ClockSampler, self).__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag = index, [], set(), False
+        self.max_mhz = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+                 getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+                 getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+                 getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown"}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "note": "NVML unavailable"}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def main_ours(args):
+    import torch
+    import torch.distributed as dist
+    from pyhybridcontrol_b200 import cabi
+    from pyhybridcontrol_b200.examples.residential_mg_with_pv_and_dewhs import synthetic as syn
+    from pyhybridcontrol_b200.examples.residential_mg_with_pv_and_dewhs.fleet import DewhFleet
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, N_p, Nt = args.agents, args.N_p, args.N_p + 1
+    K, W = args.steps, max(args.warmup, 3)
+    first_agent = rank * B
+
+    # ---- synthetic inputs for W + K distinct control instants, resident in HBM before timing starts
+    wl0 = syn.dewh_batch(B, N_p, seed=1, k0=0, first_agent=first_agent)
+    fleet = DewhFleet(wl0["params"], N_p, device=dev)
+    steps_in = []
+    for s in range(W + K):
+        wl = wl0 if s == 0 else syn.dewh_batch(B, N_p, seed=1, k0=s, first_agent=first_agent)
+        cost = np.zeros((B, Nt, 3))
+        cost[:, :, 0] = wl["q_u"]
+        cost[:, :, 1:] = wl["q_mu"][:, None, :]
+        steps_in.append(dict(
+            x0=torch.as_tensor(wl["x0"]).to(dev), omega=torch.as_tensor(wl["omega"]).to(dev),
+            cost=torch.as_tensor(cost.reshape(B, -1)).to(dev), host=wl, host_cost=cost.reshape(B, -1)))
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+    names = ("condense", "rhs", "solve", "sim", "aggregate")
+    kernel_ms = {k: 0.0 for k in names}
+    solve_stats = []
+
+    def one_step(inp, timed_events=None):
+        ev = timed_events
+        if ev:
+            ev[0].record()
+        fleet.build()
+        if ev:
+            ev[1].record()
+        rhs = cabi.constraint_rhs(fleet.batch.dims, fleet.batch.evo, inp["x0"], inp["omega"])
+        if ev:
+            ev[2].record()
+        lb, ub, isb = fleet.batch._bounds_dev()
+        v, obj, status, stats = cabi.milp_solve(inp["cost"], fleet.batch.evo["H_v"], rhs, lb, ub, isb, fleet.batch.opts)
+        if ev:
+            ev[3].record()
+        u = v.view(B, Nt, 3)[:, :, 0]
+        T1, cons = fleet.sim_step(inp["x0"][:, 0].contiguous(), u[:, 0].contiguous(), inp["omega"][:, 0].contiguous())
+        if ev:
+            ev[4].record()
+        p_agg = fleet.aggregate_power(u)
+        if ev:
+            ev[5].record()
+        return v, obj, status, stats, T1, p_agg
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for s in range(W):
+        flush.fill_(float(s))
+        out = one_step(steps_in[s])
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = cabi.launch_count
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(6)] for _ in range(K)]
+    outs = []
+    t_wall0 = time.perf_counter()
+    for s in range(K):
+        flush.fill_(float(s))
+        outs.append(one_step(steps_in[W + s], evs[s]))
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    sampler.stop_flag = True
+    launches = cabi.launch_count - launches0
+    step_ms = [e[0].elapsed_time(e[5]) for e in evs]
+    for e in evs:
+        for i, k in enumerate(names):
+            kernel_ms[k] += e[i].elapsed_time(e[i + 1])
+    total_ms = float(sum(step_ms))
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    not_opt = 0
+    fma = 0.0
+    piv = []
+    for o in outs:
+        st = o[2].cpu().numpy()
+        ss = o[3].cpu().numpy()
+        not_opt += int((st != 0).sum())
+        fma += float(ss[:, 7].astype(np.float64).sum()) * 1024.0
+        piv.append(ss[:, 1])
+        solve_stats.append(ss)
+    piv = np.concatenate(piv)
+    value = world * B * K / (total_ms * 1e-3)
+
+    # ---- e2e: host buffers through hmpc_mpc_step_host_f64 (numpy in, numpy out, copies inside the timed region)
+    plan = cabi.StepPlan(fleet.batch.dims, fleet.batch.opts)
+    hmats = dict(wl0["mats"])
+    hmats["C"] = np.ones((1, 1, 1))
+    e2e_times = []
+    for s in range(W + K):
+        inp = steps_in[s]
+        flush.fill_(float(s))
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        v_h, obj_h, st_h, stats_h, tm = plan.step(hmats, inp["host"]["x0"], inp["host"]["omega"], inp["host_cost"],
+                                                  fleet.batch.lb_v, fleet.batch.ub_v, fleet.batch.is_bin_v,
+                                                  recondense=True)
+        u0 = v_h[:, 0].sum()  # the step's result is read on the host
+        dt = time.perf_counter() - t0
+        if s >= W:
+            e2e_times.append(dt)
+    h2d, d2h = plan.bytes_per_step(True)
+    e2e_total = float(sum(e2e_times))
+    if world > 1:
+        t = torch.tensor([e2e_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_total = float(t.item())
+    e2e_value = world * B * K / e2e_total
+    # parity spot check inside the bench: e2e path and device path agree on the last step
+    assert np.allclose(obj_h, outs[-1][1].cpu().numpy(), rtol=1e-9, atol=1e-12), "host and device paths disagree"
+    plan.close()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    fp64_peak = cabi.fp64_peak_tflops()
+    solve_ms = kernel_ms["solve"] / K
+    cond_ms = kernel_ms["condense"] / K
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    cond_bytes = 4 * 8 * 0  # placeholder, replaced below
+    d = fleet.batch.dims
+    # bytes K1 writes per launch in this pipeline (the four constraint matrices) -- algorithmic, see DESIGN.md
+    cond_bytes = 8 * B * (d.nc * Nt) * (d.nx + d.nv * Nt + d.nomega * Nt + 1)
+    achieved_tf = (2.0 * fma / K) / (solve_ms * 1e-3) / 1e12 if solve_ms > 0 else 0.0
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
+        "latency_p50_ms": float(np.median(step_ms)), "latency_max_ms": float(np.max(step_ms)),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": 1e3 * e2e_total / K, "api": "hmpc_mpc_step_host_f64 via cabi.StepPlan.step"},
+        "gpu_launches": int(launches),
+        "kernel_ms_per_step": {k: v / K for k, v in kernel_ms.items()},
+        "roofline": {"kernel": "milp_bnc_kernel", "bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak,
+                     "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak if fp64_peak else None, "traffic": None,
+                     "peak_source": "hmpc_fp64_peak_probe (DFMA micro-benchmark, measured in this run)",
+                     "share_of_step": solve_ms / (total_ms / K),
+                     "note": "latency-bound tree search: algorithmic FMAs (pivots, row transforms) counted by the "
+                             "kernel itself; SURVEY 8(d) names FP64 pipe / latency, not HBM, as the bound"},
+        "roofline_condense": {"kernel": "condense_kernel", "bound": "hbm", "achieved": cond_bytes / (cond_ms * 1e-3) / 1e9,
+                              "peak": hbm_peak, "unit": "GB/s",
+                              "frac": cond_bytes / (cond_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+                              "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
+                              "bytes_per_launch": cond_bytes},
+        "solver": {"not_optimal": not_opt, "pivots_mean": float(piv.mean()), "pivots_p50": float(np.median(piv)),
+                   "pivots_max": int(piv.max())},
+        "wall_s_timed_region": t_wall,
+        "clocks": sampler.summary(),
+    }
+    if not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        sample = max(cores, args.cpu_sample)
+        times = run_cpu(args, lambda s: cpu_jobs(args, s, count=sample), 1, 0, cores)
+        line["cpu_baseline"] = {"value": sample / times[0], "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": "%d agent-solves of the same workload (numpy condensing + HiGHS 1.12 via "
+                                          "scipy.optimize.milp, gap 0) on a %d-process pool" % (sample, cores)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        main_reference(a)
+    else:
+        main_ours(a)

@@ -129,7 +129,7 @@ int  hmpc_milp_workspace_bytes(int32_t B, int32_t n, int32_t m, const hmpc_milp_
 /*  c [B,n] (stride_c_b), H [B,m,n] (stride_H_b), rhs [B,m], lb/ub [B,n] (stride_bnd_b; +-inf allowed),
  *  is_bin [n] bytes shared by the batch.  Outputs: v [B,n], obj [B] (= c'v, caller adds c0),
  *  status [B] (hmpc_solve_status), stats [B,8] = {nodes, pivots, cuts, rows_added, max_rows, lp_solves,
- *  purges, reserved}.                                                                                 */
+ *  purges, kilo-FMAs (1024 algorithmic FP64 FMAs)}.                                                                                 */
 int  hmpc_milp_solve_f64(int32_t B, int32_t n, int32_t m,
                          const double* c, int64_t stride_c_b, const double* H, int64_t stride_H_b,
                          const double* rhs, const double* lb, const double* ub, int64_t stride_bnd_b,

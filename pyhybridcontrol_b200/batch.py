@@ -1,0 +1,193 @@
+"""Batched front door of the GPU hot path: condense -> assemble -> mixed-integer solve for B agents at once.
+
+``BatchMpc`` is what the per-agent ``MpcController`` objects are thin views over (B = 1) and what the
+benchmark and the closed-loop driver use directly.  All arithmetic happens in the CUDA kernels behind
+``cabi``; torch tensors are device buffers only.
+
+Reference call stack being replaced (per agent, serially, in the reference):
+  MpcController.build  (controllers/mpc_controller.py:76-101)  -> MldEvoMatrices.update (K1)
+  ConstraintSolvedController.gen_evo_constraints (controllers/controller_base.py:411-456)  (K2)
+  ConstraintSolvedController.solve (controllers/controller_base.py:491-540) -> cvxpy -> Gurobi  (K3/K4)
+"""
+import numpy as np
+import torch
+
+from . import cabi
+
+
+def _dev_tensor(a, device, dtype=torch.float64):
+    if isinstance(a, torch.Tensor):
+        return a.to(device=device, dtype=dtype).contiguous()
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype).to(device)
+
+
+class BatchMpc(object):
+    def __init__(self, mats, N_p, N_tilde=None, nu_l=0, nmu_l=0, B=None, device="cuda", opts=None):
+        """mats: name -> array [B|1, r, c] (or [r, c]); missing blocks are zero, C defaults to I (nx == ny)."""
+        self.device = torch.device(device)
+        self.N_p = int(N_p)
+        self.Nt = int(N_tilde) if N_tilde is not None else self.N_p + 1
+        m = {}
+        Bs = set()
+        for k, v in mats.items():
+            if v is None:
+                continue
+            t = _dev_tensor(v, self.device)
+            if t.dim() == 2:
+                t = t.unsqueeze(0)
+            if t.numel() == 0:
+                continue
+            m[k] = t
+            Bs.add(t.shape[0])
+        Bs.discard(1)
+        if len(Bs) > 1:
+            raise ValueError("inconsistent batch sizes in mats: %s" % sorted(Bs))
+        self.B = int(B) if B is not None else (Bs.pop() if Bs else 1)
+
+        def rows(names):
+            return max([m[n].shape[1] for n in names if n in m] + [0])
+
+        def cols(names):
+            return max([m[n].shape[2] for n in names if n in m] + [0])
+        nx = rows(("A", "B1", "B2", "B3", "B4", "b5"))
+        if "C" not in m and nx:
+            m["C"] = torch.eye(nx, dtype=torch.float64, device=self.device).unsqueeze(0)
+        ny = rows(("C", "D1", "D2", "D3", "D4", "d5"))
+        nc = rows(("E", "F1", "F2", "F3", "F4", "f5", "G", "Psi"))
+        self.dims = cabi.make_dims(self.B, self.Nt, nx=nx, nu=cols(("B1", "D1", "F1")), ndelta=cols(("B2", "D2", "F2")),
+                                   nz=cols(("B3", "D3", "F3")), nmu=cols(("Psi",)), nomega=cols(("B4", "D4", "F4")),
+                                   ny=ny, nc=nc)
+        self.mats = m
+        d = self.dims
+        self.nv = d.nv
+        self.nvt = d.nv * self.Nt
+        self.nwt = d.nomega * self.Nt
+        self.mrows = d.nc * self.Nt
+        self.nu_l, self.nmu_l = int(nu_l), int(nmu_l)
+        step_bin = [0] * (d.nu - self.nu_l) + [1] * self.nu_l + [1] * d.ndelta + [0] * d.nz + \
+                   [0] * (d.nmu - self.nmu_l) + [1] * self.nmu_l
+        self.is_bin_step = np.array(step_bin, dtype=np.uint8)
+        lb_step = np.full(d.nv, -np.inf)
+        ub_step = np.full(d.nv, np.inf)
+        lb_step[self.is_bin_step == 1] = 0.0
+        ub_step[self.is_bin_step == 1] = 1.0
+        lb_step[d.nu + d.ndelta + d.nz:] = np.maximum(lb_step[d.nu + d.ndelta + d.nz:], 0.0)   # mu >= 0
+        self.lb_v = np.tile(lb_step, self.Nt)
+        self.ub_v = np.tile(ub_step, self.Nt)
+        self.is_bin_v = np.tile(self.is_bin_step, self.Nt)
+        self.opts = opts if opts is not None else cabi.default_opts()
+        self.evo = None
+        self._lb_dev = self._ub_dev = self._bin_dev = None
+        self.disable_soft_constraints = False
+
+    # ---- index helpers (v(k) = [u; delta; z; mu], reference: controllers/components/variables.py:233-241)
+    def var_slices(self):
+        d = self.dims
+        o = 0
+        out = {}
+        for name, dim in (("u", d.nu), ("delta", d.ndelta), ("z", d.nz), ("mu", d.nmu)):
+            out[name] = (o, o + dim)
+            o += dim
+        return out
+
+    def var_index(self, name):
+        a, b = self.var_slices()[name]
+        return (np.arange(self.Nt)[:, None] * self.nv + np.arange(a, b)[None, :]).ravel()
+
+    # ---- K1
+    def build(self, want=cabi.EVO_NAMES):
+        self.evo = cabi.condense(self.dims, self.mats, want=want, out=None)
+        return self.evo
+
+    def _bounds_dev(self):
+        lb, ub = self.lb_v.copy(), self.ub_v.copy()
+        if self.disable_soft_constraints and self.dims.nmu:
+            idx = self.var_index("mu")
+            lb[idx] = 0.0
+            ub[idx] = 0.0
+        key = (self.disable_soft_constraints,)
+        if self._lb_dev is None or self._bkey != key:
+            self._lb_dev = _dev_tensor(lb, self.device)
+            self._ub_dev = _dev_tensor(ub, self.device)
+            self._bin_dev = torch.as_tensor(self.is_bin_v, dtype=torch.uint8).to(self.device)
+            self._bkey = key
+        return self._lb_dev, self._ub_dev, self._bin_dev
+
+    # ---- K2 + cost + K3/K4
+    def constraint_rows(self, x0, omega=None, scenarios=None, N_tilde=None):
+        """(H rows view, rhs) of one evolution-constraint set (reference: controller_base.py:411-456)."""
+        rows = self.mrows if N_tilde is None else int(N_tilde) * self.dims.nc
+        rhs = cabi.constraint_rhs(self.dims, self.evo, x0, omega, scenarios=scenarios, rows=rows)
+        H = self.evo["H_v"][:, :rows, :]
+        return H, rhs
+
+    def linear_cost(self, w_v=None, w_x=None, w_y=None, x0=None, omega=None):
+        """Linear atoms -> (c [B,nvt], c0 [B]); weights on x / y are pulled back through Gamma_v / L_v."""
+        d = self.dims
+        xc = yc = None
+        if w_x is not None:
+            xc = cabi.predict(self.evo["Phi_x"], None, self.evo["Gamma_omega"], self.evo["Gamma_5"].reshape(d.B, -1),
+                              x0, None, omega)
+        if w_y is not None:
+            yc = cabi.predict(self.evo["L_x"], None, self.evo["L_omega"], self.evo["L_5"].reshape(d.B, -1), x0, None,
+                              omega)
+        if w_v is None and w_x is None and w_y is None:
+            z = torch.zeros((d.B, self.nvt), dtype=torch.float64, device=self.device)
+            return z, torch.zeros((d.B,), dtype=torch.float64, device=self.device)
+        return cabi.linear_cost(d.B, self.nvt, w_v=w_v, w_x=w_x, Gamma_v=self.evo.get("Gamma_v"), xc=xc, w_y=w_y,
+                                L_v=self.evo.get("L_v"), yc=yc)
+
+    def solve(self, x0, omega, cost_v=None, w_x=None, w_y=None, scenarios=None, extra_constraints=(),
+              with_std_constraints=True):
+        """One control step for the whole batch.  Returns dict(v, obj, status, stats, c0) of device tensors."""
+        if self.evo is None:
+            raise RuntimeError("build() must be called before solve()")
+        d = self.dims
+        x0 = _dev_tensor(x0, self.device).reshape(d.B, d.nx) if d.nx else None
+        omega = _dev_tensor(omega, self.device).reshape(d.B, self.nwt) if self.nwt else None
+        if scenarios is not None:
+            scenarios = _dev_tensor(scenarios, self.device)
+        cost_v = None if cost_v is None else _dev_tensor(cost_v, self.device).reshape(-1, self.nvt)
+        w_x = None if w_x is None else _dev_tensor(w_x, self.device).reshape(d.B, -1)
+        w_y = None if w_y is None else _dev_tensor(w_y, self.device).reshape(d.B, -1)
+        if w_x is None and w_y is None and cost_v is not None:
+            c, c0 = cost_v, torch.zeros((d.B,), dtype=torch.float64, device=self.device)
+        else:
+            c, c0 = self.linear_cost(cost_v, w_x, w_y, x0, omega)
+        Hs, rs = [], []
+        if d.nc and with_std_constraints:
+            H, r = self.constraint_rows(x0, omega, scenarios=scenarios)
+            Hs.append(H)
+            rs.append(r)
+        for ec in extra_constraints:
+            w2 = ec.get("omega_tilde_k")
+            sc = ec.get("omega_scenarios_k")
+            w2 = omega if w2 is None else _dev_tensor(w2, self.device).reshape(d.B, self.nwt)
+            sc = None if sc is None else _dev_tensor(sc, self.device).reshape(d.B, self.nwt, -1)
+            H, r = self.constraint_rows(x0, w2, scenarios=sc, N_tilde=ec.get("N_tilde"))
+            Hs.append(H)
+            rs.append(r)
+        if len(Hs) == 1 and Hs[0].shape[1] == self.mrows:
+            H, rhs = self.evo["H_v"], rs[0]
+        elif Hs:
+            H, rhs = torch.cat(Hs, dim=1).contiguous(), torch.cat(rs, dim=1).contiguous()
+        else:
+            H = torch.zeros((d.B, 0, self.nvt), dtype=torch.float64, device=self.device)
+            rhs = torch.zeros((d.B, 0), dtype=torch.float64, device=self.device)
+        lb, ub, isb = self._bounds_dev()
+        v, obj, status, stats = cabi.milp_solve(c, H, rhs, lb, ub, isb, self.opts)
+        return dict(v=v, obj=obj + c0, status=status, stats=stats, c0=c0)
+
+    def predictions(self, v, x0, omega):
+        """x~ [B, nx*Nt], y~ [B, ny*Nt] for a given v~ (reference: variables.py:245-286)."""
+        d = self.dims
+        x0 = _dev_tensor(x0, self.device).reshape(d.B, d.nx) if d.nx else None
+        omega = _dev_tensor(omega, self.device).reshape(d.B, self.nwt) if self.nwt else None
+        xt = yt = None
+        if d.nx:
+            xt = cabi.predict(self.evo["Phi_x"], self.evo["Gamma_v"], self.evo["Gamma_omega"],
+                              self.evo["Gamma_5"].reshape(d.B, -1), x0, v, omega)
+        if d.ny:
+            yt = cabi.predict(self.evo["L_x"], self.evo["L_v"], self.evo["L_omega"], self.evo["L_5"].reshape(d.B, -1),
+                              x0, v, omega)
+        return xt, yt

@@ -102,6 +102,7 @@ struct Ctx {
     double ptol, itol, big;
     double z;          // running LP objective (uniform across threads)
     int R;             // active rows (uniform across threads)
+    double fmas;       // algorithmic FMA count (uniform), reported in stats[7] in units of 1024
 };
 
 // ---------------------------------------------------------------- block reductions (uniform result)
@@ -182,6 +183,7 @@ __device__ inline void node_setup(Ctx& c) {
     double part = 0.0;
     for (int j = threadIdx.x; j < c.n; j += kThreads) part += c.cc[j] * c.x[j];
     c.z = block_sum(c, part);
+    c.fmas += (double)c.R * c.n;
 }
 
 // ---------------------------------------------------------------- bounded dual simplex on the active rows
@@ -284,6 +286,7 @@ __device__ inline int dual_simplex(Ctx& c, double cutoff, int& pivots_left) {
             }
         }
         c.z += dq * t;
+        c.fmas += (double)R * n;
         --pivots_left;
         __syncthreads();
         if (c.z >= cutoff) return LP_CUT;
@@ -318,6 +321,7 @@ __device__ inline void add_row(Ctx& c, const double* g, double g0, int slack_id)
         if (R + 1 > c.sint[SI_MAX_ROWS]) c.sint[SI_MAX_ROWS] = R + 1;
     }
     c.R = R + 1;
+    c.fmas += (double)R * n;
     __syncthreads();
 }
 
@@ -385,6 +389,7 @@ __device__ inline int scan_rows(Ctx& c) {
     }
     __syncthreads();
     const int nsel = c.sint[SI_NSEL];
+    c.fmas += (double)m * n;
     if (nsel == 0) return 0;
     if (c.R + nsel > c.rmax) purge(c);
     int added = 0;
@@ -624,7 +629,7 @@ __global__ void __launch_bounds__(kThreads, 1) milp_bnc_kernel(const MilpArgs a)
     c.isbin = sb + p.isbin; c.poolState = sb + p.poolState;
     c.H = a.H + (int64_t)b * a.sH;
     c.ptol = a.o.feas_tol; c.itol = a.o.int_tol; c.big = a.o.big_bound;
-    c.R = 0; c.z = 0.0;
+    c.R = 0; c.z = 0.0; c.fmas = 0.0;
 
     // ---- load problem data
     const double* cg = a.c + (int64_t)b * a.sc;
@@ -752,7 +757,7 @@ __global__ void __launch_bounds__(kThreads, 1) milp_bnc_kernel(const MilpArgs a)
         a.obj[b] = have_inc ? best : INFINITY;
         int32_t* s = a.stats + (int64_t)b * 8;
         s[0] = nodes; s[1] = c.sint[SI_PIVOTS]; s[2] = c.sint[SI_CUTS]; s[3] = c.sint[SI_ROWS_ADDED];
-        s[4] = c.sint[SI_MAX_ROWS]; s[5] = c.sint[SI_LP]; s[6] = c.sint[SI_PURGES]; s[7] = 0;
+        s[4] = c.sint[SI_MAX_ROWS]; s[5] = c.sint[SI_LP]; s[6] = c.sint[SI_PURGES]; s[7] = (int32_t)fmin(c.fmas / 1024.0, 2.0e9);
     }
     if (!have_inc) for (int j = threadIdx.x; j < n; j += kThreads) vout[j] = nan("");
 }

@@ -1,0 +1,53 @@
+"""Multi-GPU plumbing: agents (and agent x scenario pairs) are independent, so the batch is sharded in contiguous
+blocks, one process per GPU, with NO data-path collective during condense / solve / sim.  The only exchange per
+control step is the aggregate power trajectory the grid agent needs
+(reference: examples/.../micro_grid_agents.py:625-646 stacks every device's power; the grid model only uses the
+sum, micro_grid_models.py:143): an all-reduce of [Nt] FP64 values (392 B at N_p = 48) on the solve stream, or an
+all-gather of the per-agent trajectories when the caller wants them.  Works with NCCL (GPU) and gloo (CPU tests).
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_range(num_agents, rank, world_size):
+    """Contiguous block [lo, hi) of agents owned by ``rank`` (sizes differ by at most one)."""
+    base, rem = divmod(int(num_agents), int(world_size))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def is_distributed():
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
+def allreduce_aggregate(p_local):
+    """Sum of the per-rank aggregate power trajectories [Nt]; in place, asynchronous on the current stream."""
+    if is_distributed():
+        dist.all_reduce(p_local, op=dist.ReduceOp.SUM)
+    return p_local
+
+
+def allgather_trajectories(traj_local, counts=None):
+    """[B_local, Nt] per rank -> [B_total, Nt] on every rank, rank-major (the order the reference stacks devices)."""
+    if not is_distributed():
+        return traj_local
+    world = dist.get_world_size()
+    if counts is None:
+        out = [torch.empty_like(traj_local) for _ in range(world)]
+        dist.all_gather(out, traj_local.contiguous())
+        return torch.cat(out, dim=0)
+    mx = max(counts)
+    pad = torch.zeros((mx,) + tuple(traj_local.shape[1:]), dtype=traj_local.dtype, device=traj_local.device)
+    pad[:traj_local.shape[0]] = traj_local
+    out = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(out, pad)
+    return torch.cat([o[:c] for o, c in zip(out, counts)], dim=0)
+
+
+def grid_evaluate(p_devices_sum, p_pv, p_res):
+    """Grid agent closed form on the gathered aggregate (reference grid MLD, micro_grid_models.py:145-168):
+    y = sum of device powers, delta = [y >= 0], z = delta*y (import), export = y - z."""
+    y = p_devices_sum + p_pv + p_res
+    delta = (y >= 0).to(y.dtype)
+    z = delta * y
+    return dict(y=y, delta=delta, p_imp=z, p_exp=y - z)
