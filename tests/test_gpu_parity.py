@@ -119,7 +119,9 @@ def test_lsim_vs_reference_golden(case, cuda_device):
     from pyhybridcontrol_b200 import cabi
     g = load_golden("lsim", case)
     T = g["x"].shape[0]
-    bm, mats = _golden_batch(g, cuda_device, B=T)
+    from pyhybridcontrol_b200.batch import BatchMpc
+    mats = {k[3:]: v for k, v in g.items() if k.startswith("in_")}
+    bm = BatchMpc(mats, 0, 1, nu_l=int(g["nu_l"]), B=T, device=cuda_device)
     d = cabi.make_dims(T, 1, nx=bm.dims.nx, nu=bm.dims.nu, ndelta=bm.dims.ndelta, nz=bm.dims.nz, nmu=bm.dims.nmu,
                        nomega=bm.dims.nomega, ny=bm.dims.ny, nc=bm.dims.nc)
     f = lambda k: _t(g[k].reshape(T, -1), cuda_device) if g[k].size else None
