@@ -137,6 +137,34 @@ int  hmpc_milp_solve_f64(int32_t B, int32_t n, int32_t m,
                          void* workspace, size_t workspace_bytes,
                          double* v, double* obj, int32_t* status, int32_t* stats, void* stream);
 
+/* ---- K3s/K4s exact solve for SCALAR-STATE MLDs (the reference example's water heaters): same problem and
+ *      same boundary as hmpc_milp_solve_f64 (controllers/controller_base.py:509-512), for the class
+ *        nx == 1, nz == 0, every input/delta binary (nb = nu + ndelta <= 4), Psi = -diag(d) (each row owns at most
+ *        its own slack; nmu in {0, nc}), linear cost, Nt <= 128, nb*Nt <= 128
+ *      (examples/residential_mg_with_pv_and_dewhs/modelling/micro_grid_models.py:27-100).  Instead of the condensed
+ *      H_v it reads the MLD blocks directly (mats as in hmpc_condense_f64: A, B1, B2, C, D1, D2, E, F1, F2, G, Psi)
+ *      and solves  min cost_v'v  s.t.  H_v v <= rhs  exactly: a backward value-table lower bound over the scaled
+ *      scalar state + an exact depth-first search over the binary sequence.
+ *  rhs [B, nc*Nt] (from hmpc_constraint_rhs_f64; several constraint sets over the same rows fold into their
+ *  row-wise minimum), cost_v [B|1, nv*Nt], lb_v/ub_v/is_bin_v [nv*Nt] shared by the batch, v(k) = [u; delta; mu].
+ *  status[b] = HMPC_SOLVE_UNSUPPORTED marks an agent outside the class (use hmpc_milp_solve_f64 for it).
+ *  stats [B,8] = {search nodes, 0, 0, cells, max open nodes, incumbent updates, 0, kilo-FMAs}.               */
+typedef struct {
+    double  mip_rel_gap;   /* 0 = prove optimality                                     */
+    double  feas_tol;      /* tolerance of hard (slack-free) rows, default 1e-9        */
+    int32_t cells;         /* value-table cells per stage, default 8192                */
+    int32_t max_nodes;     /* search nodes per agent, default 4,000,000                */
+} hmpc_stage_dp_opts;
+void hmpc_stage_dp_default_opts(hmpc_stage_dp_opts* opts);
+int  hmpc_stage_dp_supported(const hmpc_dims* dims);     /* 1 when the dimensions fit the class */
+int  hmpc_stage_dp_workspace_bytes(const hmpc_dims* dims, const hmpc_stage_dp_opts* opts, size_t* bytes);
+int  hmpc_stage_dp_solve_f64(const hmpc_dims* dims, const double* const mats[HMPC_NUM_MATS],
+                             const int64_t mat_stride_b[HMPC_NUM_MATS], const double* rhs,
+                             const double* cost_v, int64_t cost_v_stride_b, const double* lb_v, const double* ub_v,
+                             const uint8_t* is_bin_v, const hmpc_stage_dp_opts* opts,
+                             void* workspace, size_t workspace_bytes,
+                             double* v, double* obj, int32_t* status, int32_t* stats, void* stream);
+
 /* ---- K5 simulation step: replaces MldModel.lsim_k (models/mld_model.py:647-699): mu ignored in cons
  *      (:694), tolerance cons_tol (default 1e-6, :648).  mats as in hmpc_condense_f64.
  *  x [B,nx], u [B,nu], delta [B,ndelta], z [B,nz], w [B,nomega] -> x1 [B,nx], y [B,ny], cons [B,nc] bytes */

@@ -22,8 +22,13 @@ def _dev_tensor(a, device, dtype=torch.float64):
 
 
 class BatchMpc(object):
-    def __init__(self, mats, N_p, N_tilde=None, nu_l=0, nmu_l=0, B=None, device="cuda", opts=None):
-        """mats: name -> array [B|1, r, c] (or [r, c]); missing blocks are zero, C defaults to I (nx == ny)."""
+    def __init__(self, mats, N_p, N_tilde=None, nu_l=0, nmu_l=0, B=None, device="cuda", opts=None, solver="auto",
+                 dp_opts=None):
+        """mats: name -> array [B|1, r, c] (or [r, c]); missing blocks are zero, C defaults to I (nx == ny).
+
+        solver: "auto" -- the exact stage-DP kernels (csrc/stage_dp.cu) when the MLD is in their class (scalar
+        state, binary inputs, one slack per row: every DEWH of the reference example), else the general
+        branch-and-cut kernel (csrc/milp_bnc.cu); "bnc" / "stage_dp" force one of them."""
         self.device = torch.device(device)
         self.N_p = int(N_p)
         self.Nt = int(N_tilde) if N_tilde is not None else self.N_p + 1
@@ -76,9 +81,37 @@ class BatchMpc(object):
         self.ub_v = np.tile(ub_step, self.Nt)
         self.is_bin_v = np.tile(self.is_bin_step, self.Nt)
         self.opts = opts if opts is not None else cabi.default_opts()
+        if solver not in ("auto", "bnc", "stage_dp"):
+            raise ValueError("solver must be 'auto', 'bnc' or 'stage_dp'")
+        self.solver = solver
+        self.dp_opts = dp_opts if dp_opts is not None else cabi.stage_dp_default_opts()
+        self.stage_dp_ok = self._stage_dp_class()
+        if solver == "stage_dp" and not self.stage_dp_ok:
+            raise ValueError("this MLD is outside the stage-DP class (needs nx == 1, nz == 0, binary inputs, "
+                             "Psi = -diag(d >= 0), A > 0)")
         self.evo = None
         self._lb_dev = self._ub_dev = self._bin_dev = None
         self.disable_soft_constraints = False
+
+    def _stage_dp_class(self):
+        """One-time host check that every agent of the batch is in the class of hmpc_stage_dp_solve_f64."""
+        d = self.dims
+        if not cabi.stage_dp_supported(d) or self.nu_l != d.nu or self.nmu_l != 0:
+            return False
+        A = self.mats.get("A")
+        if A is None or not bool((A > 0).all()):
+            return False
+        aN = A.reshape(-1) ** self.Nt
+        if not bool(((aN > 1e-3) & (aN < 1e3)).all()):
+            return False
+        Psi = self.mats.get("Psi")
+        if d.nmu:
+            if Psi is None:
+                return False
+            off = Psi - torch.diag_embed(torch.diagonal(Psi, dim1=1, dim2=2))
+            if bool((off != 0).any()) or bool((torch.diagonal(Psi, dim1=1, dim2=2) > 0).any()):
+                return False
+        return True
 
     # ---- index helpers (v(k) = [u; delta; z; mu], reference: controllers/components/variables.py:233-241)
     def var_slices(self):
@@ -167,6 +200,18 @@ class BatchMpc(object):
             H, r = self.constraint_rows(x0, w2, scenarios=sc, N_tilde=ec.get("N_tilde"))
             Hs.append(H)
             rs.append(r)
+        lb, ub, isb = self._bounds_dev()
+        use_dp = self.solver == "stage_dp" or (self.solver == "auto" and self.stage_dp_ok)
+        if use_dp and rs:
+            # every constraint set shares the rows of H_v (prefixes for reduced horizons), so the sets fold into
+            # the row-wise minimum of their right-hand sides
+            rhs = torch.full((d.B, self.mrows), float("inf"), dtype=torch.float64, device=self.device)
+            for r in rs:
+                rhs[:, :r.shape[1]] = torch.minimum(rhs[:, :r.shape[1]], r)
+            if len(rs) == 1 and rs[0].shape[1] == self.mrows:
+                rhs = rs[0]
+            v, obj, status, stats = cabi.stage_dp_solve(d, self.mats, rhs, c, lb, ub, isb, self.dp_opts)
+            return dict(v=v, obj=obj + c0, status=status, stats=stats, c0=c0, solver="stage_dp")
         if len(Hs) == 1 and Hs[0].shape[1] == self.mrows:
             H, rhs = self.evo["H_v"], rs[0]
         elif Hs:
@@ -174,9 +219,8 @@ class BatchMpc(object):
         else:
             H = torch.zeros((d.B, 0, self.nvt), dtype=torch.float64, device=self.device)
             rhs = torch.zeros((d.B, 0), dtype=torch.float64, device=self.device)
-        lb, ub, isb = self._bounds_dev()
         v, obj, status, stats = cabi.milp_solve(c, H, rhs, lb, ub, isb, self.opts)
-        return dict(v=v, obj=obj + c0, status=status, stats=stats, c0=c0)
+        return dict(v=v, obj=obj + c0, status=status, stats=stats, c0=c0, solver="bnc")
 
     def predictions(self, v, x0, omega):
         """x~ [B, nx*Nt], y~ [B, ny*Nt] for a given v~ (reference: variables.py:245-286)."""

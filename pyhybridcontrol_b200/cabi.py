@@ -19,13 +19,15 @@ EVO_NAMES = ("Phi_x", "Gamma_v", "Gamma_omega", "Gamma_5", "L_x", "L_v", "L_omeg
              "H_x", "H_v", "H_omega", "H_5")
 EXPORTS = ("hmpc_version", "hmpc_last_cuda_error", "hmpc_device_info", "hmpc_condense_f64",
            "hmpc_condense_bytes_per_agent", "hmpc_constraint_rhs_f64", "hmpc_predict_f64", "hmpc_linear_cost_f64",
-           "hmpc_milp_default_opts", "hmpc_milp_workspace_bytes", "hmpc_milp_solve_f64", "hmpc_lsim_step_f64",
+           "hmpc_milp_default_opts", "hmpc_milp_workspace_bytes", "hmpc_milp_solve_f64", "hmpc_stage_dp_default_opts",
+           "hmpc_stage_dp_supported", "hmpc_stage_dp_workspace_bytes", "hmpc_stage_dp_solve_f64", "hmpc_lsim_step_f64",
            "hmpc_dewh_sim_step_f64", "hmpc_dewh_control_model_f64", "hmpc_aggregate_power_f64",
            "hmpc_step_plan_create", "hmpc_step_plan_destroy", "hmpc_mpc_step_host_f64", "hmpc_mpc_step_host_bytes",
            "hmpc_fp64_peak_probe")
 
 SOLVE_STATUS = {0: "optimal", 1: "infeasible", 2: "node_limit", 3: "iter_limit", 4: "numeric", 5: "unsupported"}
 STAT_NAMES = ("nodes", "pivots", "cuts", "rows_added", "max_rows", "lp_solves", "purges", "reserved")
+DP_STAT_NAMES = ("nodes", "unused1", "unused2", "cells", "max_open", "incumbent_updates", "unused6", "kilo_fma")
 
 
 class HmpcError(RuntimeError):
@@ -45,6 +47,10 @@ class MilpOpts(C.Structure):
                 ("big_bound", C.c_double), ("max_nodes", C.c_int32), ("max_pivots", C.c_int32),
                 ("max_cuts", C.c_int32), ("max_rows", C.c_int32), ("cut_rounds_root", C.c_int32),
                 ("cut_rounds_node", C.c_int32), ("cuts_per_round", C.c_int32), ("reserved", C.c_int32)]
+
+
+class StageDpOpts(C.Structure):
+    _fields_ = [("mip_rel_gap", C.c_double), ("feas_tol", C.c_double), ("cells", C.c_int32), ("max_nodes", C.c_int32)]
 
 
 if not os.path.exists(LIB_PATH):
@@ -71,6 +77,12 @@ _lib.hmpc_milp_default_opts.restype = None
 _lib.hmpc_milp_workspace_bytes.argtypes = [C.c_int32] * 3 + [C.POINTER(MilpOpts), C.POINTER(C.c_size_t)]
 _lib.hmpc_milp_solve_f64.argtypes = [C.c_int32] * 3 + [_P, C.c_int64, _P, C.c_int64, _P, _P, _P, C.c_int64, _P,
                                                        C.POINTER(MilpOpts), _P, C.c_size_t, _P, _P, _P, _P, _P]
+_lib.hmpc_stage_dp_default_opts.argtypes = [C.POINTER(StageDpOpts)]
+_lib.hmpc_stage_dp_default_opts.restype = None
+_lib.hmpc_stage_dp_supported.argtypes = [C.POINTER(Dims)]
+_lib.hmpc_stage_dp_workspace_bytes.argtypes = [C.POINTER(Dims), C.POINTER(StageDpOpts), C.POINTER(C.c_size_t)]
+_lib.hmpc_stage_dp_solve_f64.argtypes = [C.POINTER(Dims), _MatArr, _StrideArr, _P, _P, C.c_int64, _P, _P, _P,
+                                         C.POINTER(StageDpOpts), _P, C.c_size_t, _P, _P, _P, _P, _P]
 _lib.hmpc_lsim_step_f64.argtypes = [C.POINTER(Dims), _MatArr, _StrideArr] + [_P] * 5 + [C.c_double] + [_P] * 4
 _lib.hmpc_dewh_sim_step_f64.argtypes = [C.c_int32] + [_P] * 8
 _lib.hmpc_dewh_control_model_f64.argtypes = [C.c_int32, _P, _P, _P]
@@ -250,6 +262,56 @@ def milp_solve(c, H, rhs, lb, ub, is_bin, opts=None):
                                     n if lb2.shape[0] == B and B > 1 else 0, _ptr(is_bin), C.byref(o), None, 0,
                                     _ptr(v), _ptr(obj), _ptr(status), _ptr(stats), _stream()), "hmpc_milp_solve_f64")
     launch_count += 1
+    return v, obj, status, stats
+
+
+def stage_dp_default_opts(**kw):
+    o = StageDpOpts()
+    _lib.hmpc_stage_dp_default_opts(C.byref(o))
+    for k, v in kw.items():
+        setattr(o, k, v)
+    return o
+
+
+def stage_dp_supported(d):
+    """True when the DIMENSIONS fit the scalar-state class of hmpc_stage_dp_solve_f64 (the matrix pattern --
+    Psi = -diag(d), A > 0 -- is checked per agent on the device and reported as status 5)."""
+    return bool(_lib.hmpc_stage_dp_supported(C.byref(d)))
+
+
+_dp_workspaces = {}
+
+
+def _dp_workspace(d, o, dev):
+    need = C.c_size_t()
+    _check(_lib.hmpc_stage_dp_workspace_bytes(C.byref(d), C.byref(o), C.byref(need)), "hmpc_stage_dp_workspace_bytes")
+    key = (dev.index, torch.cuda.current_stream().cuda_stream)
+    ws = _dp_workspaces.get(key)
+    if ws is None or ws.numel() < need.value:
+        ws = torch.empty((need.value,), dtype=torch.uint8, device=dev)
+        _dp_workspaces[key] = ws
+    return ws, need.value
+
+
+def stage_dp_solve(d, mats, rhs, cost_v, lb, ub, is_bin, opts=None):
+    """K3s/K4s.  mats as for condense(); rhs [B, nc*Nt]; cost_v [B|1, nv*Nt]; lb/ub [nv*Nt]; is_bin uint8 [nv*Nt]."""
+    global launch_count
+    arr, strides, keep = _pack_mats(d, mats)
+    nvt = (d.nu + d.ndelta + d.nmu) * d.Nt
+    dev = cost_v.device
+    c2 = cost_v.reshape(-1, nvt)
+    o = opts if opts is not None else stage_dp_default_opts()
+    ws, nbytes = _dp_workspace(d, o, dev)
+    v = torch.empty((d.B, nvt), dtype=torch.float64, device=dev)
+    obj = torch.empty((d.B,), dtype=torch.float64, device=dev)
+    status = torch.empty((d.B,), dtype=torch.int32, device=dev)
+    stats = torch.empty((d.B, 8), dtype=torch.int32, device=dev)
+    _check(_lib.hmpc_stage_dp_solve_f64(C.byref(d), arr, strides, _ptr(rhs) if d.nc else None, _ptr(c2),
+                                        nvt if (c2.shape[0] == d.B and d.B > 1) or d.B == 1 else 0,
+                                        _ptr(lb.reshape(-1)), _ptr(ub.reshape(-1)), _ptr(is_bin), C.byref(o),
+                                        C.c_void_p(ws.data_ptr()), nbytes, _ptr(v), _ptr(obj), _ptr(status),
+                                        _ptr(stats), _stream()), "hmpc_stage_dp_solve_f64")
+    launch_count += 2
     return v, obj, status, stats
 
 

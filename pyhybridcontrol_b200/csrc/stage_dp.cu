@@ -1,0 +1,594 @@
+// stage_dp.cu -- K3s/K4s: exact mixed-integer solve for MLD models with a SCALAR state, by a value-table
+// bound plus an exact forward search.  Replaces the cvxpy -> Gurobi/CPLEX call inside
+// ConstraintSolvedController.solve (reference: controllers/controller_base.py:509-512) for the problem class
+// the reference's own example poses for every water heater (examples/residential_mg_with_pv_and_dewhs/
+// modelling/micro_grid_models.py:27-100: nx = 1, one binary input, slack-softened box constraints, linear cost).
+//
+// Problem class (per agent; v(k) = [binaries (nb = nu + ndelta); mu (nmu = nc or 0)], k = 0..Nt-1):
+//     minimise  sum_k  cu_k' alpha_k + q_k' mu_k
+//     s.t.      e_i p_k + f_i' alpha_k - d_i mu_k,i <= rhs_k,i ,   mu >= 0 ,   alpha_k in {0,1}^nb (within lb/ub)
+//               p_0 = 0 ,  p_k+1 = a p_k + g' alpha_k            (p = forced response = row k of Gamma_v times v)
+// with a = A, g = [B1 B2], e = E + G C, f = [F1 F2] + G [D1 D2], d_i = -Psi_ii (0: hard row), rhs from K2.
+// This is exactly  min c'v  s.t.  H_v v <= rhs  of the condensed form (mld_evolution_matrices.py:237-240), whose
+// continuous part has the closed form  mu_k,i = max(0, e_i p_k + f_i' alpha_k - rhs_k,i) / d_i.
+//
+// Algorithm
+//   * scaled state s_k = p_k / a^k turns the recursion into a pure translation s_k+1 = s_k + beta_k(alpha),
+//     beta_k = g' alpha / a^(k+1): the "no input" action maps every cell of a uniform s-grid onto itself.
+//   * kernel 1 (stage_dp_table_kernel, one CTA per agent): backward sweep over the stages of a LOWER BOUND
+//     LB_k[cell] of the cost-to-go that is valid for every state in the cell (stage penalties are bounded from
+//     below over the cell, a translated cell overlaps two cells of the next stage and takes their min).  The
+//     current stage lives in shared memory; every stage is streamed to HBM as FP32 rounded DOWN, so the stored
+//     table is still a valid bound.  States outside the grid window get the trivial bound (sum of negative
+//     costs), so the window only affects speed, never correctness.
+//   * kernel 2 (stage_dp_search_kernel, one warp per agent): exact depth-first search over the binary
+//     sequence in time order; states and costs are exact FP64, a node is pruned when
+//     cost so far + LB >= incumbent.  Up to 32 open nodes are expanded per iteration.  The first dive follows
+//     the table and lands on (or next to) the optimum; the rest of the search is the optimality proof.
+// Work: Nt * G cell updates (~25 FP64 operations each) + a few hundred scalar nodes per agent -- against
+// ~10^3..10^5 dense simplex pivots of the general branch-and-cut kernel (milp_bnc.cu) on the same problems.
+#include "common.cuh"
+
+namespace hmpc {
+
+constexpr int kDpThreads = 256;
+constexpr int kDpMaxNb = 4;
+constexpr int kDpMaxAct = 1 << kDpMaxNb;
+constexpr int kDpMaxNc = 8;
+constexpr int kDpMaxNt = 128;
+constexpr int kSearchWarps = 4;
+constexpr int kStackCap = 768;        // open nodes per agent
+constexpr double kEdgeEps = 1e-9;     // cell-boundary guard (fraction of a cell)
+
+struct DpArgs {
+    hmpc_dims d;
+    const double* mats[HMPC_NUM_MATS];
+    int64_t stride[HMPC_NUM_MATS];
+    const double* rhs;                 // [B, Nt*nc]
+    const double* cost; int64_t sc;    // [B|1, Nt*nv]
+    const double* lb; const double* ub;  // [Nt*nv] shared by the batch
+    const uint8_t* is_bin;             // [Nt*nv]
+    hmpc_stage_dp_opts o;
+    int G, nb, nact, nv;
+    float* table;                      // [B, Nt, G]   (stage 0 unused)
+    double* hdr;                       // [B, 8]: S0, w, flags
+    double* v; double* obj; int32_t* status; int32_t* stats;
+};
+
+// per-agent stage data in shared memory (doubles first, then ints)
+struct DpPlan {
+    int ak, cu, qs, rhs, tailmin, e, dscale, galpha, falpha, misc, nd;
+    int amask, ni;
+    size_t bytes;
+};
+
+__host__ __device__ inline DpPlan make_dp_plan(int Nt, int nb, int nc) {
+    DpPlan p;
+    const int nact = 1 << nb;
+    int o = 0;
+    auto take = [&](int n) { int r = o; o += n; return r; };
+    p.ak = take(Nt + 2); p.cu = take(Nt * nb); p.qs = take(Nt * nc); p.rhs = take(Nt * nc); p.tailmin = take(Nt + 1);
+    p.e = take(nc); p.dscale = take(nc); p.galpha = take(nact); p.falpha = take(nc * nact); p.misc = take(8);
+    p.nd = o;
+    p.amask = 0; p.ni = Nt;
+    p.bytes = (size_t)p.nd * 8 + (size_t)((p.ni + 1) & ~1) * 4;
+    return p;
+}
+
+enum { MISC_S0 = 0, MISC_W, MISC_A, MISC_FLAG };
+
+struct DpCtx {
+    int Nt, nb, nc, nact, nmu, nv, G;
+    double *ak, *cu, *qs, *rhs, *tailmin, *e, *dscale, *galpha, *falpha, *misc;
+    int* amask;
+    double feas_tol;
+};
+
+__device__ inline DpCtx bind_ctx(const DpArgs& A, unsigned char* smem) {
+    DpCtx c;
+    c.Nt = A.d.Nt; c.nb = A.nb; c.nc = A.d.nc; c.nact = A.nact; c.nmu = A.d.nmu; c.nv = A.nv; c.G = A.G;
+    const DpPlan p = make_dp_plan(c.Nt, c.nb, c.nc);
+    double* sd = reinterpret_cast<double*>(smem);
+    c.ak = sd + p.ak; c.cu = sd + p.cu; c.qs = sd + p.qs; c.rhs = sd + p.rhs; c.tailmin = sd + p.tailmin;
+    c.e = sd + p.e; c.dscale = sd + p.dscale; c.galpha = sd + p.galpha; c.falpha = sd + p.falpha; c.misc = sd + p.misc;
+    c.amask = reinterpret_cast<int*>(sd + p.nd);
+    c.feas_tol = A.o.feas_tol;
+    return c;
+}
+
+__device__ __forceinline__ const double* mat_of(const DpArgs& A, int which, int b) {
+    return A.mats[which] ? A.mats[which] + (int64_t)b * A.stride[which] : nullptr;
+}
+
+// Cooperative load of one agent's stage data by `nthr` threads (tid in [0, nthr)); `sync` is a barrier over
+// exactly those threads.  On return misc[MISC_FLAG] != 0 marks an agent outside the supported class.
+template <typename Sync>
+__device__ inline void dp_load(const DpArgs& A, int b, DpCtx& c, int tid, int nthr, Sync sync) {
+    const int Nt = c.Nt, nb = c.nb, nc = c.nc, nv = c.nv, nu = A.d.nu, nmu = c.nmu;
+    if (tid == 0) {
+        int flag = 0;
+        const double* Am = mat_of(A, HMPC_A, b);
+        const double a = Am ? Am[0] : 0.0;
+        c.misc[MISC_A] = a;
+        // a^k by running products, like the reference's A_pow_tilde (mld_evolution_matrices.py:266-272)
+        double ap = 1.0;
+        for (int k = 0; k <= Nt + 1; ++k) { c.ak[k] = ap; ap *= a; }
+        if (!(a > 0.0) || !(c.ak[Nt] > 1e-3) || !(c.ak[Nt] < 1e3)) flag = 1;
+        const double* B1 = mat_of(A, HMPC_B1, b); const double* B2 = mat_of(A, HMPC_B2, b);
+        const double* Cm = mat_of(A, HMPC_C, b);
+        const double* D1 = mat_of(A, HMPC_D1, b); const double* D2 = mat_of(A, HMPC_D2, b);
+        const double* E = mat_of(A, HMPC_E, b);
+        const double* F1 = mat_of(A, HMPC_F1, b); const double* F2 = mat_of(A, HMPC_F2, b);
+        const double* Gm = mat_of(A, HMPC_G, b); const double* Psi = mat_of(A, HMPC_Psi, b);
+        const int ny = A.d.ny, nd = A.d.ndelta;
+        double g[kDpMaxNb], f[kDpMaxNc][kDpMaxNb];
+        for (int j = 0; j < nb; ++j) g[j] = j < nu ? (B1 ? B1[j] : 0.0) : (B2 ? B2[j - nu] : 0.0);
+        for (int i = 0; i < nc; ++i) {
+            double ei = E ? E[i] : 0.0;                       // E is [nc, nx = 1]
+            for (int j = 0; j < nb; ++j) f[i][j] = j < nu ? (F1 ? F1[i * nu + j] : 0.0) : (F2 ? F2[i * nd + (j - nu)] : 0.0);
+            if (Gm) for (int r = 0; r < ny; ++r) {            // y = C x + D1 u + D2 delta (+ terms already in rhs)
+                const double gir = Gm[i * ny + r];
+                if (gir == 0.0) continue;
+                ei += gir * (Cm ? Cm[r] : 0.0);
+                for (int j = 0; j < nb; ++j) f[i][j] += gir * (j < nu ? (D1 ? D1[r * nu + j] : 0.0) : (D2 ? D2[r * nd + (j - nu)] : 0.0));
+            }
+            c.e[i] = ei;
+            double di = 0.0;
+            if (nmu) {
+                for (int j = 0; j < nmu; ++j) {
+                    const double pij = Psi ? Psi[i * nmu + j] : 0.0;
+                    if (j == i) di = -pij; else if (pij != 0.0) flag = 1;   // every row owns at most its own slack
+                }
+                if (di < 0.0) flag = 1;
+            }
+            c.dscale[i] = di;
+        }
+        for (int al = 0; al < c.nact; ++al) {
+            double ga = 0.0;
+            for (int j = 0; j < nb; ++j) if (al >> j & 1) ga += g[j];
+            c.galpha[al] = ga;
+            for (int i = 0; i < nc; ++i) {
+                double fa = 0.0;
+                for (int j = 0; j < nb; ++j) if (al >> j & 1) fa += f[i][j];
+                c.falpha[i * c.nact + al] = fa;
+            }
+        }
+        c.misc[MISC_FLAG] = (double)flag;
+    }
+    sync();
+    const double* cost = A.cost + (int64_t)b * A.sc;
+    const double* rhs = A.rhs + (int64_t)b * Nt * nc;
+    int bad = 0;
+    for (int k = tid; k < Nt; k += nthr) {
+        int mask = 0;
+        for (int al = 0; al < c.nact; ++al) {
+            bool ok = true;
+            for (int j = 0; j < nb; ++j) {
+                const double bit = (double)(al >> j & 1);
+                if (bit < A.lb[k * nv + j] || bit > A.ub[k * nv + j]) ok = false;
+            }
+            if (ok) mask |= 1 << al;
+        }
+        c.amask[k] = mask;
+        for (int j = 0; j < nb; ++j) { c.cu[k * nb + j] = cost[k * nv + j]; if (!A.is_bin[k * nv + j]) bad = 1; }
+        for (int i = 0; i < nc; ++i) {
+            c.rhs[k * nc + i] = rhs[k * nc + i];
+            double qs = INFINITY;                                // hard row
+            if (nmu) {
+                const int col = k * nv + nb + i;
+                const double q = cost[col], di = c.dscale[i], ubm = A.ub[col], lbm = A.lb[col];
+                if (A.is_bin[col] || lbm > 0.0 || (lbm < 0.0 && di > 0.0)) bad = 1;
+                if (di > 0.0 && ubm > 0.0) {
+                    if (isfinite(ubm) || q < 0.0) bad = 1;      // bounded or rewarded slack: not this class
+                    qs = q / di;
+                } else if (q < 0.0 && ubm > 0.0) bad = 1;         // free column with negative cost: unbounded
+            }
+            c.qs[k * nc + i] = qs;
+        }
+    }
+    if (bad) c.misc[MISC_FLAG] = 1.0;   // benign race: every writer stores the same value
+    sync();
+    if (tid == 0) {
+        // trivial bound on the cost-to-go from ANY state: the negative action costs that are still ahead
+        c.tailmin[Nt] = 0.0;
+        for (int k = Nt - 1; k >= 0; --k) {
+            double m = INFINITY;
+            for (int al = 0; al < c.nact; ++al) if (c.amask[k] >> al & 1) {
+                double ca = 0.0;
+                for (int j = 0; j < nb; ++j) if (al >> j & 1) ca += c.cu[k * nb + j];
+                m = fmin(m, ca);
+            }
+            c.tailmin[k] = c.tailmin[k + 1] + fmin(m, 0.0);   // m = +inf (no action allowed) -> infeasible later
+        }
+        // grid window in s = p / a^k: hull over the stages of the violation-free band, one max shift of margin,
+        // intersected with what is reachable at all
+        double rlo = 0.0, rhi = 0.0, blo = INFINITY, bhi = -INFINITY, margin = 0.0;
+        for (int k = 0; k < Nt; ++k) {
+            double lo_k = -INFINITY, hi_k = INFINITY;
+            for (int i = 0; i < nc; ++i) {
+                const double ei = c.e[i];
+                if (ei == 0.0) continue;
+                double fmin_a = INFINITY;
+                for (int al = 0; al < c.nact; ++al) if (c.amask[k] >> al & 1) fmin_a = fmin(fmin_a, c.falpha[i * c.nact + al]);
+                if (!isfinite(fmin_a)) fmin_a = 0.0;
+                const double lim = (c.rhs[k * nc + i] - fmin_a) / (ei * c.ak[k]);
+                if (ei > 0.0) hi_k = fmin(hi_k, lim); else lo_k = fmax(lo_k, lim);
+            }
+            // only states reachable at stage k matter
+            const double lo_c = fmin(fmax(lo_k, rlo), rhi), hi_c = fmax(fmin(hi_k, rhi), rlo);
+            blo = fmin(blo, fmin(lo_c, hi_c)); bhi = fmax(bhi, fmax(lo_c, hi_c));
+            double smin = 0.0, smax = 0.0;
+            bool any = false;
+            for (int al = 0; al < c.nact; ++al) if (c.amask[k] >> al & 1) {
+                const double sh = c.galpha[al] / c.ak[k + 1];
+                smin = any ? fmin(smin, sh) : sh; smax = any ? fmax(smax, sh) : sh; any = true;
+                margin = fmax(margin, fabs(sh));
+            }
+            rlo += smin; rhi += smax;
+        }
+        double S0 = fmax(rlo, blo - margin), S1 = fmin(rhi, bhi + margin);
+        if (!(S1 > S0)) { S0 = rlo; S1 = rhi; }
+        double w = (S1 - S0) / (double)c.G;
+        if (!(w > 0.0) || !isfinite(w)) w = 1.0;
+        c.misc[MISC_S0] = S0; c.misc[MISC_W] = w;
+    }
+    sync();
+}
+
+__device__ __forceinline__ double action_cost(const DpCtx& c, int k, int al) {
+    double ca = 0.0;
+    for (int j = 0; j < c.nb; ++j) if (al >> j & 1) ca += c.cu[k * c.nb + j];
+    return ca;
+}
+
+// stage cost of action `al` at stage k, bounded from below over p in [plo, phi] (exact when plo == phi)
+__device__ __forceinline__ double stage_cost(const DpCtx& c, int k, int al, double plo, double phi) {
+    double st = action_cost(c, k, al);
+    for (int i = 0; i < c.nc; ++i) {
+        const double ei = c.e[i];
+        const double viol = fma(ei, ei >= 0.0 ? plo : phi, c.falpha[i * c.nact + al] - c.rhs[k * c.nc + i]);
+        const double qs = c.qs[k * c.nc + i];
+        if (isinf(qs)) { if (viol > c.feas_tol) st = INFINITY; }
+        else st = fma(qs, fmax(viol, 0.0), st);
+    }
+    return st;
+}
+
+// ------------------------------------------------------------------------------------------------ kernel 1
+// per-stage, per-action constants staged in shared memory before the cell loop
+struct StageConst {
+    double ca[kDpMaxAct];                 // action cost
+    double off[kDpMaxNc * kDpMaxAct];     // f_i' alpha - rhs_k,i
+    double q[kDpMaxNc];                   // slack price / d_i (+inf: hard row)
+    int c0[kDpMaxAct];                    // translation of a cell, whole cells
+    int span[kDpMaxAct];                  // 0: identity (exact), else bit0: also c0+1, bit1: also c0-1, bit2: also c0+2
+    int anyhard;
+};
+
+// NC / NACT > 0: compile-time row and action counts (the DEWH shape is <2, 2>); 0: run-time loops.
+template <int NC, int NACT>
+__global__ void __launch_bounds__(1024) stage_dp_table_kernel(const DpArgs A) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ StageConst sc;
+    const int b = blockIdx.x;
+    const int nthr = blockDim.x;
+    DpCtx c = bind_ctx(A, smem);
+    const DpPlan plan = make_dp_plan(c.Nt, c.nb, c.nc);
+    float* buf0 = reinterpret_cast<float*>(smem + ((plan.bytes + 15) & ~(size_t)15));   // [2][G] stages k+1 / k
+    dp_load(A, b, c, threadIdx.x, nthr, [] { __syncthreads(); });
+    const int G = c.G, Nt = c.Nt;
+    const int nc = NC > 0 ? NC : c.nc, nact = NACT > 0 ? NACT : c.nact;
+    if (threadIdx.x == 0) {
+        double* h = A.hdr + (int64_t)b * 8;
+        h[0] = c.misc[MISC_S0]; h[1] = c.misc[MISC_W]; h[2] = c.misc[MISC_FLAG];
+    }
+    if (c.misc[MISC_FLAG] != 0.0) return;
+    const double S0 = c.misc[MISC_S0], w = c.misc[MISC_W];
+    float* tab = A.table + (int64_t)b * Nt * G;
+    float* cur = buf0;            // stage k+1
+    float* nxt = buf0 + G;        // stage k (being written)
+    double e_r[NC > 0 ? NC : kDpMaxNc];
+    for (int i = 0; i < nc; ++i) e_r[i] = c.e[i];
+    for (int k = Nt - 1; k >= 1; --k) {
+        const double akk = c.ak[k];
+        const int mask = c.amask[k];
+        const bool last = (k == Nt - 1);
+        const float out_next = __double2float_rd(c.tailmin[k + 1]);
+        if (threadIdx.x < nact) {
+            const int al = threadIdx.x;
+            sc.ca[al] = action_cost(c, k, al);
+            const double ga = c.galpha[al];
+            int c0 = 0, span = 0;
+            if (ga != 0.0) {
+                const double r = ga / (c.ak[k + 1] * w);   // translation of a cell, in cells
+                const double fl = floor(r), fr = r - fl;
+                c0 = (int)fmax(fmin(fl, 2.0e9), -2.0e9);
+                span = 1 | (fr < kEdgeEps ? 2 : 0) | (fr > 1.0 - kEdgeEps ? 4 : 0);
+            }
+            sc.c0[al] = c0; sc.span[al] = span;
+            for (int i = 0; i < nc; ++i) sc.off[i * nact + al] = c.falpha[i * nact + al] - c.rhs[k * nc + i];
+        }
+        if (threadIdx.x == 32) {
+            int anyhard = 0;
+            for (int i = 0; i < nc; ++i) { const double q = c.qs[k * nc + i]; sc.q[i] = q; if (isinf(q)) anyhard = 1; }
+            sc.anyhard = anyhard;
+        }
+        __syncthreads();
+        const bool anyhard = sc.anyhard != 0;
+        for (int cell = threadIdx.x; cell < G; cell += nthr) {
+            // the cell, widened by a hair so that the bound also holds for states that floating-point
+            // rounding assigns to it from just outside
+            const double slo = fma((double)cell - kEdgeEps, w, S0);
+            const double plo = akk * slo, phi = akk * (slo + (1.0 + 2.0 * kEdgeEps) * w);
+            double ep[NC > 0 ? NC : kDpMaxNc];
+            for (int i = 0; i < nc; ++i) ep[i] = e_r[i] * (e_r[i] >= 0.0 ? plo : phi);
+            double best = INFINITY;
+            for (int al = 0; al < nact; ++al) {
+                if (!(mask >> al & 1)) continue;
+                double st = sc.ca[al];
+                for (int i = 0; i < nc; ++i) {
+                    const double viol = ep[i] + sc.off[i * nact + al];
+                    const double q = sc.q[i];
+                    if (anyhard && isinf(q)) { if (viol > c.feas_tol) st = INFINITY; }
+                    else st = fma(q, fmax(viol, 0.0), st);
+                }
+                if (!last) {
+                    const int span = sc.span[al];
+                    const long long c0 = (long long)cell + sc.c0[al];
+                    auto at = [&](long long i) -> float { return (i < 0 || i >= G) ? out_next : cur[i]; };
+                    float nx = at(c0);
+                    if (span & 1) nx = fminf(nx, at(c0 + 1));
+                    if (span & 2) nx = fminf(nx, at(c0 - 1));
+                    if (span & 4) nx = fminf(nx, at(c0 + 2));
+                    st += (double)nx;
+                }
+                best = fmin(best, st);
+            }
+            const float r32 = __double2float_rd(best);     // rounded DOWN: the stored table stays a lower bound
+            nxt[cell] = r32;
+            tab[(int64_t)k * G + cell] = r32;
+        }
+        __syncthreads();
+        float* t = cur; cur = nxt; nxt = t;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ kernel 2
+struct Node { double s, cost, bound; unsigned long long p0, p1; int k, pad; };
+
+__device__ __forceinline__ void path_set(unsigned long long& p0, unsigned long long& p1, int k, int nb, int al) {
+    const int pos = k * nb;
+    const unsigned long long a = (unsigned long long)al;
+    if (pos < 64) { p0 |= a << pos; if (pos + nb > 64) p1 |= a >> (64 - pos); }
+    else p1 |= a << (pos - 64);
+}
+__device__ __forceinline__ int path_get(unsigned long long p0, unsigned long long p1, int k, int nb) {
+    const int pos = k * nb;
+    unsigned long long a;
+    if (pos < 64) { a = p0 >> pos; if (pos + nb > 64) a |= p1 << (64 - pos); }
+    else a = p1 >> (pos - 64);
+    return (int)(a & ((1ull << nb) - 1ull));
+}
+
+// lower bound of the cost-to-go from exact state s at stage k (table cells are widened by kEdgeEps, so the
+// cell that floor() picks is valid even when s sits on a boundary up to rounding)
+__device__ __forceinline__ double lb_at(const DpCtx& c, const float* tab, int k, double s, double S0, double w) {
+    if (k >= c.Nt) return 0.0;
+    const double fl = floor((s - S0) / w);
+    if (!(fl >= 0.0) || !(fl < (double)c.G)) return c.tailmin[k];
+    return (double)__ldg(tab + (int64_t)k * c.G + (int)fl);
+}
+
+__global__ void __launch_bounds__(kSearchWarps * 32) stage_dp_search_kernel(const DpArgs A) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * kSearchWarps + warp;
+    if (b >= A.d.B) return;
+    const DpPlan plan = make_dp_plan(A.d.Nt, A.nb, A.d.nc);
+    const size_t per_warp = ((plan.bytes + 15) & ~(size_t)15) + sizeof(Node) * kStackCap + 8 * (kDpMaxNt + 1);
+    unsigned char* base = smem + per_warp * warp;
+    DpCtx c = bind_ctx(A, base);
+    Node* stack = reinterpret_cast<Node*>(base + ((plan.bytes + 15) & ~(size_t)15));
+    double* ptraj = reinterpret_cast<double*>(stack + kStackCap);
+    dp_load(A, b, c, lane, 32, [] { __syncwarp(); });
+    const int Nt = c.Nt, nb = c.nb, nc = c.nc, nv = c.nv;
+    double* vout = A.v + (int64_t)b * Nt * nv;
+    int32_t* st_out = A.stats + (int64_t)b * 8;
+    if (c.misc[MISC_FLAG] != 0.0) {
+        for (int j = lane; j < Nt * nv; j += 32) vout[j] = nan("");
+        if (lane == 0) { A.status[b] = HMPC_SOLVE_UNSUPPORTED; A.obj[b] = INFINITY; for (int i = 0; i < 8; ++i) st_out[i] = 0; }
+        return;
+    }
+    const double* hdr = A.hdr + (int64_t)b * 8;
+    const double S0 = hdr[0], w = hdr[1];
+    const double a = c.misc[MISC_A];
+    const float* tab = A.table + (int64_t)b * Nt * c.G;
+
+    double best = INFINITY;
+    unsigned long long bp0 = 0, bp1 = 0;
+    int sp = 0, nodes = 0, improvements = 0, max_sp = 0;
+    bool limit = false;
+    if (lane == 0) { Node r; r.s = 0.0; r.cost = 0.0; r.bound = -INFINITY; r.p0 = r.p1 = 0; r.k = 0; r.pad = 0; stack[0] = r; }
+    sp = 1;
+    __syncwarp();
+    while (sp > 0) {
+        if (nodes >= A.o.max_nodes) { limit = true; break; }
+        const double tol = isfinite(best) ? fmax(1e-11 * fmax(1.0, fabs(best)), A.o.mip_rel_gap * fabs(best)) : 0.0;
+        // when the stack is nearly full fall back to strict depth-first (one node per iteration)
+        // and until the first dive has produced an incumbent there is nothing to prune against: dive first
+        int npop = sp < 32 ? sp : 32;
+        if (sp + 32 * c.nact > kStackCap || !isfinite(best)) npop = 1;
+        if (sp - npop + npop * c.nact > kStackCap) { limit = true; break; }
+        Node nd;
+        bool active = lane < npop;
+        if (active) nd = stack[sp - 1 - lane];
+        sp -= npop;
+        active = active && (nd.bound < best - tol);
+        // expand: children of lane's node, ordered worst-first so that the best child ends up on top
+        double ch_bound[kDpMaxAct], ch_cost[kDpMaxAct], ch_s[kDpMaxAct];
+        int ch_al[kDpMaxAct];
+        int nch = 0;
+        double cand = INFINITY; unsigned long long cp0 = 0, cp1 = 0;
+        if (active) {
+            const int k = nd.k;
+            const double p = c.ak[k] * nd.s;
+            const int mask = c.amask[k];
+            for (int al = 0; al < c.nact; ++al) {
+                if (!(mask >> al & 1)) continue;
+                const double cost2 = nd.cost + stage_cost(c, k, al, p, p);
+                if (!(cost2 < best - tol)) continue;
+                const double s2 = nd.s + c.galpha[al] / c.ak[k + 1];
+                if (k + 1 == Nt) {
+                    if (cost2 < cand) { cand = cost2; cp0 = nd.p0; cp1 = nd.p1; path_set(cp0, cp1, k, nb, al); }
+                    continue;
+                }
+                const double bd = cost2 + lb_at(c, tab, k + 1, s2, S0, w);
+                if (!(bd < best - tol)) continue;
+                // insertion sort, descending bound
+                int pos = nch++;
+                while (pos > 0 && ch_bound[pos - 1] < bd) {
+                    ch_bound[pos] = ch_bound[pos - 1]; ch_cost[pos] = ch_cost[pos - 1]; ch_s[pos] = ch_s[pos - 1];
+                    ch_al[pos] = ch_al[pos - 1]; --pos;
+                }
+                ch_bound[pos] = bd; ch_cost[pos] = cost2; ch_s[pos] = s2; ch_al[pos] = al;
+            }
+        }
+        nodes += __popc(__ballot_sync(0xffffffffu, active));
+        // incumbent update (warp arg-min over the leaf candidates)
+        {
+            double m = cand; int src = lane;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double om = __shfl_xor_sync(0xffffffffu, m, o);
+                const int os = __shfl_xor_sync(0xffffffffu, src, o);
+                if (om < m || (om == m && os < src)) { m = om; src = os; }
+            }
+            if (m < best) {
+                best = m;
+                bp0 = __shfl_sync(0xffffffffu, cp0, src);
+                bp1 = __shfl_sync(0xffffffffu, cp1, src);
+                ++improvements;
+            }
+        }
+        // push: lane 31's children lowest ... lane 0's children on top (lane 0 held the top of the stack)
+        int incl = nch;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_down_sync(0xffffffffu, incl, o);
+            if (lane + o < 32) incl += t;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 0);
+        const int off = sp + (incl - nch);      // children of higher lanes sit below
+        for (int i = 0; i < nch; ++i) {
+            Node ch; ch.s = ch_s[i]; ch.cost = ch_cost[i]; ch.bound = ch_bound[i]; ch.k = nd.k + 1; ch.pad = 0;
+            ch.p0 = nd.p0; ch.p1 = nd.p1; path_set(ch.p0, ch.p1, nd.k, nb, ch_al[i]);
+            stack[off + i] = ch;
+        }
+        sp += total;
+        max_sp = sp > max_sp ? sp : max_sp;
+        __syncwarp();
+    }
+    // ---- write the solution: binaries from the path, mu in closed form along the exact trajectory
+    const bool have = isfinite(best);
+    if (lane == 0 && have) {
+        double p = 0.0;
+        for (int k = 0; k < Nt; ++k) { ptraj[k] = p; p = fma(a, p, c.galpha[path_get(bp0, bp1, k, nb)]); }
+    }
+    __syncwarp();
+    for (int k = lane; k < Nt; k += 32) {
+        double* vk = vout + (int64_t)k * nv;
+        if (!have) { for (int j = 0; j < nv; ++j) vk[j] = nan(""); continue; }
+        const int al = path_get(bp0, bp1, k, nb);
+        for (int j = 0; j < nb; ++j) vk[j] = (double)(al >> j & 1);
+        if (c.nmu) {
+            const double p = ptraj[k];
+            for (int i = 0; i < nc; ++i) {
+                const double viol = fma(c.e[i], p, c.falpha[i * c.nact + al] - c.rhs[k * nc + i]);
+                const double di = c.dscale[i];
+                vk[nb + i] = (di > 0.0 && !isinf(c.qs[k * nc + i])) ? fmax(viol, 0.0) / di : 0.0;
+            }
+        }
+    }
+    if (lane == 0) {
+        A.obj[b] = have ? best : INFINITY;
+        A.status[b] = limit ? HMPC_SOLVE_NODE_LIMIT : (have ? HMPC_SOLVE_OPTIMAL : HMPC_SOLVE_INFEASIBLE);
+        st_out[0] = nodes; st_out[1] = 0; st_out[2] = 0; st_out[3] = c.G; st_out[4] = max_sp; st_out[5] = improvements;
+        st_out[6] = 0;
+        st_out[7] = (int32_t)fmin(((double)(Nt - 1) * c.G * c.nact * (4.0 + 3.0 * nc) + (double)nodes * c.nact * (4.0 + 3.0 * nc)) / 1024.0, 2.0e9);
+    }
+}
+
+static size_t table_bytes(int B, int Nt, int G) { return (size_t)B * Nt * G * sizeof(float); }
+
+}  // namespace hmpc
+
+extern "C" void hmpc_stage_dp_default_opts(hmpc_stage_dp_opts* o) {
+    if (!o) return;
+    o->mip_rel_gap = 0.0; o->feas_tol = 1e-9; o->cells = 8192; o->max_nodes = 4000000;
+}
+
+extern "C" int hmpc_stage_dp_supported(const hmpc_dims* d) {
+    using namespace hmpc;
+    if (!d) return 0;
+    const int nb = d->nu + d->ndelta;
+    if (d->nx != 1 || d->nz != 0 || nb < 1 || nb > kDpMaxNb || d->nc > kDpMaxNc || d->Nt < 1 || d->Nt > kDpMaxNt) return 0;
+    if (d->nmu != 0 && d->nmu != d->nc) return 0;
+    if (nb * d->Nt > 128) return 0;
+    return 1;
+}
+
+extern "C" int hmpc_stage_dp_workspace_bytes(const hmpc_dims* d, const hmpc_stage_dp_opts* opts, size_t* bytes) {
+    using namespace hmpc;
+    if (!d || !bytes || d->B < 0) return HMPC_ERR_ARG;
+    hmpc_stage_dp_opts o;
+    if (opts) o = *opts; else hmpc_stage_dp_default_opts(&o);
+    if (o.cells < 64) return HMPC_ERR_ARG;
+    *bytes = table_bytes(d->B, d->Nt, o.cells) + (size_t)d->B * 8 * sizeof(double) + 256;
+    return HMPC_OK;
+}
+
+extern "C" int hmpc_stage_dp_solve_f64(const hmpc_dims* dims, const double* const mats[HMPC_NUM_MATS],
+                                       const int64_t mat_stride_b[HMPC_NUM_MATS], const double* rhs,
+                                       const double* cost_v, int64_t cost_v_stride_b, const double* lb_v,
+                                       const double* ub_v, const uint8_t* is_bin_v, const hmpc_stage_dp_opts* opts,
+                                       void* workspace, size_t workspace_bytes, double* v, double* obj,
+                                       int32_t* status, int32_t* stats, void* stream) {
+    using namespace hmpc;
+    if (!dims || !mats || !mat_stride_b || !cost_v || !lb_v || !ub_v || !is_bin_v || !v || !obj || !status || !stats)
+        return HMPC_ERR_ARG;
+    if (!hmpc_stage_dp_supported(dims)) return HMPC_ERR_ARG;
+    if (dims->nc > 0 && !rhs) return HMPC_ERR_ARG;
+    if (dims->B == 0) return HMPC_OK;
+    DpArgs a;
+    a.d = *dims;
+    for (int i = 0; i < HMPC_NUM_MATS; ++i) { a.mats[i] = mats[i]; a.stride[i] = mat_stride_b[i]; }
+    if (opts) a.o = *opts; else hmpc_stage_dp_default_opts(&a.o);
+    if (a.o.cells < 64) return HMPC_ERR_ARG;
+    a.G = a.o.cells; a.nb = dims->nu + dims->ndelta; a.nact = 1 << a.nb; a.nv = a.nb + dims->nmu;
+    a.rhs = rhs; a.cost = cost_v; a.sc = cost_v_stride_b; a.lb = lb_v; a.ub = ub_v; a.is_bin = is_bin_v;
+    size_t need = 0;
+    hmpc_stage_dp_workspace_bytes(dims, &a.o, &need);
+    if (!workspace || workspace_bytes < need) return HMPC_ERR_WORKSPACE;
+    a.table = reinterpret_cast<float*>(workspace);
+    a.hdr = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(workspace) + ((table_bytes(dims->B, dims->Nt, a.G) + 255) & ~(size_t)255));
+    a.v = v; a.obj = obj; a.status = status; a.stats = stats;
+    const DpPlan plan = make_dp_plan(dims->Nt, a.nb, dims->nc);
+    const size_t plan_b = (plan.bytes + 15) & ~(size_t)15;
+    const size_t smem1 = plan_b + 2 * (size_t)a.G * sizeof(float);
+    const size_t smem2 = (plan_b + sizeof(Node) * kStackCap + 8 * (kDpMaxNt + 1)) * kSearchWarps;
+    int dev = 0, smem_optin = 0;
+    HMPC_CUDA_TRY(cudaGetDevice(&dev));
+    HMPC_CUDA_TRY(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    if (smem1 > (size_t)smem_optin || smem2 > (size_t)smem_optin) return HMPC_ERR_ARG;
+    auto table_kernel = (dims->nc == 2 && a.nact == 2) ? stage_dp_table_kernel<2, 2> : stage_dp_table_kernel<0, 0>;
+    HMPC_CUDA_TRY(cudaFuncSetAttribute(table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+    HMPC_CUDA_TRY(cudaFuncSetAttribute(stage_dp_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    cudaStream_t s = (cudaStream_t)stream;
+    // few agents: one fat CTA per SM hides the FP64 latency; many agents: several thin CTAs share an SM
+    const int table_threads = dims->B <= 2 * kNumSM ? 1024 : kDpThreads;
+    table_kernel<<<dims->B, table_threads, smem1, s>>>(a);
+    HMPC_LAUNCH_CHECK("stage_dp_table_kernel");
+    stage_dp_search_kernel<<<ceil_div(dims->B, kSearchWarps), kSearchWarps * 32, smem2, s>>>(a);
+    HMPC_LAUNCH_CHECK("stage_dp_search_kernel");
+    return HMPC_OK;
+}
