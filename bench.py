@@ -44,6 +44,9 @@ def parse_args():
     ap.add_argument("--np", dest="N_p", type=int, default=48)
     ap.add_argument("--cpu-sample", type=int, default=64, help="agent-solves timed for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--solver", default="auto", choices=("auto", "bnc", "stage_dp"),
+                    help="auto = exact stage-DP kernels for the scalar-state DEWH class, bnc = general branch-and-cut")
+    ap.add_argument("--cells", type=int, default=0, help="stage-DP value-table cells per stage (0 = library default)")
     return ap.parse_args()
 
 
@@ -187,6 +190,8 @@ def main_ours(args):
             cost=torch.as_tensor(cost.reshape(B, -1)).to(dev), host=wl, host_cost=cost.reshape(B, -1)))
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
     names = ("condense", "rhs", "solve", "sim", "aggregate")
+    use_dp = args.solver == "stage_dp" or (args.solver == "auto" and fleet.batch.stage_dp_ok)
+    dp_opts = cabi.stage_dp_default_opts(**({"cells": args.cells} if args.cells else {}))
     kernel_ms = {k: 0.0 for k in names}
     solve_stats = []
 
@@ -201,7 +206,12 @@ def main_ours(args):
         if ev:
             ev[2].record()
         lb, ub, isb = fleet.batch._bounds_dev()
-        v, obj, status, stats = cabi.milp_solve(inp["cost"], fleet.batch.evo["H_v"], rhs, lb, ub, isb, fleet.batch.opts)
+        if use_dp:
+            v, obj, status, stats = cabi.stage_dp_solve(fleet.batch.dims, fleet.batch.mats, rhs, inp["cost"], lb, ub, isb,
+                                                        dp_opts)
+        else:
+            v, obj, status, stats = cabi.milp_solve(inp["cost"], fleet.batch.evo["H_v"], rhs, lb, ub, isb,
+                                                    fleet.batch.opts)
         if ev:
             ev[3].record()
         u = v.view(B, Nt, 3)[:, :, 0]
@@ -259,7 +269,7 @@ def main_ours(args):
     value = world * B * K / (total_ms * 1e-3)
 
     # ---- e2e: host buffers through hmpc_mpc_step_host_f64 (numpy in, numpy out, copies inside the timed region)
-    plan = cabi.StepPlan(fleet.batch.dims, fleet.batch.opts)
+    plan = cabi.StepPlan(fleet.batch.dims, cabi.default_opts(reserved=0 if use_dp else 1))
     hmats = dict(wl0["mats"])
     hmats["C"] = np.ones((1, 1, 1))
     e2e_times = []
@@ -308,25 +318,35 @@ def main_ours(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
+        "dtype": "f64", "data": "synthetic", "config": dict(workload_config(args, world), solver="stage_dp" if use_dp else "bnc"),
         "latency_p50_ms": float(np.median(step_ms)), "latency_max_ms": float(np.max(step_ms)),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": 1e3 * e2e_total / K, "api": "hmpc_mpc_step_host_f64 via cabi.StepPlan.step"},
         "gpu_launches": int(launches),
         "kernel_ms_per_step": {k: v / K for k, v in kernel_ms.items()},
-        "roofline": {"kernel": "milp_bnc_kernel", "bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak,
-                     "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak if fp64_peak else None, "traffic": None,
+        "roofline": {"kernel": "stage_dp_table_kernel + stage_dp_search_kernel" if use_dp else "milp_bnc_kernel",
+                     "bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak,
+                     "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak if fp64_peak else None,
+                     "traffic": (B * (Nt - 1) * dp_opts.cells * 4) if use_dp else None,
                      "peak_source": "hmpc_fp64_peak_probe (DFMA micro-benchmark, measured in this run)",
                      "share_of_step": solve_ms / (total_ms / K),
-                     "note": "latency-bound tree search: algorithmic FMAs (pivots, row transforms) counted by the "
-                             "kernel itself; SURVEY 8(d) names FP64 pipe / latency, not HBM, as the bound"},
+                     "note": ("value-table sweep + exact search: algorithmic FP64 FMAs counted by the kernels "
+                              "(cells x actions x (4 + 3 rows)); `traffic` = FP32 table bytes streamed to HBM per "
+                              "launch (hbm_write_gbs below); SURVEY 8(d) names the FP64 pipe / latency, not HBM, "
+                              "as the bound of the solve") if use_dp else
+                             ("latency-bound tree search: algorithmic FMAs (pivots, row transforms) counted by the "
+                              "kernel itself; SURVEY 8(d) names FP64 pipe / latency, not HBM, as the bound"),
+                     "hbm_write_gbs": (B * (Nt - 1) * dp_opts.cells * 4 / (solve_ms * 1e-3) / 1e9) if use_dp else None},
         "roofline_condense": {"kernel": "condense_kernel", "bound": "hbm", "achieved": cond_bytes / (cond_ms * 1e-3) / 1e9,
                               "peak": hbm_peak, "unit": "GB/s",
                               "frac": cond_bytes / (cond_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
                               "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                               "bytes_per_launch": cond_bytes},
-        "solver": {"not_optimal": not_opt, "pivots_mean": float(piv.mean()), "pivots_p50": float(np.median(piv)),
-                   "pivots_max": int(piv.max())},
+        "solver": ({"kernel": "stage_dp", "cells": int(dp_opts.cells), "not_optimal": not_opt,
+                    "nodes_mean": float(np.concatenate([x[:, 0] for x in solve_stats]).mean()),
+                    "nodes_max": int(np.concatenate([x[:, 0] for x in solve_stats]).max())} if use_dp else
+                   {"kernel": "bnc", "not_optimal": not_opt, "pivots_mean": float(piv.mean()),
+                    "pivots_p50": float(np.median(piv)), "pivots_max": int(piv.max())}),
         "wall_s_timed_region": t_wall,
         "clocks": sampler.summary(),
     }

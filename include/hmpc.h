@@ -121,7 +121,7 @@ typedef struct {
     int32_t cut_rounds_root; /* default 30                                                              */
     int32_t cut_rounds_node; /* default 2                                                               */
     int32_t cuts_per_round;  /* default 8                                                               */
-    int32_t reserved;
+    int32_t reserved;        /* host front door only: 1 = always use this kernel, never the stage-DP path   */
 } hmpc_milp_opts;
 
 void hmpc_milp_default_opts(hmpc_milp_opts* opts);
@@ -195,7 +195,9 @@ int hmpc_aggregate_power_f64(int32_t B, int32_t Nt, const double* u, int64_t u_s
  *      (controllers/mpc_controller.py:76-101, controllers/controller_base.py:491-540) with Linear cost atoms.
  *  All pointers are HOST memory.  The plan owns the device buffers, pinned staging and a stream; the call
  *  copies the inputs host->device, runs K1 (only when `recondense` != 0) -> K2 -> K3/K4, copies the results
- *  device->host and returns after they have landed.
+ *  device->host and returns after they have landed.  K3/K4 is hmpc_stage_dp_solve_f64 when the MLD is in its
+ *  class (falling back to hmpc_milp_solve_f64 if an agent reports HMPC_SOLVE_UNSUPPORTED), else
+ *  hmpc_milp_solve_f64.
  *    mats/strides : as hmpc_condense_f64 (ignored when recondense == 0)
  *    x0 [B,nx], w [B,nomega*Nt], cost_v [B or 1, nv*Nt] (stride 0 = broadcast): linear cost on v~
  *    lb_v, ub_v [nv*Nt] (+-inf allowed), is_bin_v [nv*Nt]: shared by the batch
@@ -208,6 +210,8 @@ int hmpc_mpc_step_host_f64(hmpc_step_plan* plan, int32_t recondense, const doubl
                            const double* cost_v, int64_t cost_v_stride_b, const double* lb_v, const double* ub_v,
                            const uint8_t* is_bin_v, double* v, double* obj, int32_t* status, int32_t* stats,
                            float* timing_ms);
+/* which solve kernels the last call used: 0 = hmpc_milp_solve_f64, 1 = hmpc_stage_dp_solve_f64 */
+int hmpc_step_plan_last_solver(const hmpc_step_plan* plan);
 /* bytes moved per step by the call above: {host->device, device->host} */
 int hmpc_mpc_step_host_bytes(const hmpc_step_plan* plan, int32_t recondense, int64_t* h2d, int64_t* d2h);
 

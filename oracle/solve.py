@@ -22,8 +22,12 @@ from scipy.optimize import Bounds, LinearConstraint, linprog, milp
 OPTIMAL, INFEASIBLE, LIMIT = 0, 1, 2
 
 
-def solve_milp(prob, mip_rel_gap=0.0, time_limit=None):
-    """-> (status, objective, v).  Requires prob.P is None."""
+def solve_milp(prob, mip_rel_gap=0.0, time_limit=None, polish=False):
+    """-> (status, objective, v).  Requires prob.P is None.
+
+    polish=True re-solves the continuous part with the binaries fixed at HiGHS' decisions and 1e-10 feasibility
+    tolerances: HiGHS' MIP answer is only accurate to its 1e-6/1e-7 primal tolerance times the largest cost
+    coefficient (the slack penalties here), which is of the order of the 1e-6 parity bar."""
     assert prob.P is None or not np.any(prob.P)
     cons = [LinearConstraint(prob.H, -np.inf, prob.rhs)] if prob.H.shape[0] else []
     opts = {"mip_rel_gap": mip_rel_gap, "presolve": True}
@@ -34,6 +38,11 @@ def solve_milp(prob, mip_rel_gap=0.0, time_limit=None):
     if res.status == 0:
         v = np.array(res.x)
         v[prob.is_bin] = np.round(v[prob.is_bin])
+        if polish and mip_rel_gap == 0.0:
+            obj2, v2 = _continuous_subproblem(prob, v[prob.is_bin])
+            if v2 is not None:
+                v2[prob.is_bin] = v[prob.is_bin]
+                return OPTIMAL, obj2, v2
         return OPTIMAL, float(res.fun + prob.c0), v
     if res.status == 2:
         return INFEASIBLE, np.inf, None
@@ -47,7 +56,8 @@ def _continuous_subproblem(prob, bin_vals):
     ub[prob.is_bin] = bin_vals
     if prob.P is None or not np.any(prob.P):
         res = linprog(prob.c, A_ub=prob.H if prob.H.shape[0] else None, b_ub=prob.rhs if prob.H.shape[0] else None,
-                      bounds=np.c_[lb, ub], method="highs")
+                      bounds=np.c_[lb, ub], method="highs",
+                      options={"primal_feasibility_tolerance": 1e-10, "dual_feasibility_tolerance": 1e-10})
         if res.status != 0:
             return np.inf, None
         return float(res.fun + prob.c0), np.array(res.x)

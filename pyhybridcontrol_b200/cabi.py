@@ -23,6 +23,7 @@ EXPORTS = ("hmpc_version", "hmpc_last_cuda_error", "hmpc_device_info", "hmpc_con
            "hmpc_stage_dp_supported", "hmpc_stage_dp_workspace_bytes", "hmpc_stage_dp_solve_f64", "hmpc_lsim_step_f64",
            "hmpc_dewh_sim_step_f64", "hmpc_dewh_control_model_f64", "hmpc_aggregate_power_f64",
            "hmpc_step_plan_create", "hmpc_step_plan_destroy", "hmpc_mpc_step_host_f64", "hmpc_mpc_step_host_bytes",
+           "hmpc_step_plan_last_solver",
            "hmpc_fp64_peak_probe")
 
 SOLVE_STATUS = {0: "optimal", 1: "infeasible", 2: "node_limit", 3: "iter_limit", 4: "numeric", 5: "unsupported"}
@@ -92,6 +93,7 @@ _lib.hmpc_step_plan_destroy.argtypes = [_P]
 _lib.hmpc_mpc_step_host_f64.argtypes = [_P, C.c_int32, _MatArr, _StrideArr, _P, _P, _P, C.c_int64, _P, _P, _P,
                                         _P, _P, _P, _P, _P]
 _lib.hmpc_mpc_step_host_bytes.argtypes = [_P, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+_lib.hmpc_step_plan_last_solver.argtypes = [_P]
 _lib.hmpc_fp64_peak_probe.argtypes = [C.POINTER(C.c_double), _P]
 
 # number of kernel launches issued through this binding (bench.py reports it as gpu_launches)
@@ -436,7 +438,8 @@ class StepPlan(object):
                                            is_bin_v.ctypes.data, self.v.ctypes.data, self.obj.ctypes.data,
                                            self.status.ctypes.data, self.stats.ctypes.data, self.timing),
                "hmpc_mpc_step_host_f64")
-        launch_count += 3 if recondense else 2
+        self.last_solver = ("bnc", "stage_dp")[max(0, _lib.hmpc_step_plan_last_solver(self._h))]
+        launch_count += (1 if recondense else 0) + 1 + (2 if self.last_solver == "stage_dp" else 1)
         return self.v, self.obj, self.status, self.stats, tuple(self.timing)
 
     def close(self):

@@ -25,6 +25,13 @@ struct hmpc_step_plan {
     int32_t* pin_iout;
     uint8_t* pin_bin;
     bool condensed;
+    // exact stage-DP path (stage_dp.cu) for scalar-state MLDs; the branch-and-cut kernel is the general path
+    bool dp_dims_ok;
+    hmpc_stage_dp_opts dp_opts;
+    void* dp_ws; size_t dp_ws_bytes;
+    const double* dev_mats[HMPC_NUM_MATS];
+    int64_t dev_stride[HMPC_NUM_MATS];
+    int32_t last_solver;   // 0 = branch and cut, 1 = stage DP
 };
 
 namespace {
@@ -86,6 +93,12 @@ extern "C" int hmpc_step_plan_create(const hmpc_dims* dims, const hmpc_milp_opts
     HMPC_CUDA_TRY(cudaMallocHost((void**)&p->pin_out, sizeof(double) * p->pin_out_elems));
     HMPC_CUDA_TRY(cudaMallocHost((void**)&p->pin_iout, sizeof(int32_t) * (size_t)B * 9));
     HMPC_CUDA_TRY(cudaMallocHost((void**)&p->pin_bin, (size_t)(p->nvt > 0 ? p->nvt : 1)));
+    hmpc_stage_dp_default_opts(&p->dp_opts);
+    p->dp_dims_ok = hmpc_stage_dp_supported(dims) != 0;
+    if (p->dp_dims_ok) {
+        if (hmpc_stage_dp_workspace_bytes(dims, &p->dp_opts, &p->dp_ws_bytes) != HMPC_OK) return HMPC_ERR_ARG;
+        HMPC_CUDA_TRY(cudaMalloc(&p->dp_ws, p->dp_ws_bytes));
+    }
     *out = p;
     return HMPC_OK;
 }
@@ -95,13 +108,15 @@ extern "C" int hmpc_step_plan_destroy(hmpc_step_plan* p) {
     cudaStreamSynchronize(p->stream);
     double* dbl[] = {p->mats_dev, p->H_x, p->H_v, p->H_w, p->H_5, p->x0, p->w, p->rhs, p->cost, p->lb, p->ub, p->v, p->obj};
     for (double* q : dbl) cudaFree(q);
-    cudaFree(p->status); cudaFree(p->stats); cudaFree(p->is_bin);
+    cudaFree(p->status); cudaFree(p->stats); cudaFree(p->is_bin); cudaFree(p->dp_ws);
     cudaFreeHost(p->pin_in); cudaFreeHost(p->pin_out); cudaFreeHost(p->pin_iout); cudaFreeHost(p->pin_bin);
     for (int i = 0; i < 4; ++i) cudaEventDestroy(p->ev[i]);
     cudaStreamDestroy(p->stream);
     delete p;
     return HMPC_OK;
 }
+
+extern "C" int hmpc_step_plan_last_solver(const hmpc_step_plan* p) { return p ? p->last_solver : -1; }
 
 extern "C" int hmpc_mpc_step_host_bytes(const hmpc_step_plan* p, int32_t recondense, int64_t* h2d, int64_t* d2h) {
     if (!p) return HMPC_ERR_ARG;
@@ -130,8 +145,8 @@ extern "C" int hmpc_mpc_step_host_f64(hmpc_step_plan* p, int32_t recondense, con
     double* pin = p->pin_in;
     size_t off = 0;
     HMPC_CUDA_TRY(cudaEventRecord(p->ev[0], s));
-    const double* dev_mats[HMPC_NUM_MATS];
-    int64_t dev_stride[HMPC_NUM_MATS];
+    const double** dev_mats = p->dev_mats;
+    int64_t* dev_stride = p->dev_stride;
     if (recondense) {
         for (int i = 0; i < HMPC_NUM_MATS; ++i) {
             const int64_t e = p->mat_elems[i];
@@ -178,17 +193,44 @@ extern "C" int hmpc_mpc_step_host_f64(hmpc_step_plan* p, int32_t recondense, con
     }
     rc = hmpc_constraint_rhs_f64(&d, p->mrows, p->H_x, p->H_w, p->H_5, p->x0, p->w, 0, p->rhs, s);
     if (rc != HMPC_OK) return rc;
-    rc = hmpc_milp_solve_f64(d.B, p->nvt, p->mrows, p->cost, bc ? 0 : p->nvt, p->H_v, (int64_t)p->mrows * p->nvt, p->rhs,
-                             p->lb, p->ub, 0, p->is_bin, &p->opts, nullptr, 0, p->v, p->obj, p->status, p->stats, s);
+    auto solve_bnc = [&]() -> int {
+        p->last_solver = 0;
+        return hmpc_milp_solve_f64(d.B, p->nvt, p->mrows, p->cost, bc ? 0 : p->nvt, p->H_v, (int64_t)p->mrows * p->nvt,
+                                   p->rhs, p->lb, p->ub, 0, p->is_bin, &p->opts, nullptr, 0, p->v, p->obj, p->status,
+                                   p->stats, s);
+    };
+    auto fetch = [&]() -> int {
+        HMPC_CUDA_TRY(cudaEventRecord(p->ev[2], s));
+        HMPC_CUDA_TRY(cudaMemcpyAsync(p->pin_out, p->v, sizeof(double) * (size_t)(B * p->nvt), cudaMemcpyDeviceToHost, s));
+        HMPC_CUDA_TRY(cudaMemcpyAsync(p->pin_out + B * p->nvt, p->obj, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, s));
+        HMPC_CUDA_TRY(cudaMemcpyAsync(p->pin_iout, p->status, sizeof(int32_t) * (size_t)B, cudaMemcpyDeviceToHost, s));
+        HMPC_CUDA_TRY(cudaMemcpyAsync(p->pin_iout + B, p->stats, sizeof(int32_t) * (size_t)B * 8, cudaMemcpyDeviceToHost, s));
+        HMPC_CUDA_TRY(cudaEventRecord(p->ev[3], s));
+        HMPC_CUDA_TRY(cudaStreamSynchronize(s));
+        return HMPC_OK;
+    };
+    if (p->dp_dims_ok && p->opts.reserved == 0) {
+        // scalar-state class: exact stage-DP kernels straight from the MLD blocks (H_v is not read)
+        p->last_solver = 1;
+        rc = hmpc_stage_dp_solve_f64(&d, dev_mats, dev_stride, p->rhs, p->cost, bc ? 0 : p->nvt, p->lb, p->ub, p->is_bin,
+                                     &p->dp_opts, p->dp_ws, p->dp_ws_bytes, p->v, p->obj, p->status, p->stats, s);
+    } else {
+        rc = solve_bnc();
+    }
     if (rc != HMPC_OK) return rc;
-    HMPC_CUDA_TRY(cudaEventRecord(p->ev[2], s));
     // ---- device -> host
-    HMPC_CUDA_TRY(cudaMemcpyAsync(p->pin_out, p->v, sizeof(double) * (size_t)(B * p->nvt), cudaMemcpyDeviceToHost, s));
-    HMPC_CUDA_TRY(cudaMemcpyAsync(p->pin_out + B * p->nvt, p->obj, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, s));
-    HMPC_CUDA_TRY(cudaMemcpyAsync(p->pin_iout, p->status, sizeof(int32_t) * (size_t)B, cudaMemcpyDeviceToHost, s));
-    HMPC_CUDA_TRY(cudaMemcpyAsync(p->pin_iout + B, p->stats, sizeof(int32_t) * (size_t)B * 8, cudaMemcpyDeviceToHost, s));
-    HMPC_CUDA_TRY(cudaEventRecord(p->ev[3], s));
-    HMPC_CUDA_TRY(cudaStreamSynchronize(s));
+    rc = fetch();
+    if (rc != HMPC_OK) return rc;
+    if (p->last_solver == 1) {
+        bool unsupported = false;
+        for (int64_t b = 0; b < B; ++b) if (p->pin_iout[b] == HMPC_SOLVE_UNSUPPORTED) unsupported = true;
+        if (unsupported) {   // some agent's matrices are outside the class: the general kernel takes the batch
+            rc = solve_bnc();
+            if (rc != HMPC_OK) return rc;
+            rc = fetch();
+            if (rc != HMPC_OK) return rc;
+        }
+    }
     memcpy(v, p->pin_out, sizeof(double) * (size_t)(B * p->nvt));
     memcpy(obj, p->pin_out + B * p->nvt, sizeof(double) * (size_t)B);
     memcpy(status, p->pin_iout, sizeof(int32_t) * (size_t)B);

@@ -51,15 +51,16 @@ struct DpArgs {
     hmpc_stage_dp_opts o;
     int G, nb, nact, nv;
     float* table;                      // [B, Nt, G]   (stage 0 unused)
-    double* hdr;                       // [B, 8]: S0, w, flags
+    double* pblk;                      // [B, plan doubles]: the agent's stage data, handed from kernel 1 to kernel 2
     double* v; double* obj; int32_t* status; int32_t* stats;
 };
 
-// per-agent stage data in shared memory (doubles first, then ints)
+// per-agent stage data in shared memory (all doubles; amask is stored as doubles too so that the block can be
+// handed to the search kernel with one coalesced copy)
 struct DpPlan {
-    int ak, cu, qs, rhs, tailmin, e, dscale, galpha, falpha, misc, nd;
-    int amask, ni;
-    size_t bytes;
+    int ak, iak, cu, qs, rhs, tailmin, amask, e, dscale, galpha, falpha, misc, nd;   // persistent part
+    int scr;                                                                      // load-time scratch [6*Nt]
+    int total;
 };
 
 __host__ __device__ inline DpPlan make_dp_plan(int Nt, int nb, int nc) {
@@ -67,20 +68,22 @@ __host__ __device__ inline DpPlan make_dp_plan(int Nt, int nb, int nc) {
     const int nact = 1 << nb;
     int o = 0;
     auto take = [&](int n) { int r = o; o += n; return r; };
-    p.ak = take(Nt + 2); p.cu = take(Nt * nb); p.qs = take(Nt * nc); p.rhs = take(Nt * nc); p.tailmin = take(Nt + 1);
-    p.e = take(nc); p.dscale = take(nc); p.galpha = take(nact); p.falpha = take(nc * nact); p.misc = take(8);
-    p.nd = o;
-    p.amask = 0; p.ni = Nt;
-    p.bytes = (size_t)p.nd * 8 + (size_t)((p.ni + 1) & ~1) * 4;
+    p.misc = take(8);
+    p.ak = take(Nt + 2); p.iak = take(Nt + 2); p.cu = take(Nt * nb); p.qs = take(Nt * nc); p.rhs = take(Nt * nc);
+    p.tailmin = take(Nt + 1); p.amask = take(Nt);
+    p.e = take(nc); p.dscale = take(nc); p.galpha = take(nact); p.falpha = take(nc * nact);
+    p.nd = (o + 1) & ~1;
+    o = p.nd;
+    p.scr = take(6 * Nt);
+    p.total = (o + 1) & ~1;
     return p;
 }
 
-enum { MISC_S0 = 0, MISC_W, MISC_A, MISC_FLAG };
+enum { MISC_S0 = 0, MISC_W, MISC_A, MISC_FLAG, MISC_INVW };
 
 struct DpCtx {
     int Nt, nb, nc, nact, nmu, nv, G;
-    double *ak, *cu, *qs, *rhs, *tailmin, *e, *dscale, *galpha, *falpha, *misc;
-    int* amask;
+    double *ak, *iak, *cu, *qs, *rhs, *tailmin, *amask, *e, *dscale, *galpha, *falpha, *misc, *scr;
     double feas_tol;
 };
 
@@ -89,9 +92,9 @@ __device__ inline DpCtx bind_ctx(const DpArgs& A, unsigned char* smem) {
     c.Nt = A.d.Nt; c.nb = A.nb; c.nc = A.d.nc; c.nact = A.nact; c.nmu = A.d.nmu; c.nv = A.nv; c.G = A.G;
     const DpPlan p = make_dp_plan(c.Nt, c.nb, c.nc);
     double* sd = reinterpret_cast<double*>(smem);
-    c.ak = sd + p.ak; c.cu = sd + p.cu; c.qs = sd + p.qs; c.rhs = sd + p.rhs; c.tailmin = sd + p.tailmin;
-    c.e = sd + p.e; c.dscale = sd + p.dscale; c.galpha = sd + p.galpha; c.falpha = sd + p.falpha; c.misc = sd + p.misc;
-    c.amask = reinterpret_cast<int*>(sd + p.nd);
+    c.ak = sd + p.ak; c.iak = sd + p.iak; c.cu = sd + p.cu; c.qs = sd + p.qs; c.rhs = sd + p.rhs;
+    c.tailmin = sd + p.tailmin; c.amask = sd + p.amask; c.e = sd + p.e; c.dscale = sd + p.dscale;
+    c.galpha = sd + p.galpha; c.falpha = sd + p.falpha; c.misc = sd + p.misc; c.scr = sd + p.scr;
     c.feas_tol = A.o.feas_tol;
     return c;
 }
@@ -100,11 +103,11 @@ __device__ __forceinline__ const double* mat_of(const DpArgs& A, int which, int 
     return A.mats[which] ? A.mats[which] + (int64_t)b * A.stride[which] : nullptr;
 }
 
-// Cooperative load of one agent's stage data by `nthr` threads (tid in [0, nthr)); `sync` is a barrier over
-// exactly those threads.  On return misc[MISC_FLAG] != 0 marks an agent outside the supported class.
-template <typename Sync>
-__device__ inline void dp_load(const DpArgs& A, int b, DpCtx& c, int tid, int nthr, Sync sync) {
-    const int Nt = c.Nt, nb = c.nb, nc = c.nc, nv = c.nv, nu = A.d.nu, nmu = c.nmu;
+// Block-cooperative load of one agent's stage data (table kernel).  On return misc[MISC_FLAG] != 0 marks an
+// agent outside the supported class.
+__device__ inline void dp_load(const DpArgs& A, int b, DpCtx& c) {
+    const int Nt = c.Nt, nb = c.nb, nc = c.nc, nv = c.nv, nu = A.d.nu, nmu = c.nmu, nact = c.nact;
+    const int tid = threadIdx.x, nthr = blockDim.x;
     if (tid == 0) {
         int flag = 0;
         const double* Am = mat_of(A, HMPC_A, b);
@@ -143,25 +146,29 @@ __device__ inline void dp_load(const DpArgs& A, int b, DpCtx& c, int tid, int nt
             }
             c.dscale[i] = di;
         }
-        for (int al = 0; al < c.nact; ++al) {
+        for (int al = 0; al < nact; ++al) {
             double ga = 0.0;
             for (int j = 0; j < nb; ++j) if (al >> j & 1) ga += g[j];
             c.galpha[al] = ga;
             for (int i = 0; i < nc; ++i) {
                 double fa = 0.0;
                 for (int j = 0; j < nb; ++j) if (al >> j & 1) fa += f[i][j];
-                c.falpha[i * c.nact + al] = fa;
+                c.falpha[i * nact + al] = fa;
             }
         }
         c.misc[MISC_FLAG] = (double)flag;
     }
-    sync();
+    __syncthreads();
+    // ---- per-stage data, one stage per thread
     const double* cost = A.cost + (int64_t)b * A.sc;
     const double* rhs = A.rhs + (int64_t)b * Nt * nc;
+    double* s_lo = c.scr; double* s_hi = c.scr + Nt; double* s_smin = c.scr + 2 * Nt; double* s_smax = c.scr + 3 * Nt;
+    double* s_cmin = c.scr + 4 * Nt; double* s_marg = c.scr + 5 * Nt;
     int bad = 0;
+    for (int k = tid; k <= Nt + 1; k += nthr) c.iak[k] = 1.0 / c.ak[k];
     for (int k = tid; k < Nt; k += nthr) {
         int mask = 0;
-        for (int al = 0; al < c.nact; ++al) {
+        for (int al = 0; al < nact; ++al) {
             bool ok = true;
             for (int j = 0; j < nb; ++j) {
                 const double bit = (double)(al >> j & 1);
@@ -169,7 +176,7 @@ __device__ inline void dp_load(const DpArgs& A, int b, DpCtx& c, int tid, int nt
             }
             if (ok) mask |= 1 << al;
         }
-        c.amask[k] = mask;
+        c.amask[k] = (double)mask;
         for (int j = 0; j < nb; ++j) { c.cu[k * nb + j] = cost[k * nv + j]; if (!A.is_bin[k * nv + j]) bad = 1; }
         for (int i = 0; i < nc; ++i) {
             c.rhs[k * nc + i] = rhs[k * nc + i];
@@ -185,54 +192,52 @@ __device__ inline void dp_load(const DpArgs& A, int b, DpCtx& c, int tid, int nt
             }
             c.qs[k * nc + i] = qs;
         }
+        // shifts, cheapest action, violation-free band of this stage (all in s = p / a^k)
+        const double ik = 1.0 / c.ak[k], ik1 = 1.0 / c.ak[k + 1];
+        double smin = 0.0, smax = 0.0, cmin = INFINITY, marg = 0.0;
+        bool any = false;
+        for (int al = 0; al < nact; ++al) if (mask >> al & 1) {
+            const double sh = c.galpha[al] * ik1;
+            smin = any ? fmin(smin, sh) : sh; smax = any ? fmax(smax, sh) : sh; any = true;
+            marg = fmax(marg, fabs(sh));
+            double ca = 0.0;
+            for (int j = 0; j < nb; ++j) if (al >> j & 1) ca += cost[k * nv + j];
+            cmin = fmin(cmin, ca);
+        }
+        double lo_k = -INFINITY, hi_k = INFINITY;
+        for (int i = 0; i < nc; ++i) {
+            const double ei = c.e[i];
+            if (ei == 0.0) continue;
+            double fmin_a = INFINITY;
+            for (int al = 0; al < nact; ++al) if (mask >> al & 1) fmin_a = fmin(fmin_a, c.falpha[i * nact + al]);
+            if (!isfinite(fmin_a)) fmin_a = 0.0;
+            const double lim = (rhs[k * nc + i] - fmin_a) / ei * ik;
+            if (ei > 0.0) hi_k = fmin(hi_k, lim); else lo_k = fmax(lo_k, lim);
+        }
+        s_lo[k] = lo_k; s_hi[k] = hi_k; s_smin[k] = smin; s_smax[k] = smax; s_cmin[k] = cmin; s_marg[k] = marg;
     }
     if (bad) c.misc[MISC_FLAG] = 1.0;   // benign race: every writer stores the same value
-    sync();
+    __syncthreads();
     if (tid == 0) {
         // trivial bound on the cost-to-go from ANY state: the negative action costs that are still ahead
         c.tailmin[Nt] = 0.0;
-        for (int k = Nt - 1; k >= 0; --k) {
-            double m = INFINITY;
-            for (int al = 0; al < c.nact; ++al) if (c.amask[k] >> al & 1) {
-                double ca = 0.0;
-                for (int j = 0; j < nb; ++j) if (al >> j & 1) ca += c.cu[k * nb + j];
-                m = fmin(m, ca);
-            }
-            c.tailmin[k] = c.tailmin[k + 1] + fmin(m, 0.0);   // m = +inf (no action allowed) -> infeasible later
-        }
-        // grid window in s = p / a^k: hull over the stages of the violation-free band, one max shift of margin,
-        // intersected with what is reachable at all
+        for (int k = Nt - 1; k >= 0; --k) c.tailmin[k] = c.tailmin[k + 1] + fmin(s_cmin[k], 0.0);
+        // grid window: hull over the stages of the violation-free band (clamped to what is reachable at that
+        // stage), one max shift of margin, intersected with what is reachable at all
         double rlo = 0.0, rhi = 0.0, blo = INFINITY, bhi = -INFINITY, margin = 0.0;
         for (int k = 0; k < Nt; ++k) {
-            double lo_k = -INFINITY, hi_k = INFINITY;
-            for (int i = 0; i < nc; ++i) {
-                const double ei = c.e[i];
-                if (ei == 0.0) continue;
-                double fmin_a = INFINITY;
-                for (int al = 0; al < c.nact; ++al) if (c.amask[k] >> al & 1) fmin_a = fmin(fmin_a, c.falpha[i * c.nact + al]);
-                if (!isfinite(fmin_a)) fmin_a = 0.0;
-                const double lim = (c.rhs[k * nc + i] - fmin_a) / (ei * c.ak[k]);
-                if (ei > 0.0) hi_k = fmin(hi_k, lim); else lo_k = fmax(lo_k, lim);
-            }
-            // only states reachable at stage k matter
-            const double lo_c = fmin(fmax(lo_k, rlo), rhi), hi_c = fmax(fmin(hi_k, rhi), rlo);
+            const double lo_c = fmin(fmax(s_lo[k], rlo), rhi), hi_c = fmax(fmin(s_hi[k], rhi), rlo);
             blo = fmin(blo, fmin(lo_c, hi_c)); bhi = fmax(bhi, fmax(lo_c, hi_c));
-            double smin = 0.0, smax = 0.0;
-            bool any = false;
-            for (int al = 0; al < c.nact; ++al) if (c.amask[k] >> al & 1) {
-                const double sh = c.galpha[al] / c.ak[k + 1];
-                smin = any ? fmin(smin, sh) : sh; smax = any ? fmax(smax, sh) : sh; any = true;
-                margin = fmax(margin, fabs(sh));
-            }
-            rlo += smin; rhi += smax;
+            margin = fmax(margin, s_marg[k]);
+            rlo += s_smin[k]; rhi += s_smax[k];
         }
         double S0 = fmax(rlo, blo - margin), S1 = fmin(rhi, bhi + margin);
         if (!(S1 > S0)) { S0 = rlo; S1 = rhi; }
         double w = (S1 - S0) / (double)c.G;
         if (!(w > 0.0) || !isfinite(w)) w = 1.0;
-        c.misc[MISC_S0] = S0; c.misc[MISC_W] = w;
+        c.misc[MISC_S0] = S0; c.misc[MISC_W] = w; c.misc[MISC_INVW] = 1.0 / w;
     }
-    sync();
+    __syncthreads();
 }
 
 __device__ __forceinline__ double action_cost(const DpCtx& c, int k, int al) {
@@ -241,12 +246,11 @@ __device__ __forceinline__ double action_cost(const DpCtx& c, int k, int al) {
     return ca;
 }
 
-// stage cost of action `al` at stage k, bounded from below over p in [plo, phi] (exact when plo == phi)
-__device__ __forceinline__ double stage_cost(const DpCtx& c, int k, int al, double plo, double phi) {
+// exact stage cost of action `al` at stage k and forced response p
+__device__ __forceinline__ double stage_cost(const DpCtx& c, int k, int al, double p) {
     double st = action_cost(c, k, al);
     for (int i = 0; i < c.nc; ++i) {
-        const double ei = c.e[i];
-        const double viol = fma(ei, ei >= 0.0 ? plo : phi, c.falpha[i * c.nact + al] - c.rhs[k * c.nc + i]);
+        const double viol = fma(c.e[i], p, c.falpha[i * c.nact + al] - c.rhs[k * c.nc + i]);
         const double qs = c.qs[k * c.nc + i];
         if (isinf(qs)) { if (viol > c.feas_tol) st = INFINITY; }
         else st = fma(qs, fmax(viol, 0.0), st);
@@ -274,13 +278,14 @@ __global__ void __launch_bounds__(1024) stage_dp_table_kernel(const DpArgs A) {
     const int nthr = blockDim.x;
     DpCtx c = bind_ctx(A, smem);
     const DpPlan plan = make_dp_plan(c.Nt, c.nb, c.nc);
-    float* buf0 = reinterpret_cast<float*>(smem + ((plan.bytes + 15) & ~(size_t)15));   // [2][G] stages k+1 / k
-    dp_load(A, b, c, threadIdx.x, nthr, [] { __syncthreads(); });
+    float* buf0 = reinterpret_cast<float*>(smem + (size_t)plan.total * 8);   // [2][G] stages k+1 / k
+    dp_load(A, b, c);
     const int G = c.G, Nt = c.Nt;
     const int nc = NC > 0 ? NC : c.nc, nact = NACT > 0 ? NACT : c.nact;
-    if (threadIdx.x == 0) {
-        double* h = A.hdr + (int64_t)b * 8;
-        h[0] = c.misc[MISC_S0]; h[1] = c.misc[MISC_W]; h[2] = c.misc[MISC_FLAG];
+    {   // hand the stage data to the search kernel
+        const double* src = reinterpret_cast<const double*>(smem);
+        double* dst = A.pblk + (int64_t)b * plan.nd;
+        for (int i = threadIdx.x; i < plan.nd; i += nthr) dst[i] = src[i];
     }
     if (c.misc[MISC_FLAG] != 0.0) return;
     const double S0 = c.misc[MISC_S0], w = c.misc[MISC_W];
@@ -291,7 +296,7 @@ __global__ void __launch_bounds__(1024) stage_dp_table_kernel(const DpArgs A) {
     for (int i = 0; i < nc; ++i) e_r[i] = c.e[i];
     for (int k = Nt - 1; k >= 1; --k) {
         const double akk = c.ak[k];
-        const int mask = c.amask[k];
+        const int mask = (int)c.amask[k];
         const bool last = (k == Nt - 1);
         const float out_next = __double2float_rd(c.tailmin[k + 1]);
         if (threadIdx.x < nact) {
@@ -300,7 +305,7 @@ __global__ void __launch_bounds__(1024) stage_dp_table_kernel(const DpArgs A) {
             const double ga = c.galpha[al];
             int c0 = 0, span = 0;
             if (ga != 0.0) {
-                const double r = ga / (c.ak[k + 1] * w);   // translation of a cell, in cells
+                const double r = ga * c.iak[k + 1] * c.misc[MISC_INVW];   // translation of a cell, in cells
                 const double fl = floor(r), fr = r - fl;
                 c0 = (int)fmax(fmin(fl, 2.0e9), -2.0e9);
                 span = 1 | (fr < kEdgeEps ? 2 : 0) | (fr > 1.0 - kEdgeEps ? 4 : 0);
@@ -370,28 +375,27 @@ __device__ __forceinline__ int path_get(unsigned long long p0, unsigned long lon
     return (int)(a & ((1ull << nb) - 1ull));
 }
 
-// lower bound of the cost-to-go from exact state s at stage k (table cells are widened by kEdgeEps, so the
-// cell that floor() picks is valid even when s sits on a boundary up to rounding)
-__device__ __forceinline__ double lb_at(const DpCtx& c, const float* tab, int k, double s, double S0, double w) {
-    if (k >= c.Nt) return 0.0;
-    const double fl = floor((s - S0) / w);
-    if (!(fl >= 0.0) || !(fl < (double)c.G)) return c.tailmin[k];
-    return (double)__ldg(tab + (int64_t)k * c.G + (int)fl);
-}
-
+// One warp per agent.  Every iteration pops up to 32 / nact open nodes; lane (j, al) evaluates action `al` of the
+// j-th popped node: exact stage cost, exact next state, table bound.  Surviving children are pushed so that the
+// best child of the former top of the stack ends up on top (depth-first, best-bound child first).
 __global__ void __launch_bounds__(kSearchWarps * 32) stage_dp_search_kernel(const DpArgs A) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.x * kSearchWarps + warp;
     if (b >= A.d.B) return;
     const DpPlan plan = make_dp_plan(A.d.Nt, A.nb, A.d.nc);
-    const size_t per_warp = ((plan.bytes + 15) & ~(size_t)15) + sizeof(Node) * kStackCap + 8 * (kDpMaxNt + 1);
+    const size_t per_warp = (size_t)plan.nd * 8 + sizeof(Node) * kStackCap + 8 * (kDpMaxNt + 1);
     unsigned char* base = smem + per_warp * warp;
     DpCtx c = bind_ctx(A, base);
-    Node* stack = reinterpret_cast<Node*>(base + ((plan.bytes + 15) & ~(size_t)15));
+    Node* stack = reinterpret_cast<Node*>(base + (size_t)plan.nd * 8);
     double* ptraj = reinterpret_cast<double*>(stack + kStackCap);
-    dp_load(A, b, c, lane, 32, [] { __syncwarp(); });
-    const int Nt = c.Nt, nb = c.nb, nc = c.nc, nv = c.nv;
+    {
+        const double* src = A.pblk + (int64_t)b * plan.nd;
+        double* dst = reinterpret_cast<double*>(base);
+        for (int i = lane; i < plan.nd; i += 32) dst[i] = src[i];
+    }
+    __syncwarp();
+    const int Nt = c.Nt, nb = c.nb, nc = c.nc, nv = c.nv, nact = c.nact;
     double* vout = A.v + (int64_t)b * Nt * nv;
     int32_t* st_out = A.stats + (int64_t)b * 8;
     if (c.misc[MISC_FLAG] != 0.0) {
@@ -399,64 +403,54 @@ __global__ void __launch_bounds__(kSearchWarps * 32) stage_dp_search_kernel(cons
         if (lane == 0) { A.status[b] = HMPC_SOLVE_UNSUPPORTED; A.obj[b] = INFINITY; for (int i = 0; i < 8; ++i) st_out[i] = 0; }
         return;
     }
-    const double* hdr = A.hdr + (int64_t)b * 8;
-    const double S0 = hdr[0], w = hdr[1];
-    const double a = c.misc[MISC_A];
+    const double S0 = c.misc[MISC_S0], invw = c.misc[MISC_INVW], a = c.misc[MISC_A];
     const float* tab = A.table + (int64_t)b * Nt * c.G;
+    const int npl = 32 / nact;                 // nodes expanded per iteration
+    const int j = lane / nact, al = lane - j * nact;
+    const unsigned gmask = (nact == 32 ? 0xffffffffu : ((1u << nact) - 1u)) << (j * nact);
 
     double best = INFINITY;
     unsigned long long bp0 = 0, bp1 = 0;
-    int sp = 0, nodes = 0, improvements = 0, max_sp = 0;
+    int sp = 1, nodes = 0, improvements = 0, max_sp = 1;
     bool limit = false;
     if (lane == 0) { Node r; r.s = 0.0; r.cost = 0.0; r.bound = -INFINITY; r.p0 = r.p1 = 0; r.k = 0; r.pad = 0; stack[0] = r; }
-    sp = 1;
     __syncwarp();
     while (sp > 0) {
         if (nodes >= A.o.max_nodes) { limit = true; break; }
         const double tol = isfinite(best) ? fmax(1e-11 * fmax(1.0, fabs(best)), A.o.mip_rel_gap * fabs(best)) : 0.0;
-        // when the stack is nearly full fall back to strict depth-first (one node per iteration)
-        // and until the first dive has produced an incumbent there is nothing to prune against: dive first
-        int npop = sp < 32 ? sp : 32;
-        if (sp + 32 * c.nact > kStackCap || !isfinite(best)) npop = 1;
-        if (sp - npop + npop * c.nact > kStackCap) { limit = true; break; }
+        const double cut = best - tol;
+        // until the first dive has produced an incumbent there is nothing to prune against: dive first; and when
+        // the stack is nearly full fall back to strict depth-first
+        int npop = sp < npl ? sp : npl;
+        if (!isfinite(best) || sp + 32 > kStackCap) npop = 1;
+        if (sp - npop + npop * nact > kStackCap) { limit = true; break; }
+        const bool has = j < npop;
         Node nd;
-        bool active = lane < npop;
-        if (active) nd = stack[sp - 1 - lane];
+        nd.k = 0; nd.s = 0.0; nd.cost = 0.0; nd.bound = INFINITY; nd.p0 = nd.p1 = 0;
+        if (has) nd = stack[sp - 1 - j];
         sp -= npop;
-        active = active && (nd.bound < best - tol);
-        // expand: children of lane's node, ordered worst-first so that the best child ends up on top
-        double ch_bound[kDpMaxAct], ch_cost[kDpMaxAct], ch_s[kDpMaxAct];
-        int ch_al[kDpMaxAct];
-        int nch = 0;
-        double cand = INFINITY; unsigned long long cp0 = 0, cp1 = 0;
-        if (active) {
-            const int k = nd.k;
-            const double p = c.ak[k] * nd.s;
-            const int mask = c.amask[k];
-            for (int al = 0; al < c.nact; ++al) {
-                if (!(mask >> al & 1)) continue;
-                const double cost2 = nd.cost + stage_cost(c, k, al, p, p);
-                if (!(cost2 < best - tol)) continue;
-                const double s2 = nd.s + c.galpha[al] / c.ak[k + 1];
-                if (k + 1 == Nt) {
-                    if (cost2 < cand) { cand = cost2; cp0 = nd.p0; cp1 = nd.p1; path_set(cp0, cp1, k, nb, al); }
-                    continue;
-                }
-                const double bd = cost2 + lb_at(c, tab, k + 1, s2, S0, w);
-                if (!(bd < best - tol)) continue;
-                // insertion sort, descending bound
-                int pos = nch++;
-                while (pos > 0 && ch_bound[pos - 1] < bd) {
-                    ch_bound[pos] = ch_bound[pos - 1]; ch_cost[pos] = ch_cost[pos - 1]; ch_s[pos] = ch_s[pos - 1];
-                    ch_al[pos] = ch_al[pos - 1]; --pos;
-                }
-                ch_bound[pos] = bd; ch_cost[pos] = cost2; ch_s[pos] = s2; ch_al[pos] = al;
-            }
+        __syncwarp();
+        const bool alive = has && nd.bound < cut;
+        const int k = nd.k;
+        bool valid = alive && (((int)c.amask[k] >> al) & 1);
+        double cost2 = INFINITY, s2 = 0.0, bd = INFINITY;
+        if (valid) {
+            cost2 = nd.cost + stage_cost(c, k, al, c.ak[k] * nd.s);
+            valid = cost2 < cut;
         }
-        nodes += __popc(__ballot_sync(0xffffffffu, active));
-        // incumbent update (warp arg-min over the leaf candidates)
+        const bool leaf = (k + 1 == Nt);
+        if (valid && !leaf) {
+            s2 = fma(c.galpha[al], c.iak[k + 1], nd.s);
+            const double fl = floor((s2 - S0) * invw);
+            const double lbv = (fl >= 0.0 && fl < (double)c.G) ? (double)__ldg(tab + (int64_t)(k + 1) * c.G + (int)fl)
+                                                               : c.tailmin[k + 1];
+            bd = cost2 + lbv;
+            valid = bd < cut;
+        }
+        nodes += __popc(__ballot_sync(0xffffffffu, alive && al == 0));
+        // ---- incumbent: warp arg-min over the completed sequences
         {
-            double m = cand; int src = lane;
+            double m = (valid && leaf) ? cost2 : INFINITY; int src = lane;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 const double om = __shfl_xor_sync(0xffffffffu, m, o);
@@ -464,27 +458,31 @@ __global__ void __launch_bounds__(kSearchWarps * 32) stage_dp_search_kernel(cons
                 if (om < m || (om == m && os < src)) { m = om; src = os; }
             }
             if (m < best) {
+                unsigned long long q0 = nd.p0, q1 = nd.p1;
+                path_set(q0, q1, k, nb, al);
                 best = m;
-                bp0 = __shfl_sync(0xffffffffu, cp0, src);
-                bp1 = __shfl_sync(0xffffffffu, cp1, src);
+                bp0 = __shfl_sync(0xffffffffu, q0, src);
+                bp1 = __shfl_sync(0xffffffffu, q1, src);
                 ++improvements;
             }
         }
-        // push: lane 31's children lowest ... lane 0's children on top (lane 0 held the top of the stack)
-        int incl = nch;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_down_sync(0xffffffffu, incl, o);
-            if (lane + o < 32) incl += t;
+        // ---- push the surviving children: node j = 0 was the top, its children go on top, best bound last
+        const bool push = valid && !leaf;
+        const unsigned pm = __ballot_sync(0xffffffffu, push);
+        int below = 0;                                     // children of my node that sit beneath me
+        for (int t = 0; t < nact; ++t) {
+            const double ob = __shfl_sync(0xffffffffu, bd, j * nact + t);
+            if ((pm >> (j * nact + t) & 1u) && t != al && (ob > bd || (ob == bd && t < al))) ++below;
         }
-        const int total = __shfl_sync(0xffffffffu, incl, 0);
-        const int off = sp + (incl - nch);      // children of higher lanes sit below
-        for (int i = 0; i < nch; ++i) {
-            Node ch; ch.s = ch_s[i]; ch.cost = ch_cost[i]; ch.bound = ch_bound[i]; ch.k = nd.k + 1; ch.pad = 0;
-            ch.p0 = nd.p0; ch.p1 = nd.p1; path_set(ch.p0, ch.p1, nd.k, nb, ch_al[i]);
-            stack[off + i] = ch;
+        const int hi_shift = (j + 1) * nact;
+        const int base_j = hi_shift >= 32 ? 0 : __popc(pm >> hi_shift);   // children of deeper-popped nodes
+        if (push) {
+            Node ch; ch.s = s2; ch.cost = cost2; ch.bound = bd; ch.k = k + 1; ch.pad = 0;
+            ch.p0 = nd.p0; ch.p1 = nd.p1; path_set(ch.p0, ch.p1, k, nb, al);
+            stack[sp + base_j + below] = ch;
         }
-        sp += total;
+        (void)gmask;
+        sp += __popc(pm);
         max_sp = sp > max_sp ? sp : max_sp;
         __syncwarp();
     }
@@ -497,13 +495,13 @@ __global__ void __launch_bounds__(kSearchWarps * 32) stage_dp_search_kernel(cons
     __syncwarp();
     for (int k = lane; k < Nt; k += 32) {
         double* vk = vout + (int64_t)k * nv;
-        if (!have) { for (int j = 0; j < nv; ++j) vk[j] = nan(""); continue; }
-        const int al = path_get(bp0, bp1, k, nb);
-        for (int j = 0; j < nb; ++j) vk[j] = (double)(al >> j & 1);
+        if (!have) { for (int i = 0; i < nv; ++i) vk[i] = nan(""); continue; }
+        const int ak_ = path_get(bp0, bp1, k, nb);
+        for (int i = 0; i < nb; ++i) vk[i] = (double)(ak_ >> i & 1);
         if (c.nmu) {
             const double p = ptraj[k];
             for (int i = 0; i < nc; ++i) {
-                const double viol = fma(c.e[i], p, c.falpha[i * c.nact + al] - c.rhs[k * nc + i]);
+                const double viol = fma(c.e[i], p, c.falpha[i * nact + ak_] - c.rhs[k * nc + i]);
                 const double di = c.dscale[i];
                 vk[nb + i] = (di > 0.0 && !isinf(c.qs[k * nc + i])) ? fmax(viol, 0.0) / di : 0.0;
             }
@@ -514,7 +512,7 @@ __global__ void __launch_bounds__(kSearchWarps * 32) stage_dp_search_kernel(cons
         A.status[b] = limit ? HMPC_SOLVE_NODE_LIMIT : (have ? HMPC_SOLVE_OPTIMAL : HMPC_SOLVE_INFEASIBLE);
         st_out[0] = nodes; st_out[1] = 0; st_out[2] = 0; st_out[3] = c.G; st_out[4] = max_sp; st_out[5] = improvements;
         st_out[6] = 0;
-        st_out[7] = (int32_t)fmin(((double)(Nt - 1) * c.G * c.nact * (4.0 + 3.0 * nc) + (double)nodes * c.nact * (4.0 + 3.0 * nc)) / 1024.0, 2.0e9);
+        st_out[7] = (int32_t)fmin(((double)(Nt - 1) * c.G * nact * (4.0 + 3.0 * nc) + (double)nodes * nact * (4.0 + 3.0 * nc)) / 1024.0, 2.0e9);
     }
 }
 
@@ -543,7 +541,8 @@ extern "C" int hmpc_stage_dp_workspace_bytes(const hmpc_dims* d, const hmpc_stag
     hmpc_stage_dp_opts o;
     if (opts) o = *opts; else hmpc_stage_dp_default_opts(&o);
     if (o.cells < 64) return HMPC_ERR_ARG;
-    *bytes = table_bytes(d->B, d->Nt, o.cells) + (size_t)d->B * 8 * sizeof(double) + 256;
+    const DpPlan plan = make_dp_plan(d->Nt, d->nu + d->ndelta, d->nc);
+    *bytes = ((table_bytes(d->B, d->Nt, o.cells) + 255) & ~(size_t)255) + (size_t)d->B * plan.nd * sizeof(double) + 256;
     return HMPC_OK;
 }
 
@@ -570,12 +569,11 @@ extern "C" int hmpc_stage_dp_solve_f64(const hmpc_dims* dims, const double* cons
     hmpc_stage_dp_workspace_bytes(dims, &a.o, &need);
     if (!workspace || workspace_bytes < need) return HMPC_ERR_WORKSPACE;
     a.table = reinterpret_cast<float*>(workspace);
-    a.hdr = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(workspace) + ((table_bytes(dims->B, dims->Nt, a.G) + 255) & ~(size_t)255));
+    a.pblk = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(workspace) + ((table_bytes(dims->B, dims->Nt, a.G) + 255) & ~(size_t)255));
     a.v = v; a.obj = obj; a.status = status; a.stats = stats;
     const DpPlan plan = make_dp_plan(dims->Nt, a.nb, dims->nc);
-    const size_t plan_b = (plan.bytes + 15) & ~(size_t)15;
-    const size_t smem1 = plan_b + 2 * (size_t)a.G * sizeof(float);
-    const size_t smem2 = (plan_b + sizeof(Node) * kStackCap + 8 * (kDpMaxNt + 1)) * kSearchWarps;
+    const size_t smem1 = (size_t)plan.total * 8 + 2 * (size_t)a.G * sizeof(float);
+    const size_t smem2 = ((size_t)plan.nd * 8 + sizeof(Node) * kStackCap + 8 * (kDpMaxNt + 1)) * kSearchWarps;
     int dev = 0, smem_optin = 0;
     HMPC_CUDA_TRY(cudaGetDevice(&dev));
     HMPC_CUDA_TRY(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));

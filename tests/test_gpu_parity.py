@@ -170,24 +170,31 @@ def test_aggregate_power(cuda_device):
         assert np.array_equal(got, cabi.aggregate_power(u, P).cpu().numpy())      # deterministic
 
 
-def _dewh_solve(wl, dev, opts=None):
+SOLVERS = ("stage_dp", "bnc")     # both K3/K4 implementations must pass every DEWH solve test
+
+
+def _dewh_solve(wl, dev, solver="auto", mip_rel_gap=0.0):
+    from pyhybridcontrol_b200 import cabi
     from pyhybridcontrol_b200.batch import BatchMpc
     B, Nt = wl["B"], wl["Nt"]
-    bm = BatchMpc(wl["mats"], wl["N_p"], nu_l=1, device=dev, opts=opts)
+    bm = BatchMpc(wl["mats"], wl["N_p"], nu_l=1, device=dev, solver=solver,
+                  opts=cabi.default_opts(mip_rel_gap=mip_rel_gap), dp_opts=cabi.stage_dp_default_opts(mip_rel_gap=mip_rel_gap))
     bm.build()
     cost = np.zeros((B, Nt, 3))
     cost[:, :, 0] = wl["q_u"]
     cost[:, :, 1:] = wl["q_mu"][:, None, :]
     res = bm.solve(wl["x0"], wl["omega"], cost_v=cost.reshape(B, -1))
-    return bm, {k: v.cpu().numpy() for k, v in res.items()}, cost.reshape(B, -1)
+    assert res["solver"] == (solver if solver != "auto" else "stage_dp")
+    return bm, {k: (v.cpu().numpy() if hasattr(v, "cpu") else v) for k, v in res.items()}, cost.reshape(B, -1)
 
 
+@pytest.mark.parametrize("solver", SOLVERS)
 @pytest.mark.parametrize("N_p", [24, 48])
-def test_milp_vs_highs_golden(N_p, cuda_device):
+def test_milp_vs_highs_golden(N_p, solver, cuda_device):
     from pyhybridcontrol_b200.examples.residential_mg_with_pv_and_dewhs import synthetic as syn
     g = load_golden("milp", "dewh_N%d" % N_p)
     wl = syn.dewh_batch(int(g["B"]), N_p, seed=int(g["seed"]))
-    bm, res, _ = _dewh_solve(wl, cuda_device)
+    bm, res, _ = _dewh_solve(wl, cuda_device, solver)
     assert (res["status"] == 0).all()
     np.testing.assert_allclose(res["obj"], g["obj"], rtol=1e-6, atol=1e-9)
     isb = bm.is_bin_v.astype(bool)
@@ -195,12 +202,13 @@ def test_milp_vs_highs_golden(N_p, cuda_device):
     assert np.array_equal(res["v"][:, 0], np.round(g["v"][:, 0]))                    # first applied control
 
 
-def test_milp_vs_enumeration_small(cuda_device):
+@pytest.mark.parametrize("solver", SOLVERS)
+def test_milp_vs_enumeration_small(solver, cuda_device):
     """independent check on problems small enough to enumerate (2^9 assignments)."""
     from oracle import mld as omld, condense as oc, assemble as oa, solve as osv
     from pyhybridcontrol_b200.examples.residential_mg_with_pv_and_dewhs import synthetic as syn
     wl = syn.dewh_batch(6, 8, seed=9)
-    bm, res, _ = _dewh_solve(wl, cuda_device)
+    bm, res, _ = _dewh_solve(wl, cuda_device, solver)
     for b in range(6):
         full, d, vt = omld.complete({k: v[b] for k, v in wl["mats"].items()}, nu_l=1)
         prob = oa.build_problem(oc.condense(full, d, 9), d, vt, 9, wl["x0"][b], wl["omega"][b],
@@ -211,14 +219,15 @@ def test_milp_vs_enumeration_small(cuda_device):
             assert np.array_equal(np.round(res["v"][b][prob.is_bin]), np.round(v[prob.is_bin]))
 
 
-def test_milp_full_size_properties(cuda_device):
+@pytest.mark.parametrize("solver", SOLVERS)
+def test_milp_full_size_properties(solver, cuda_device):
     """BASELINE config 2 (B=100, N_p=48): every returned point is binary-integral, satisfies H v <= rhs, its
     objective equals c'v, and a sample of agents matches HiGHS."""
     from oracle import mld as omld, condense as oc, assemble as oa, solve as osv
     from pyhybridcontrol_b200 import cabi
     from pyhybridcontrol_b200.examples.residential_mg_with_pv_and_dewhs import synthetic as syn
     wl = syn.dewh_batch(100, 48, seed=1)
-    bm, res, cost = _dewh_solve(wl, cuda_device)
+    bm, res, cost = _dewh_solve(wl, cuda_device, solver)
     assert (res["status"] == 0).all()
     v = res["v"]
     isb = bm.is_bin_v.astype(bool)
@@ -273,28 +282,29 @@ def test_milp_edge_cases(cuda_device):
         assert int(st[b]) == 0 and abs(float(obj[b]) - best) < 1e-9
 
 
-def test_mip_gap_option(cuda_device):
+@pytest.mark.parametrize("solver", SOLVERS)
+def test_mip_gap_option(solver, cuda_device):
     """with MIPGap = 1e-2 (what the reference ran) the returned objective is within 1 % of the proven optimum."""
-    from pyhybridcontrol_b200 import cabi
     from pyhybridcontrol_b200.examples.residential_mg_with_pv_and_dewhs import synthetic as syn
     wl = syn.dewh_batch(16, 48, seed=5)
-    _, exact, _ = _dewh_solve(wl, cuda_device)
-    _, loose, _ = _dewh_solve(wl, cuda_device, opts=cabi.default_opts(mip_rel_gap=1e-2))
+    _, exact, _ = _dewh_solve(wl, cuda_device, solver)
+    _, loose, _ = _dewh_solve(wl, cuda_device, solver, mip_rel_gap=1e-2)
     assert (loose["status"] == 0).all()
     assert np.all(loose["obj"] >= exact["obj"] - 1e-9) and np.all(loose["obj"] <= exact["obj"] * 1.01 + 1e-9)
 
 
-def test_host_front_door_matches_device_path(cuda_device):
+@pytest.mark.parametrize("solver", SOLVERS)
+def test_host_front_door_matches_device_path(solver, cuda_device):
     """hmpc_mpc_step_host_f64 (numpy in / numpy out) == device-pointer path, and re-use without recondensing."""
     from pyhybridcontrol_b200 import cabi
     from pyhybridcontrol_b200.examples.residential_mg_with_pv_and_dewhs import synthetic as syn
     wl = syn.dewh_batch(10, 24, seed=6)
-    bm, res, cost = _dewh_solve(wl, cuda_device)
-    plan = cabi.StepPlan(bm.dims)
+    bm, res, cost = _dewh_solve(wl, cuda_device, solver)
+    plan = cabi.StepPlan(bm.dims, cabi.default_opts(reserved=int(solver == "bnc")))
     hm = dict(wl["mats"])
     hm["C"] = np.ones((1, 1, 1))
     v, obj, st, stats, tm = plan.step(hm, wl["x0"], wl["omega"], cost, bm.lb_v, bm.ub_v, bm.is_bin_v, recondense=True)
-    assert (st == 0).all()
+    assert (st == 0).all() and plan.last_solver == solver
     np.testing.assert_allclose(obj, res["obj"], rtol=1e-12)
     assert np.array_equal(v, res["v"])
     v2, obj2, st2, _, _ = plan.step(None, wl["x0"], wl["omega"], cost, bm.lb_v, bm.ub_v, bm.is_bin_v, recondense=False)

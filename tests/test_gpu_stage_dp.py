@@ -1,0 +1,239 @@
+"""GPU parity tests of the exact stage-DP solve (csrc/stage_dp.cu, hmpc_stage_dp_solve_f64) on the whole problem
+class it claims -- scalar state, 1..3 binary inputs/deltas, output rows through G/C/D, soft AND hard rows, fixed
+binaries, negative costs -- against (a) the oracle (numpy condensing + assembly + HiGHS / enumeration) and (b) the
+general branch-and-cut kernel on the condensed problem.  Objectives 1e-6 relative, decisions exact (random
+continuous costs make the optimum unique)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def random_scalar_mld(rng, B, nu, ndelta, nc, ny, soft, hard_rows=0):
+    """Batch of random MLDs of the stage-DP class (numpy, float64): name -> [B, r, c]."""
+    m = {}
+    m["A"] = rng.uniform(0.93, 1.03, size=(B, 1, 1))
+    m["B1"] = rng.uniform(0.5, 3.0, size=(B, 1, nu)) * rng.choice([-1.0, 1.0], size=(B, 1, nu), p=[0.25, 0.75])
+    if ndelta:
+        m["B2"] = rng.uniform(-2.0, 2.0, size=(B, 1, ndelta))
+    m["B4"] = rng.uniform(-1.0, 1.0, size=(B, 1, 1))
+    m["b5"] = rng.uniform(-0.3, 0.3, size=(B, 1, 1))
+    m["C"] = rng.uniform(0.5, 1.5, size=(B, ny, 1))
+    m["D1"] = rng.uniform(-0.2, 0.2, size=(B, ny, nu))
+    m["D4"] = rng.uniform(-0.2, 0.2, size=(B, ny, 1))
+    E = rng.uniform(0.5, 1.5, size=(B, nc, 1)) * np.where(np.arange(nc) % 2 == 0, 1.0, -1.0)[None, :, None]
+    m["E"] = E
+    m["F1"] = rng.uniform(-0.3, 0.3, size=(B, nc, nu))
+    if ndelta:
+        m["F2"] = rng.uniform(-0.3, 0.3, size=(B, nc, ndelta))
+    m["F4"] = rng.uniform(-0.2, 0.2, size=(B, nc, 1))
+    m["G"] = rng.uniform(-0.3, 0.3, size=(B, nc, ny)) * (rng.random((B, nc, ny)) < 0.5)
+    width = rng.uniform(2.0, 6.0, size=(B, 1, 1))
+    m["f5"] = np.where(np.arange(nc)[None, :, None] % 2 == 0, width, 0.5 * width) * rng.uniform(0.8, 1.2, size=(B, nc, 1))
+    if soft:
+        d = rng.uniform(0.5, 2.0, size=(B, nc))
+        d[:, nc - hard_rows:] = 0.0          # rows without a slack: hard constraints
+        m["Psi"] = -np.einsum("bi,ij->bij", d, np.eye(nc))
+    return m
+
+
+def solve_both(m, Nt, nu, ndelta, x0, omega, cost, dev, lb=None, ub=None, cells=None):
+    import torch
+    from pyhybridcontrol_b200 import cabi
+    from pyhybridcontrol_b200.batch import BatchMpc
+    out = {}
+    for solver in ("stage_dp", "bnc"):
+        kw = dict(dp_opts=cabi.stage_dp_default_opts(cells=cells)) if cells else {}
+        bm = BatchMpc(m, Nt - 1, Nt, nu_l=nu, device=dev, solver=solver, **kw)
+        if lb is not None:
+            bm.lb_v, bm.ub_v = lb.copy(), ub.copy()
+        bm.build()
+        res = bm.solve(x0, omega, cost_v=cost)
+        torch.cuda.synchronize()
+        out[solver] = {k: (v.cpu().numpy() if hasattr(v, "cpu") else v) for k, v in res.items()}
+        out[solver]["bm"] = bm
+    return out
+
+
+def oracle_problem(m, b, Nt, nu, x0, omega, cost):
+    from oracle import mld as omld, condense as oc, assemble as oa
+    full, d, vt = omld.complete({k: v[b] for k, v in m.items()}, nu_l=nu)
+    evo = oc.condense(full, d, Nt)
+    prob = oa.build_problem(evo, d, vt, Nt, x0[b], omega[b], atoms=None)
+    prob.c = cost[b].copy()
+    return prob
+
+
+CASES = [  # nu, ndelta, nc, ny, soft, hard_rows, Nt
+    (1, 0, 2, 1, True, 0, 12),
+    (1, 1, 2, 1, True, 0, 10),
+    (2, 0, 3, 2, True, 1, 9),
+    (1, 0, 2, 1, False, 0, 12),
+    (2, 1, 4, 1, True, 2, 6),
+]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_stage_dp_class_vs_oracle_and_bnc(case, cuda_device):
+    from oracle import solve as osv
+    nu, ndelta, nc, ny, soft, hard_rows, Nt = case
+    rng = np.random.default_rng([nu, ndelta, nc, Nt, 77])
+    B = 12
+    m = random_scalar_mld(rng, B, nu, ndelta, nc, ny, soft, hard_rows)
+    nb, nmu = nu + ndelta, (nc if soft else 0)
+    nv = nb + nmu
+    x0 = rng.uniform(-1.0, 1.0, size=(B, 1))
+    omega = rng.uniform(-1.0, 1.0, size=(B, Nt))
+    cost = np.zeros((B, Nt, nv))
+    cost[:, :, :nb] = rng.uniform(-0.3, 1.0, size=(B, Nt, nb))          # some negative action costs
+    cost[:, :, nb:] = rng.uniform(2.0, 20.0, size=(B, 1, nmu))
+    cost = cost.reshape(B, -1)
+    out = solve_both(m, Nt, nu, ndelta, x0, omega, cost, cuda_device)
+    dp, bnc = out["stage_dp"], out["bnc"]
+    assert dp["solver"] == "stage_dp" and bnc["solver"] == "bnc"
+    isb = out["stage_dp"]["bm"].is_bin_v.astype(bool)
+    n_feasible = 0
+    for b in range(B):
+        prob = oracle_problem(m, b, Nt, nu, x0, omega, cost)
+        if prob.is_bin.sum() <= 8 or b == 0 and prob.is_bin.sum() <= 12:
+            st, obj, v, second = osv.solve_enumerate(prob)      # independent of HiGHS' branch and bound
+        else:
+            st, obj, v = osv.solve_milp(prob, polish=True)
+            second = np.inf
+        if st == osv.INFEASIBLE:
+            assert dp["status"][b] == 1, (b, dp["status"][b])
+            continue
+        n_feasible += 1
+        assert dp["status"][b] == 0, (b, dp["status"][b])
+        assert abs(dp["obj"][b] - obj) <= 1e-6 * max(1.0, abs(obj)), (b, dp["obj"][b], obj)
+        if second - obj > 1e-6:
+            assert np.array_equal(np.round(dp["v"][b][isb]), np.round(v[isb])), b
+        # the point the kernel returns is feasible for the condensed problem and its objective is c'v
+        assert np.all(prob.H @ dp["v"][b] <= prob.rhs + 1e-7)
+        assert abs(cost[b] @ dp["v"][b] - dp["obj"][b]) <= 1e-9 * max(1.0, abs(obj))
+        if bnc["status"][b] == 0:
+            assert abs(bnc["obj"][b] - dp["obj"][b]) <= 1e-6 * max(1.0, abs(obj)), (b, bnc["obj"][b], dp["obj"][b])
+    assert n_feasible >= B // 2
+
+
+def test_stage_dp_fixed_binaries_and_disabled_slack(cuda_device):
+    """lb/ub fix some inputs (reference: a Parameter-pinned binary), mu forced to 0 (disable_soft_constraints,
+    controllers/controller_base.py:467-472) turns every row hard."""
+    from oracle import solve as osv
+    rng = np.random.default_rng(5)
+    B, Nt, nu, nc = 8, 12, 1, 2
+    m = random_scalar_mld(rng, B, nu, 0, nc, 1, True)
+    m["f5"] = m["f5"] * 4.0      # wide box so that the hard version stays feasible for most agents
+    nv = nu + nc
+    x0 = rng.uniform(-0.5, 0.5, size=(B, 1))
+    omega = rng.uniform(-0.5, 0.5, size=(B, Nt))
+    cost = np.zeros((B, Nt, nv))
+    cost[:, :, 0] = rng.uniform(0.1, 1.0, size=(B, Nt))
+    cost[:, :, 1:] = 10.0
+    cost = cost.reshape(B, -1)
+    lb = np.tile([0.0, 0.0, 0.0], Nt)
+    ub = np.tile([1.0, np.inf, np.inf], Nt)
+    lb[3 * 2] = 1.0                      # u_2 pinned on
+    ub[3 * 5] = 0.0                      # u_5 pinned off
+    ub[np.arange(Nt) * 3 + 2] = 0.0      # second slack disabled: row 1 is hard
+    out = solve_both(m, Nt, nu, 0, x0, omega, cost, cuda_device, lb=lb, ub=ub)
+    dp = out["stage_dp"]
+    for b in range(B):
+        prob = oracle_problem(m, b, Nt, nu, x0, omega, cost)
+        prob.lb, prob.ub = lb.copy(), ub.copy()
+        st, obj, v = osv.solve_milp(prob, polish=True)
+        if st == osv.INFEASIBLE:
+            assert dp["status"][b] == 1
+            continue
+        assert dp["status"][b] == 0 and abs(dp["obj"][b] - obj) <= 1e-6 * max(1.0, abs(obj))
+        assert dp["v"][b][6] == 1.0 and dp["v"][b][15] == 0.0
+        assert np.all(dp["v"][b][2::3] == 0.0)
+
+
+@pytest.mark.parametrize("N_p,cells", [(96, 8192), (48, 512), (48, 16384)])
+def test_stage_dp_long_horizon_and_cell_counts(N_p, cells, cuda_device):
+    """N_p = 96 (BASELINE config 5's longest horizon) and extreme table resolutions: the answer never depends on
+    the number of cells (only the search effort does); checked against HiGHS."""
+    from oracle import mld as omld, condense as oc, assemble as oa, solve as osv
+    from pyhybridcontrol_b200 import cabi
+    from pyhybridcontrol_b200.batch import BatchMpc
+    from pyhybridcontrol_b200.examples.residential_mg_with_pv_and_dewhs import synthetic as syn
+    B = 6
+    wl = syn.dewh_batch(B, N_p, seed=21)
+    Nt = wl["Nt"]
+    bm = BatchMpc(wl["mats"], N_p, nu_l=1, device=cuda_device, solver="stage_dp",
+                  dp_opts=cabi.stage_dp_default_opts(cells=cells))
+    bm.build()
+    cost = np.zeros((B, Nt, 3))
+    cost[:, :, 0] = wl["q_u"]
+    cost[:, :, 1:] = wl["q_mu"][:, None, :]
+    res = bm.solve(wl["x0"], wl["omega"], cost_v=cost.reshape(B, -1))
+    obj, v, st = res["obj"].cpu().numpy(), res["v"].cpu().numpy(), res["status"].cpu().numpy()
+    assert (st == 0).all()
+    for b in range(B if N_p <= 48 else 3):
+        full, d, vt = omld.complete({k: mm[b] for k, mm in wl["mats"].items()}, nu_l=1)
+        prob = oa.build_problem(oc.condense(full, d, Nt), d, vt, Nt, wl["x0"][b], wl["omega"][b],
+                                atoms=dict(q_u=wl["q_u"][b], q_mu=wl["q_mu"][b]))
+        s, o, vr = osv.solve_milp(prob)
+        assert abs(obj[b] - o) <= 1e-6 * max(1.0, abs(o))
+        assert np.array_equal(np.round(v[b][prob.is_bin]), np.round(vr[prob.is_bin]))
+
+
+def test_stage_dp_reports_unsupported_agents(cuda_device):
+    """An agent whose Psi couples two rows is outside the class: status 5 for it alone, the others are solved; the
+    BatchMpc front door refuses solver='stage_dp' for such a batch and 'auto' picks the general kernel."""
+    import torch
+    from pyhybridcontrol_b200 import cabi
+    from pyhybridcontrol_b200.batch import BatchMpc
+    from pyhybridcontrol_b200.examples.residential_mg_with_pv_and_dewhs import synthetic as syn
+    B, N_p = 4, 12
+    wl = syn.dewh_batch(B, N_p, seed=3)
+    Nt = wl["Nt"]
+    mats = {k: v.copy() for k, v in wl["mats"].items()}
+    mats["Psi"][2, 0, 1] = -0.5
+    with pytest.raises(ValueError):
+        BatchMpc(mats, N_p, nu_l=1, device=cuda_device, solver="stage_dp")
+    bm = BatchMpc(mats, N_p, nu_l=1, device=cuda_device, solver="auto")
+    assert not bm.stage_dp_ok
+    bm.build()
+    cost = np.zeros((B, Nt, 3))
+    cost[:, :, 0] = wl["q_u"]
+    cost[:, :, 1:] = wl["q_mu"][:, None, :]
+    res = bm.solve(wl["x0"], wl["omega"], cost_v=cost.reshape(B, -1))
+    assert res["solver"] == "bnc" and (res["status"].cpu().numpy() == 0).all()
+    # raw C-ABI call: per-agent flag
+    dev = cuda_device
+    x0 = torch.as_tensor(wl["x0"]).to(dev)
+    w = torch.as_tensor(wl["omega"]).to(dev)
+    rhs = cabi.constraint_rhs(bm.dims, bm.evo, x0, w)
+    lb, ub, isb = bm._bounds_dev()
+    v, obj, st, stats = cabi.stage_dp_solve(bm.dims, bm.mats, rhs, torch.as_tensor(cost.reshape(B, -1)).to(dev), lb, ub, isb)
+    st = st.cpu().numpy()
+    assert st[2] == 5 and (np.delete(st, 2) == 0).all()
+    assert np.allclose(np.delete(obj.cpu().numpy(), 2), np.delete(res["obj"].cpu().numpy(), 2), rtol=1e-9)
+
+
+def test_stage_dp_folds_extra_constraint_sets(cuda_device):
+    """scenario / min-max controllers add constraint sets over the same rows (examples/.../
+    micro_grid_control_simulation.py:200-227); stage-DP folds them into a row-wise min of the right-hand sides and
+    must agree with the branch-and-cut kernel that stacks them."""
+    from pyhybridcontrol_b200.batch import BatchMpc
+    from pyhybridcontrol_b200.examples.residential_mg_with_pv_and_dewhs import synthetic as syn
+    B, N_p = 8, 24
+    wl = syn.dewh_batch(B, N_p, seed=4)
+    Nt = wl["Nt"]
+    rng = np.random.default_rng(8)
+    scen = wl["omega"][:, :, None] * rng.uniform(0.5, 1.6, size=(B, Nt, 6))
+    cost = np.zeros((B, Nt, 3))
+    cost[:, :, 0] = wl["q_u"]
+    cost[:, :, 1:] = wl["q_mu"][:, None, :]
+    extra = [dict(omega_scenarios_k=scen), dict(omega_tilde_k=wl["omega"] * 1.3, N_tilde=9)]
+    res = {}
+    for solver in ("stage_dp", "bnc"):
+        bm = BatchMpc(wl["mats"], N_p, nu_l=1, device=cuda_device, solver=solver)
+        bm.build()
+        r = bm.solve(wl["x0"], wl["omega"], cost_v=cost.reshape(B, -1), extra_constraints=extra)
+        res[solver] = (r["obj"].cpu().numpy(), r["v"].cpu().numpy(), r["status"].cpu().numpy())
+    assert (res["stage_dp"][2] == 0).all() and (res["bnc"][2] == 0).all()
+    np.testing.assert_allclose(res["stage_dp"][0], res["bnc"][0], rtol=1e-6)
+    assert np.array_equal(res["stage_dp"][1][:, ::3], np.round(res["bnc"][1][:, ::3]))
