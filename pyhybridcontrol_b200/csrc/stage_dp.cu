@@ -37,7 +37,7 @@ constexpr int kDpMaxAct = 1 << kDpMaxNb;
 constexpr int kDpMaxNc = 8;
 constexpr int kDpMaxNt = 128;
 constexpr int kSearchWarps = 4;
-constexpr int kStackCap = 768;        // open nodes per agent
+constexpr int kStackCap = 512;        // open nodes per agent
 constexpr double kEdgeEps = 1e-9;     // cell-boundary guard (fraction of a cell)
 
 struct DpArgs {
@@ -59,9 +59,14 @@ struct DpArgs {
 // handed to the search kernel with one coalesced copy)
 struct DpPlan {
     int ak, iak, cu, qs, rhs, tailmin, amask, e, dscale, galpha, falpha, misc, nd;   // persistent part
+    int x_eak, x_foff, x_hq, x_ca, x_shift;
     int scr;                                                                      // load-time scratch [6*Nt]
+    int mst;                                                                      // staged MLD blocks [11][64]
+    int sc_ca, sc_base, sc_slope, sc_i0, sc_span, sc_flags;                       // per-stage sweep constants
     int total;
 };
+
+constexpr int kMstMats = 11, kMstElems = 64;
 
 __host__ __device__ inline DpPlan make_dp_plan(int Nt, int nb, int nc) {
     DpPlan p;
@@ -72,18 +77,28 @@ __host__ __device__ inline DpPlan make_dp_plan(int Nt, int nb, int nc) {
     p.ak = take(Nt + 2); p.iak = take(Nt + 2); p.cu = take(Nt * nb); p.qs = take(Nt * nc); p.rhs = take(Nt * nc);
     p.tailmin = take(Nt + 1); p.amask = take(Nt);
     p.e = take(nc); p.dscale = take(nc); p.galpha = take(nact); p.falpha = take(nc * nact);
+    // per-stage constants of the forward search: viol_i = x_eak[k][i] * s + x_foff[k][i][al], penalty weight / 2,
+    // action cost, translation of s
+    p.x_eak = take(Nt * nc); p.x_foff = take(Nt * nc * nact); p.x_hq = take(Nt * nc); p.x_ca = take(Nt * nact);
+    p.x_shift = take(Nt * nact);
     p.nd = (o + 1) & ~1;
     o = p.nd;
     p.scr = take(6 * Nt);
+    p.mst = take(kMstMats * kMstElems);
+    const int nc_ = nc > 0 ? nc : 1;
+    p.sc_ca = take(Nt * nact); p.sc_base = take(Nt * nc_ * nact); p.sc_slope = take(Nt * nc_);
+    p.sc_i0 = take((Nt * nact + 1) / 2); p.sc_span = take((Nt * nact + 1) / 2); p.sc_flags = take((Nt + 1) / 2);
     p.total = (o + 1) & ~1;
     return p;
 }
 
-enum { MISC_S0 = 0, MISC_W, MISC_A, MISC_FLAG, MISC_INVW };
+enum { MISC_S0 = 0, MISC_W, MISC_A, MISC_FLAG, MISC_INVW, MISC_SIMPLE };
 
 struct DpCtx {
     int Nt, nb, nc, nact, nmu, nv, G;
-    double *ak, *iak, *cu, *qs, *rhs, *tailmin, *amask, *e, *dscale, *galpha, *falpha, *misc, *scr;
+    double *ak, *iak, *cu, *qs, *rhs, *tailmin, *amask, *e, *dscale, *galpha, *falpha, *misc, *scr, *mst;
+    double *sc_ca, *sc_base, *sc_slope; int *sc_i0, *sc_span, *sc_flags;
+    double *x_eak, *x_foff, *x_hq, *x_ca, *x_shift;
     double feas_tol;
 };
 
@@ -94,7 +109,11 @@ __device__ inline DpCtx bind_ctx(const DpArgs& A, unsigned char* smem) {
     double* sd = reinterpret_cast<double*>(smem);
     c.ak = sd + p.ak; c.iak = sd + p.iak; c.cu = sd + p.cu; c.qs = sd + p.qs; c.rhs = sd + p.rhs;
     c.tailmin = sd + p.tailmin; c.amask = sd + p.amask; c.e = sd + p.e; c.dscale = sd + p.dscale;
-    c.galpha = sd + p.galpha; c.falpha = sd + p.falpha; c.misc = sd + p.misc; c.scr = sd + p.scr;
+    c.galpha = sd + p.galpha; c.falpha = sd + p.falpha; c.misc = sd + p.misc; c.scr = sd + p.scr; c.mst = sd + p.mst;
+    c.sc_ca = sd + p.sc_ca; c.sc_base = sd + p.sc_base; c.sc_slope = sd + p.sc_slope;
+    c.sc_i0 = reinterpret_cast<int*>(sd + p.sc_i0); c.sc_span = reinterpret_cast<int*>(sd + p.sc_span);
+    c.sc_flags = reinterpret_cast<int*>(sd + p.sc_flags);
+    c.x_eak = sd + p.x_eak; c.x_foff = sd + p.x_foff; c.x_hq = sd + p.x_hq; c.x_ca = sd + p.x_ca; c.x_shift = sd + p.x_shift;
     c.feas_tol = A.o.feas_tol;
     return c;
 }
@@ -108,21 +127,32 @@ __device__ __forceinline__ const double* mat_of(const DpArgs& A, int which, int 
 __device__ inline void dp_load(const DpArgs& A, int b, DpCtx& c) {
     const int Nt = c.Nt, nb = c.nb, nc = c.nc, nv = c.nv, nu = A.d.nu, nmu = c.nmu, nact = c.nact;
     const int tid = threadIdx.x, nthr = blockDim.x;
+    {   // all MLD blocks of this agent in one round of loads (missing blocks are zero)
+        const int which[kMstMats] = {HMPC_A, HMPC_B1, HMPC_B2, HMPC_C, HMPC_D1, HMPC_D2, HMPC_E, HMPC_F1, HMPC_F2, HMPC_G, HMPC_Psi};
+        const int ny_ = A.d.ny, nd_ = A.d.ndelta;
+        const int cnt[kMstMats] = {1, nu, nd_, ny_, ny_ * nu, ny_ * nd_, nc, nc * nu, nc * nd_, nc * ny_, nc * nmu};
+        for (int i = tid; i < kMstMats * kMstElems; i += nthr) {
+            const int mi = i / kMstElems, e = i - mi * kMstElems;
+            const double* src = mat_of(A, which[mi], b);
+            c.mst[i] = (src && e < cnt[mi]) ? src[e] : 0.0;
+        }
+    }
+    __syncthreads();
     if (tid == 0) {
         int flag = 0;
-        const double* Am = mat_of(A, HMPC_A, b);
-        const double a = Am ? Am[0] : 0.0;
+        const double* Am = c.mst;
+        const double a = Am[0];
         c.misc[MISC_A] = a;
         // a^k by running products, like the reference's A_pow_tilde (mld_evolution_matrices.py:266-272)
         double ap = 1.0;
         for (int k = 0; k <= Nt + 1; ++k) { c.ak[k] = ap; ap *= a; }
         if (!(a > 0.0) || !(c.ak[Nt] > 1e-3) || !(c.ak[Nt] < 1e3)) flag = 1;
-        const double* B1 = mat_of(A, HMPC_B1, b); const double* B2 = mat_of(A, HMPC_B2, b);
-        const double* Cm = mat_of(A, HMPC_C, b);
-        const double* D1 = mat_of(A, HMPC_D1, b); const double* D2 = mat_of(A, HMPC_D2, b);
-        const double* E = mat_of(A, HMPC_E, b);
-        const double* F1 = mat_of(A, HMPC_F1, b); const double* F2 = mat_of(A, HMPC_F2, b);
-        const double* Gm = mat_of(A, HMPC_G, b); const double* Psi = mat_of(A, HMPC_Psi, b);
+        const double* B1 = c.mst + 1 * kMstElems; const double* B2 = c.mst + 2 * kMstElems;
+        const double* Cm = c.mst + 3 * kMstElems;
+        const double* D1 = c.mst + 4 * kMstElems; const double* D2 = c.mst + 5 * kMstElems;
+        const double* E = c.mst + 6 * kMstElems;
+        const double* F1 = c.mst + 7 * kMstElems; const double* F2 = c.mst + 8 * kMstElems;
+        const double* Gm = c.mst + 9 * kMstElems; const double* Psi = c.mst + 10 * kMstElems;
         const int ny = A.d.ny, nd = A.d.ndelta;
         double g[kDpMaxNb], f[kDpMaxNc][kDpMaxNb];
         for (int j = 0; j < nb; ++j) g[j] = j < nu ? (B1 ? B1[j] : 0.0) : (B2 ? B2[j - nu] : 0.0);
@@ -235,7 +265,7 @@ __device__ inline void dp_load(const DpArgs& A, int b, DpCtx& c) {
         if (!(S1 > S0)) { S0 = rlo; S1 = rhi; }
         double w = (S1 - S0) / (double)c.G;
         if (!(w > 0.0) || !isfinite(w)) w = 1.0;
-        c.misc[MISC_S0] = S0; c.misc[MISC_W] = w; c.misc[MISC_INVW] = 1.0 / w;
+        c.misc[MISC_S0] = S0; c.misc[MISC_W] = w; c.misc[MISC_INVW] = 1.0 / w; c.misc[MISC_SIMPLE] = 1.0;
     }
     __syncthreads();
 }
@@ -259,21 +289,73 @@ __device__ __forceinline__ double stage_cost(const DpCtx& c, int k, int al, doub
 }
 
 // ------------------------------------------------------------------------------------------------ kernel 1
-// per-stage, per-action constants staged in shared memory before the cell loop
-struct StageConst {
-    double ca[kDpMaxAct];                 // action cost
-    double off[kDpMaxNc * kDpMaxAct];     // f_i' alpha - rhs_k,i
-    double q[kDpMaxNc];                   // slack price / d_i (+inf: hard row)
-    int c0[kDpMaxAct];                    // translation of a cell, whole cells
-    int span[kDpMaxAct];                  // 0: identity (exact), else bit0: also c0+1, bit1: also c0-1, bit2: also c0+2
-    int anyhard;
-};
+// Hot loop of the backward sweep over the cells [lo, hi) whose translated neighbours are all inside the table:
+// no bound checks, every per-stage constant in registers.  q max(v, 0) is evaluated as (q/2) (v + |v|) -- exact,
+// and |v| is a free operand modifier of the FP64 add.
+template <int NC, int NACT, bool SAME>
+__device__ __forceinline__ void sweep_interior(const float* __restrict__ cur, float* __restrict__ nxt,
+                                               float* __restrict__ tabk, int lo, int hi, int nthr,
+                                               const double* __restrict__ s_slope, const double* __restrict__ s_q,
+                                               const double* __restrict__ s_base, const double* __restrict__ s_ca,
+                                               const int* __restrict__ s_i0, const int* __restrict__ s_span) {
+    double slope[NC], hq[NC], base[NC * NACT], ca[NACT];
+    int i0[NACT]; bool two[NACT];
+#pragma unroll
+    for (int i = 0; i < NC; ++i) { slope[i] = s_slope[i]; hq[i] = 0.5 * s_q[i]; }
+#pragma unroll
+    for (int al = 0; al < NACT; ++al) {
+        ca[al] = s_ca[al]; i0[al] = s_i0[al]; two[al] = (s_span[al] & 1) != 0;
+#pragma unroll
+        for (int i = 0; i < NC; ++i) base[i * NACT + al] = s_base[i * NACT + al];
+    }
+    int cell = lo + threadIdx.x;
+    double cd = (double)cell;
+    const double dstep = (double)nthr;
+#pragma unroll 2
+    for (; cell < hi; cell += nthr, cd += dstep) {
+        double pen = 0.0;
+        if (SAME) {
+#pragma unroll
+            for (int i = 0; i < NC; ++i) {
+                const double v = fma(cd, slope[i], base[i * NACT]);
+                pen = fma(hq[i], v + fabs(v), pen);
+            }
+        }
+        double best = 0.0;
+#pragma unroll
+        for (int al = 0; al < NACT; ++al) {
+            double st = ca[al];
+            if (!SAME) {
+#pragma unroll
+                for (int i = 0; i < NC; ++i) {
+                    const double v = fma(cd, slope[i], base[i * NACT + al]);
+                    st = fma(hq[i], v + fabs(v), st);
+                }
+            }
+            const float* src = cur + (cell + i0[al]);
+            float nx = src[0];
+            if (two[al]) nx = fminf(nx, src[1]);
+            st += (double)nx;
+            best = (al == 0 || st < best) ? st : best;
+        }
+        const float r32 = __double2float_rd(best + pen);   // rounded DOWN: the stored table stays a lower bound
+        nxt[cell] = r32;
+        tabk[cell] = r32;
+    }
+}
 
 // NC / NACT > 0: compile-time row and action counts (the DEWH shape is <2, 2>); 0: run-time loops.
+// Per-stage sweep constants (computed for all stages at once, one thread per stage, before the sweep):
+//   ca[k][al]      action cost
+//   base[k][i][al] violation of row i under action al at the favourable edge of cell 0,
+//   slope[k][i]    ... and its increment per cell:  viol(cell) = slope * cell + base
+//   i0[k][al]      translation of a cell in whole cells; span bit0: also i0+1, bit1: also i0-1, bit2: also i0+2
+//                  (span 0 = identity: the "no input" action maps a cell onto itself exactly)
+//   flags[k]       bit0 fast (every action allowed, no hard row, no boundary-case translation),
+//                  bit1 samepen (row violations do not depend on the action: F = 0, G D = 0)
 template <int NC, int NACT>
-__global__ void __launch_bounds__(1024) stage_dp_table_kernel(const DpArgs A) {
+__global__ void __launch_bounds__(512) stage_dp_table_kernel(const DpArgs A) {
     extern __shared__ __align__(16) unsigned char smem[];
-    __shared__ StageConst sc;
     const int b = blockIdx.x;
     const int nthr = blockDim.x;
     DpCtx c = bind_ctx(A, smem);
@@ -282,76 +364,113 @@ __global__ void __launch_bounds__(1024) stage_dp_table_kernel(const DpArgs A) {
     dp_load(A, b, c);
     const int G = c.G, Nt = c.Nt;
     const int nc = NC > 0 ? NC : c.nc, nact = NACT > 0 ? NACT : c.nact;
+    const double S0 = c.misc[MISC_S0], w = c.misc[MISC_W];
+    float* tab = A.table + (int64_t)b * Nt * G;
+    float* cur = buf0;            // stage k+1
+    float* nxt = buf0 + G;        // stage k (being written)
+    for (int cell = threadIdx.x; cell < G; cell += nthr) cur[cell] = 0.f;      // LB of the terminal stage
+    for (int k = threadIdx.x; k < Nt; k += nthr) {
+        const double akk = c.ak[k];
+        const int mask = (int)c.amask[k];
+        int fast = mask == (1 << nact) - 1, same = 1;
+        for (int i = 0; i < nc; ++i) {
+            c.sc_slope[k * nc + i] = c.e[i] * akk * w;
+            if (isinf(c.qs[k * nc + i])) fast = 0;
+        }
+        for (int al = 0; al < nact; ++al) {
+            c.sc_ca[k * nact + al] = action_cost(c, k, al);
+            const double ga = c.galpha[al];
+            int i0 = 0, span = 0;
+            if (ga != 0.0) {
+                const double r = ga * c.iak[k + 1] * c.misc[MISC_INVW];   // translation of a cell, in cells
+                const double fl = floor(r), fr = r - fl;
+                i0 = (int)fmax(fmin(fl, 1.0e9), -1.0e9);
+                span = 1 | (fr < kEdgeEps ? 2 : 0) | (fr > 1.0 - kEdgeEps ? 4 : 0);
+            }
+            c.sc_i0[k * nact + al] = i0; c.sc_span[k * nact + al] = span;
+            if (span & 6) fast = 0;
+            // the cell is widened by a hair (kEdgeEps of its width on both sides) so that the bound also holds for
+            // states that floating-point rounding assigns to it from just outside
+            for (int i = 0; i < nc; ++i) {
+                const double ei = c.e[i];
+                const double edge = akk * (ei >= 0.0 ? fma(-kEdgeEps, w, S0) : fma(1.0 + kEdgeEps, w, S0));
+                const double bs = fma(ei, edge, c.falpha[i * nact + al] - c.rhs[k * nc + i]);
+                c.sc_base[(k * nc + i) * nact + al] = bs;
+                if (bs != c.sc_base[(k * nc + i) * nact]) same = 0;
+            }
+        }
+        c.sc_flags[k] = fast | (same << 1);
+        // forward-search constants
+        for (int i = 0; i < nc; ++i) {
+            c.x_eak[k * nc + i] = c.e[i] * akk;
+            c.x_hq[k * nc + i] = 0.5 * c.qs[k * nc + i];
+            for (int al = 0; al < nact; ++al) c.x_foff[(k * nc + i) * nact + al] = c.falpha[i * nact + al] - c.rhs[k * nc + i];
+        }
+        for (int al = 0; al < nact; ++al) {
+            c.x_ca[k * nact + al] = c.sc_ca[k * nact + al];
+            c.x_shift[k * nact + al] = c.galpha[al] * c.iak[k + 1];
+        }
+        if (!(mask == (1 << nact) - 1)) c.misc[MISC_SIMPLE] = 0.0;      // benign race: same value from every writer
+        for (int i = 0; i < nc; ++i) if (isinf(c.qs[k * nc + i])) c.misc[MISC_SIMPLE] = 0.0;
+    }
+    __syncthreads();
     {   // hand the stage data to the search kernel
         const double* src = reinterpret_cast<const double*>(smem);
         double* dst = A.pblk + (int64_t)b * plan.nd;
         for (int i = threadIdx.x; i < plan.nd; i += nthr) dst[i] = src[i];
     }
     if (c.misc[MISC_FLAG] != 0.0) return;
-    const double S0 = c.misc[MISC_S0], w = c.misc[MISC_W];
-    float* tab = A.table + (int64_t)b * Nt * G;
-    float* cur = buf0;            // stage k+1
-    float* nxt = buf0 + G;        // stage k (being written)
-    double e_r[NC > 0 ? NC : kDpMaxNc];
-    for (int i = 0; i < nc; ++i) e_r[i] = c.e[i];
     for (int k = Nt - 1; k >= 1; --k) {
-        const double akk = c.ak[k];
-        const int mask = (int)c.amask[k];
-        const bool last = (k == Nt - 1);
         const float out_next = __double2float_rd(c.tailmin[k + 1]);
-        if (threadIdx.x < nact) {
-            const int al = threadIdx.x;
-            sc.ca[al] = action_cost(c, k, al);
-            const double ga = c.galpha[al];
-            int c0 = 0, span = 0;
-            if (ga != 0.0) {
-                const double r = ga * c.iak[k + 1] * c.misc[MISC_INVW];   // translation of a cell, in cells
-                const double fl = floor(r), fr = r - fl;
-                c0 = (int)fmax(fmin(fl, 2.0e9), -2.0e9);
-                span = 1 | (fr < kEdgeEps ? 2 : 0) | (fr > 1.0 - kEdgeEps ? 4 : 0);
-            }
-            sc.c0[al] = c0; sc.span[al] = span;
-            for (int i = 0; i < nc; ++i) sc.off[i * nact + al] = c.falpha[i * nact + al] - c.rhs[k * nc + i];
+        float* tabk = tab + (int64_t)k * G;
+        const int flags = c.sc_flags[k];
+        const double* s_ca = c.sc_ca + k * nact; const double* s_base = c.sc_base + k * nc * nact;
+        const double* s_slope = c.sc_slope + k * nc; const double* s_q = c.qs + k * nc;
+        const int* s_i0 = c.sc_i0 + k * nact; const int* s_span = c.sc_span + k * nact;
+        // cells whose translated neighbours all exist (no bound checks needed): [lo, hi)
+        int lo = 0, hi = G;
+        for (int al = 0; al < nact; ++al) {
+            const int j0 = s_i0[al], j1 = s_i0[al] + (s_span[al] & 1);
+            lo = max(lo, -j0); hi = min(hi, G - j1);
         }
-        if (threadIdx.x == 32) {
-            int anyhard = 0;
-            for (int i = 0; i < nc; ++i) { const double q = c.qs[k * nc + i]; sc.q[i] = q; if (isinf(q)) anyhard = 1; }
-            sc.anyhard = anyhard;
+        if (hi < lo) hi = lo;
+        const bool fast = (flags & 1) && NC > 0;
+        if (fast) {
+            if (flags & 2) sweep_interior<(NC > 0 ? NC : 1), (NACT > 0 ? NACT : 1), true>(cur, nxt, tabk, lo, hi, nthr, s_slope, s_q, s_base, s_ca, s_i0, s_span);
+            else sweep_interior<(NC > 0 ? NC : 1), (NACT > 0 ? NACT : 1), false>(cur, nxt, tabk, lo, hi, nthr, s_slope, s_q, s_base, s_ca, s_i0, s_span);
         }
-        __syncthreads();
-        const bool anyhard = sc.anyhard != 0;
-        for (int cell = threadIdx.x; cell < G; cell += nthr) {
-            // the cell, widened by a hair so that the bound also holds for states that floating-point
-            // rounding assigns to it from just outside
-            const double slo = fma((double)cell - kEdgeEps, w, S0);
-            const double plo = akk * slo, phi = akk * (slo + (1.0 + 2.0 * kEdgeEps) * w);
-            double ep[NC > 0 ? NC : kDpMaxNc];
-            for (int i = 0; i < nc; ++i) ep[i] = e_r[i] * (e_r[i] >= 0.0 ? plo : phi);
-            double best = INFINITY;
-            for (int al = 0; al < nact; ++al) {
-                if (!(mask >> al & 1)) continue;
-                double st = sc.ca[al];
-                for (int i = 0; i < nc; ++i) {
-                    const double viol = ep[i] + sc.off[i * nact + al];
-                    const double q = sc.q[i];
-                    if (anyhard && isinf(q)) { if (viol > c.feas_tol) st = INFINITY; }
-                    else st = fma(q, fmax(viol, 0.0), st);
-                }
-                if (!last) {
-                    const int span = sc.span[al];
-                    const long long c0 = (long long)cell + sc.c0[al];
+        {
+            // ---- general loop: table edges; restricted action sets, hard rows, translations that land on a cell
+            //      boundary (then the whole stage goes through here)
+            const int mask = (int)c.amask[k];
+            const int nedge = fast ? lo + (G - hi) : G;
+            for (int e = threadIdx.x; e < nedge; e += nthr) {
+                const int cell = fast ? (e < lo ? e : hi + (e - lo)) : e;
+                const double cd = (double)cell;
+                double best = INFINITY;
+                for (int al = 0; al < nact; ++al) {
+                    if (!(mask >> al & 1)) continue;
+                    double st = s_ca[al];
+                    for (int i = 0; i < nc; ++i) {
+                        const double viol = fma(cd, s_slope[i], s_base[i * nact + al]);
+                        const double q = s_q[i];
+                        if (isinf(q)) { if (viol > c.feas_tol) st = INFINITY; }
+                        else st = fma(q, viol > 0.0 ? viol : 0.0, st);
+                    }
+                    const int span = s_span[al];
+                    const long long c0 = (long long)cell + s_i0[al];
                     auto at = [&](long long i) -> float { return (i < 0 || i >= G) ? out_next : cur[i]; };
                     float nx = at(c0);
                     if (span & 1) nx = fminf(nx, at(c0 + 1));
                     if (span & 2) nx = fminf(nx, at(c0 - 1));
                     if (span & 4) nx = fminf(nx, at(c0 + 2));
                     st += (double)nx;
+                    best = st < best ? st : best;
                 }
-                best = fmin(best, st);
+                const float r32 = __double2float_rd(best);
+                nxt[cell] = r32;
+                tabk[cell] = r32;
             }
-            const float r32 = __double2float_rd(best);     // rounded DOWN: the stored table stays a lower bound
-            nxt[cell] = r32;
-            tab[(int64_t)k * G + cell] = r32;
         }
         __syncthreads();
         float* t = cur; cur = nxt; nxt = t;
@@ -375,9 +494,91 @@ __device__ __forceinline__ int path_get(unsigned long long p0, unsigned long lon
     return (int)(a & ((1ull << nb) - 1ull));
 }
 
-// One warp per agent.  Every iteration pops up to 32 / nact open nodes; lane (j, al) evaluates action `al` of the
-// j-th popped node: exact stage cost, exact next state, table bound.  Surviving children are pushed so that the
-// best child of the former top of the stack ends up on top (depth-first, best-bound child first).
+__device__ __forceinline__ void path_set_bits(unsigned long long& p0, unsigned long long& p1, int pos, int width,
+                                              unsigned long long val) {
+    if (pos < 64) { p0 |= val << pos; if (pos + width > 64) p1 |= val >> (64 - pos); }
+    else p1 |= val << (pos - 64);
+}
+
+// monotone map double -> unsigned 64 (smaller value <=> smaller key)
+__device__ __forceinline__ unsigned long long order_key(double x) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(x);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+
+// lane holding the smallest `val` among the lanes with `flag` (lowest lane on exact ties), -1 if none:
+// two 32-bit redux.sync + one ballot instead of a 5-step shuffle butterfly
+__device__ __forceinline__ int warp_argmin(bool flag, double val, int lane) {
+    const unsigned fm = __ballot_sync(0xffffffffu, flag);
+    if (fm == 0) return -1;
+    const unsigned long long key = flag ? order_key(val) : ~0ull;
+    const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+    const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
+    const bool cand = flag && hi == mhi;
+    const unsigned mlo = __reduce_min_sync(0xffffffffu, cand ? lo : 0xffffffffu);
+    const unsigned wm = __ballot_sync(0xffffffffu, cand && lo == mlo);
+    (void)lane;
+    return wm ? __ffs(wm) - 1 : __ffs(fm) - 1;
+}
+
+// Branch-free evaluation of lane's action sequence (depth D, NB binaries per stage, NC soft rows, every action
+// allowed): the D states are a short FMA chain, the table read of the final state is issued before the D
+// independent stage costs are computed, so its latency is hidden behind them.
+template <int NC, int NB, int D>
+__device__ __forceinline__ bool expand_simple(const DpCtx& c, const float* __restrict__ tab, int k0, int lane, double S0,
+                                              double invw, double& s, double& cost, unsigned long long& q0,
+                                              unsigned long long& q1, double cut, double& bd, bool& leaf) {
+    constexpr int NACT = 1 << NB;
+    const int Nt = c.Nt;
+    const int De = (Nt - k0) < D ? (Nt - k0) : D;
+    leaf = (k0 + De == Nt);
+    bool ok = lane < (1 << (NB * De));
+    double st[D + 1];
+    int al[D];
+    st[0] = s;
+#pragma unroll
+    for (int t = 0; t < D; ++t) {
+        const int k = (k0 + t) < Nt ? (k0 + t) : (Nt - 1);
+        al[t] = (lane >> (t * NB)) & (NACT - 1);
+        st[t + 1] = st[t] + (t < De ? c.x_shift[k * NACT + al[t]] : 0.0);
+    }
+    float lbf = 0.f;
+    bool inwin = false;
+    if (!leaf) {
+        const double fl = floor((st[D] - S0) * invw);
+        inwin = fl >= 0.0 && fl < (double)c.G;
+        if (ok && inwin) lbf = __ldg(tab + (int64_t)(k0 + D) * c.G + (int)fl);
+    }
+#pragma unroll
+    for (int t = 0; t < D; ++t) {
+        if (t < De) {
+            const int k = k0 + t;
+            double lc = c.x_ca[k * NACT + al[t]];
+#pragma unroll
+            for (int i = 0; i < NC; ++i) {
+                const double v = fma(c.x_eak[k * NC + i], st[t], c.x_foff[(k * NC + i) * NACT + al[t]]);
+                lc = fma(c.x_hq[k * NC + i], v + fabs(v), lc);
+            }
+            cost += lc;
+        }
+    }
+    path_set_bits(q0, q1, k0 * NB, NB * De, (unsigned long long)(lane & ((1 << (NB * De)) - 1)));
+    s = st[D];
+    ok = ok && cost < cut;
+    bd = cost;
+    if (!leaf) {
+        bd = cost + (inwin ? (double)lbf : c.tailmin[k0 + D]);
+        ok = ok && bd < cut;
+    }
+    return ok;
+}
+
+// One warp per agent.  The unit of work is the depth-D subtree below one open node, D = the largest depth with
+// nact^D <= 32: lane l evaluates the action sequence whose base-nact digits are l -- exact stage costs, exact
+// states -- and closes it with the table bound of the state it reaches (one table read per lane per iteration).
+//   phase A: a greedy dive that keeps only the best lane of every subtree -> first incumbent after Nt / D steps;
+//   phase B: exact depth-first search from the root; a sequence survives when cost + bound < incumbent, the best
+//            survivor goes on top of the stack; whole runs of dominated nodes are discarded in one step.
 __global__ void __launch_bounds__(kSearchWarps * 32) stage_dp_search_kernel(const DpArgs A) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -405,84 +606,100 @@ __global__ void __launch_bounds__(kSearchWarps * 32) stage_dp_search_kernel(cons
     }
     const double S0 = c.misc[MISC_S0], invw = c.misc[MISC_INVW], a = c.misc[MISC_A];
     const float* tab = A.table + (int64_t)b * Nt * c.G;
-    const int npl = 32 / nact;                 // nodes expanded per iteration
-    const int j = lane / nact, al = lane - j * nact;
-    const unsigned gmask = (nact == 32 ? 0xffffffffu : ((1u << nact) - 1u)) << (j * nact);
+    const int D = nb == 1 ? 5 : (nb == 2 ? 2 : 1);      // nact^D <= 32
 
     double best = INFINITY;
     unsigned long long bp0 = 0, bp1 = 0;
-    int sp = 1, nodes = 0, improvements = 0, max_sp = 1;
+    int nodes = 0, improvements = 0, max_sp = 0;
     bool limit = false;
+
+    const bool simple21 = c.misc[MISC_SIMPLE] != 0.0 && nb == 1 && nc == 2;
+    // evaluate lane's action sequence below node (k0, s, cost, path); returns ok, and (k1, s, cost, path, bd)
+    auto expand = [&](int k0, double& s, double& cost, unsigned long long& q0, unsigned long long& q1, double cut,
+                      double& bd, bool& leaf) -> bool {
+        if (simple21) return expand_simple<2, 1, 5>(c, tab, k0, lane, S0, invw, s, cost, q0, q1, cut, bd, leaf);
+        const int De = (Nt - k0) < D ? (Nt - k0) : D;
+        bool ok = lane < (1 << (nb * De));
+        for (int t = 0; t < De; ++t) {
+            if (!ok) break;
+            const int k = k0 + t, al = (lane >> (t * nb)) & (nact - 1);
+            if (!(((int)c.amask[k] >> al) & 1)) { ok = false; break; }
+            cost += stage_cost(c, k, al, c.ak[k] * s);
+            s = fma(c.galpha[al], c.iak[k + 1], s);
+            path_set(q0, q1, k, nb, al);
+            if (!(cost < cut)) ok = false;
+        }
+        leaf = (k0 + De == Nt);
+        bd = cost;
+        if (ok && !leaf) {
+            const int k1 = k0 + De;
+            const double fl = floor((s - S0) * invw);
+            const double lbv = (fl >= 0.0 && fl < (double)c.G) ? (double)__ldg(tab + (int64_t)k1 * c.G + (int)fl)
+                                                               : c.tailmin[k1];
+            bd = cost + lbv;
+            ok = bd < cut;
+        }
+        return ok;
+    };
+    auto argmin_lane = [&](bool flag, double val) -> int { return warp_argmin(flag, val, lane); };
+
+    // ---- phase A: greedy dive
+    {
+        int k0 = 0; double s0 = 0.0, cost0 = 0.0; unsigned long long r0 = 0, r1 = 0;
+        while (k0 < Nt) {
+            double s = s0, cost = cost0, bd; unsigned long long q0 = r0, q1 = r1; bool leaf;
+            const bool ok = expand(k0, s, cost, q0, q1, INFINITY, bd, leaf);
+            ++nodes;
+            const int win = argmin_lane(ok, bd);
+            if (win < 0) break;                                   // dead end (hard rows): phase B searches properly
+            s0 = __shfl_sync(0xffffffffu, s, win); cost0 = __shfl_sync(0xffffffffu, cost, win);
+            r0 = __shfl_sync(0xffffffffu, q0, win); r1 = __shfl_sync(0xffffffffu, q1, win);
+            k0 += (Nt - k0) < D ? (Nt - k0) : D;
+            if (k0 >= Nt) { best = cost0; bp0 = r0; bp1 = r1; ++improvements; }
+        }
+    }
+    // ---- phase B: exact search
+    int sp = 1;
     if (lane == 0) { Node r; r.s = 0.0; r.cost = 0.0; r.bound = -INFINITY; r.p0 = r.p1 = 0; r.k = 0; r.pad = 0; stack[0] = r; }
     __syncwarp();
     while (sp > 0) {
         if (nodes >= A.o.max_nodes) { limit = true; break; }
         const double tol = isfinite(best) ? fmax(1e-11 * fmax(1.0, fabs(best)), A.o.mip_rel_gap * fabs(best)) : 0.0;
         const double cut = best - tol;
-        // until the first dive has produced an incumbent there is nothing to prune against: dive first; and when
-        // the stack is nearly full fall back to strict depth-first
-        int npop = sp < npl ? sp : npl;
-        if (!isfinite(best) || sp + 32 > kStackCap) npop = 1;
-        if (sp - npop + npop * nact > kStackCap) { limit = true; break; }
-        const bool has = j < npop;
-        Node nd;
-        nd.k = 0; nd.s = 0.0; nd.cost = 0.0; nd.bound = INFINITY; nd.p0 = nd.p1 = 0;
-        if (has) nd = stack[sp - 1 - j];
-        sp -= npop;
+        // discard the run of dominated nodes on top of the stack, pop the first live one
+        const bool live = lane < sp && stack[sp - 1 - lane].bound < cut;
+        const unsigned lm = __ballot_sync(0xffffffffu, live);
+        if (lm == 0) { sp -= sp < 32 ? sp : 32; continue; }
+        const int first = __ffs(lm) - 1;
+        const Node nd = stack[sp - 1 - first];
+        sp -= first + 1;
         __syncwarp();
-        const bool alive = has && nd.bound < cut;
-        const int k = nd.k;
-        bool valid = alive && (((int)c.amask[k] >> al) & 1);
-        double cost2 = INFINITY, s2 = 0.0, bd = INFINITY;
-        if (valid) {
-            cost2 = nd.cost + stage_cost(c, k, al, c.ak[k] * nd.s);
-            valid = cost2 < cut;
-        }
-        const bool leaf = (k + 1 == Nt);
-        if (valid && !leaf) {
-            s2 = fma(c.galpha[al], c.iak[k + 1], nd.s);
-            const double fl = floor((s2 - S0) * invw);
-            const double lbv = (fl >= 0.0 && fl < (double)c.G) ? (double)__ldg(tab + (int64_t)(k + 1) * c.G + (int)fl)
-                                                               : c.tailmin[k + 1];
-            bd = cost2 + lbv;
-            valid = bd < cut;
-        }
-        nodes += __popc(__ballot_sync(0xffffffffu, alive && al == 0));
-        // ---- incumbent: warp arg-min over the completed sequences
-        {
-            double m = (valid && leaf) ? cost2 : INFINITY; int src = lane;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const double om = __shfl_xor_sync(0xffffffffu, m, o);
-                const int os = __shfl_xor_sync(0xffffffffu, src, o);
-                if (om < m || (om == m && os < src)) { m = om; src = os; }
-            }
-            if (m < best) {
-                unsigned long long q0 = nd.p0, q1 = nd.p1;
-                path_set(q0, q1, k, nb, al);
-                best = m;
-                bp0 = __shfl_sync(0xffffffffu, q0, src);
-                bp1 = __shfl_sync(0xffffffffu, q1, src);
+        double s = nd.s, cost = nd.cost, bd; unsigned long long q0 = nd.p0, q1 = nd.p1; bool leaf;
+        const bool ok = expand(nd.k, s, cost, q0, q1, cut, bd, leaf);
+        ++nodes;
+        if (leaf) {
+            const int win = argmin_lane(ok, cost);
+            if (win >= 0) {
+                best = __shfl_sync(0xffffffffu, cost, win);
+                bp0 = __shfl_sync(0xffffffffu, q0, win); bp1 = __shfl_sync(0xffffffffu, q1, win);
                 ++improvements;
             }
+            continue;
         }
-        // ---- push the surviving children: node j = 0 was the top, its children go on top, best bound last
-        const bool push = valid && !leaf;
-        const unsigned pm = __ballot_sync(0xffffffffu, push);
-        int below = 0;                                     // children of my node that sit beneath me
-        for (int t = 0; t < nact; ++t) {
-            const double ob = __shfl_sync(0xffffffffu, bd, j * nact + t);
-            if ((pm >> (j * nact + t) & 1u) && t != al && (ob > bd || (ob == bd && t < al))) ++below;
+        const unsigned pm = __ballot_sync(0xffffffffu, ok);
+        const int npush = __popc(pm);
+        if (npush == 0) continue;
+        if (sp + npush > kStackCap) { limit = true; break; }
+        // best survivor on top, the others below it in lane order
+        const int win = npush > 1 ? argmin_lane(ok, bd) : __ffs(pm) - 1;
+        if (ok) {
+            int pos = __popc(pm & ((1u << lane) - 1u));           // rank among the survivors
+            if (lane == win) pos = npush - 1;
+            else if (lane > win) pos -= 1;
+            Node ch; ch.s = s; ch.cost = cost; ch.bound = bd; ch.k = nd.k + D; ch.pad = 0; ch.p0 = q0; ch.p1 = q1;
+            stack[sp + pos] = ch;
         }
-        const int hi_shift = (j + 1) * nact;
-        const int base_j = hi_shift >= 32 ? 0 : __popc(pm >> hi_shift);   // children of deeper-popped nodes
-        if (push) {
-            Node ch; ch.s = s2; ch.cost = cost2; ch.bound = bd; ch.k = k + 1; ch.pad = 0;
-            ch.p0 = nd.p0; ch.p1 = nd.p1; path_set(ch.p0, ch.p1, k, nb, al);
-            stack[sp + base_j + below] = ch;
-        }
-        (void)gmask;
-        sp += __popc(pm);
+        sp += npush;
         max_sp = sp > max_sp ? sp : max_sp;
         __syncwarp();
     }
@@ -512,7 +729,7 @@ __global__ void __launch_bounds__(kSearchWarps * 32) stage_dp_search_kernel(cons
         A.status[b] = limit ? HMPC_SOLVE_NODE_LIMIT : (have ? HMPC_SOLVE_OPTIMAL : HMPC_SOLVE_INFEASIBLE);
         st_out[0] = nodes; st_out[1] = 0; st_out[2] = 0; st_out[3] = c.G; st_out[4] = max_sp; st_out[5] = improvements;
         st_out[6] = 0;
-        st_out[7] = (int32_t)fmin(((double)(Nt - 1) * c.G * nact * (4.0 + 3.0 * nc) + (double)nodes * nact * (4.0 + 3.0 * nc)) / 1024.0, 2.0e9);
+        st_out[7] = (int32_t)fmin(((double)(Nt - 1) * c.G * nact * (4.0 + 3.0 * nc) + (double)nodes * 32.0 * D * (4.0 + 3.0 * nc)) / 1024.0, 2.0e9);
     }
 }
 
@@ -529,7 +746,7 @@ extern "C" int hmpc_stage_dp_supported(const hmpc_dims* d) {
     using namespace hmpc;
     if (!d) return 0;
     const int nb = d->nu + d->ndelta;
-    if (d->nx != 1 || d->nz != 0 || nb < 1 || nb > kDpMaxNb || d->nc > kDpMaxNc || d->Nt < 1 || d->Nt > kDpMaxNt) return 0;
+    if (d->nx != 1 || d->nz != 0 || nb < 1 || nb > kDpMaxNb || d->nc > kDpMaxNc || d->ny > 8 || d->Nt < 1 || d->Nt > kDpMaxNt) return 0;
     if (d->nmu != 0 && d->nmu != d->nc) return 0;
     if (nb * d->Nt > 128) return 0;
     return 1;
@@ -583,7 +800,7 @@ extern "C" int hmpc_stage_dp_solve_f64(const hmpc_dims* dims, const double* cons
     HMPC_CUDA_TRY(cudaFuncSetAttribute(stage_dp_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
     cudaStream_t s = (cudaStream_t)stream;
     // few agents: one fat CTA per SM hides the FP64 latency; many agents: several thin CTAs share an SM
-    const int table_threads = dims->B <= 2 * kNumSM ? 1024 : kDpThreads;
+    const int table_threads = dims->B <= 2 * kNumSM ? 512 : kDpThreads;
     table_kernel<<<dims->B, table_threads, smem1, s>>>(a);
     HMPC_LAUNCH_CHECK("stage_dp_table_kernel");
     stage_dp_search_kernel<<<ceil_div(dims->B, kSearchWarps), kSearchWarps * 32, smem2, s>>>(a);
