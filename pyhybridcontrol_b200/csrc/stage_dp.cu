@@ -39,6 +39,7 @@ constexpr int kDpMaxNt = 128;
 constexpr int kSearchWarps = 4;
 constexpr int kStackCap = 512;        // open nodes per agent
 constexpr double kEdgeEps = 1e-9;     // cell-boundary guard (fraction of a cell)
+__host__ __device__ constexpr int G_PAD(int G) { return G / 4; }   // guard cells on each side of a stage buffer
 
 struct DpArgs {
     hmpc_dims d;
@@ -360,15 +361,21 @@ __global__ void __launch_bounds__(512) stage_dp_table_kernel(const DpArgs A) {
     const int nthr = blockDim.x;
     DpCtx c = bind_ctx(A, smem);
     const DpPlan plan = make_dp_plan(c.Nt, c.nb, c.nc);
-    float* buf0 = reinterpret_cast<float*>(smem + (size_t)plan.total * 8);   // [2][G] stages k+1 / k
+    // two stage buffers (k+1 / k), each with `pad` guard cells on both sides that hold the out-of-window bound, so
+    // that the hot loop needs no bound checks
+    const int pad = G_PAD(A.G);
+    float* buf0 = reinterpret_cast<float*>(smem + (size_t)plan.total * 8);
     dp_load(A, b, c);
     const int G = c.G, Nt = c.Nt;
     const int nc = NC > 0 ? NC : c.nc, nact = NACT > 0 ? NACT : c.nact;
     const double S0 = c.misc[MISC_S0], w = c.misc[MISC_W];
     float* tab = A.table + (int64_t)b * Nt * G;
-    float* cur = buf0;            // stage k+1
-    float* nxt = buf0 + G;        // stage k (being written)
-    for (int cell = threadIdx.x; cell < G; cell += nthr) cur[cell] = 0.f;      // LB of the terminal stage
+    float* cur = buf0 + pad;                  // stage k+1
+    float* nxt = buf0 + (G + 2 * pad) + pad;  // stage k (being written)
+    for (int cell = threadIdx.x - pad; cell < G + pad; cell += nthr) cur[cell] = 0.f;      // LB of the terminal stage
+    __shared__ int s_maxshift;
+    if (threadIdx.x == 0) s_maxshift = 0;
+    __syncthreads();
     for (int k = threadIdx.x; k < Nt; k += nthr) {
         const double akk = c.ak[k];
         const int mask = (int)c.amask[k];
@@ -389,6 +396,7 @@ __global__ void __launch_bounds__(512) stage_dp_table_kernel(const DpArgs A) {
             }
             c.sc_i0[k * nact + al] = i0; c.sc_span[k * nact + al] = span;
             if (span & 6) fast = 0;
+            atomicMax(&s_maxshift, (i0 < 0 ? -i0 : i0) + 2);
             // the cell is widened by a hair (kEdgeEps of its width on both sides) so that the bound also holds for
             // states that floating-point rounding assigns to it from just outside
             for (int i = 0; i < nc; ++i) {
@@ -427,21 +435,16 @@ __global__ void __launch_bounds__(512) stage_dp_table_kernel(const DpArgs A) {
         const double* s_ca = c.sc_ca + k * nact; const double* s_base = c.sc_base + k * nc * nact;
         const double* s_slope = c.sc_slope + k * nc; const double* s_q = c.qs + k * nc;
         const int* s_i0 = c.sc_i0 + k * nact; const int* s_span = c.sc_span + k * nact;
-        // cells whose translated neighbours all exist (no bound checks needed): [lo, hi)
-        int lo = 0, hi = G;
-        for (int al = 0; al < nact; ++al) {
-            const int j0 = s_i0[al], j1 = s_i0[al] + (s_span[al] & 1);
-            lo = max(lo, -j0); hi = min(hi, G - j1);
-        }
-        if (hi < lo) hi = lo;
-        const bool fast = (flags & 1) && NC > 0;
+        // every translated neighbour lands inside the guard cells: the whole stage goes through the hot loop
+        const bool fast = (flags & 1) && NC > 0 && s_maxshift <= pad;
+        const int lo = 0, hi = G;
         if (fast) {
             if (flags & 2) sweep_interior<(NC > 0 ? NC : 1), (NACT > 0 ? NACT : 1), true>(cur, nxt, tabk, lo, hi, nthr, s_slope, s_q, s_base, s_ca, s_i0, s_span);
             else sweep_interior<(NC > 0 ? NC : 1), (NACT > 0 ? NACT : 1), false>(cur, nxt, tabk, lo, hi, nthr, s_slope, s_q, s_base, s_ca, s_i0, s_span);
         }
         {
-            // ---- general loop: table edges; restricted action sets, hard rows, translations that land on a cell
-            //      boundary (then the whole stage goes through here)
+            // ---- general loop: restricted action sets, hard rows, translations that land on a cell boundary or
+            //      beyond the guard cells
             const int mask = (int)c.amask[k];
             const int nedge = fast ? lo + (G - hi) : G;
             for (int e = threadIdx.x; e < nedge; e += nthr) {
@@ -471,6 +474,11 @@ __global__ void __launch_bounds__(512) stage_dp_table_kernel(const DpArgs A) {
                 nxt[cell] = r32;
                 tabk[cell] = r32;
             }
+        }
+        // guard cells of the stage just written: the bound of states outside the window at stage k
+        {
+            const float out_k = __double2float_rd(c.tailmin[k]);
+            for (int i = threadIdx.x; i < pad; i += nthr) { nxt[-1 - i] = out_k; nxt[G + i] = out_k; }
         }
         __syncthreads();
         float* t = cur; cur = nxt; nxt = t;
@@ -789,7 +797,7 @@ extern "C" int hmpc_stage_dp_solve_f64(const hmpc_dims* dims, const double* cons
     a.pblk = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(workspace) + ((table_bytes(dims->B, dims->Nt, a.G) + 255) & ~(size_t)255));
     a.v = v; a.obj = obj; a.status = status; a.stats = stats;
     const DpPlan plan = make_dp_plan(dims->Nt, a.nb, dims->nc);
-    const size_t smem1 = (size_t)plan.total * 8 + 2 * (size_t)a.G * sizeof(float);
+    const size_t smem1 = (size_t)plan.total * 8 + 2 * (size_t)(a.G + 2 * G_PAD(a.G)) * sizeof(float);
     const size_t smem2 = ((size_t)plan.nd * 8 + sizeof(Node) * kStackCap + 8 * (kDpMaxNt + 1)) * kSearchWarps;
     int dev = 0, smem_optin = 0;
     HMPC_CUDA_TRY(cudaGetDevice(&dev));
