@@ -344,6 +344,9 @@ class ConstraintSolvedController(ControllerBase):
         if "max_nodes" in solver_kwargs:
             opts.max_nodes = int(solver_kwargs["max_nodes"])
         batch.opts = opts
+        batch.dp_opts.mip_rel_gap = opts.mip_rel_gap
+        if "max_nodes" in solver_kwargs:
+            batch.dp_opts.max_nodes = int(solver_kwargs["max_nodes"])
         batch.disable_soft_constraints = self._disable_soft
         terms = self._cost_terms(k)
         x0 = self._x_k.reshape(1, -1)
