@@ -247,6 +247,17 @@ def main_ours(args):
         load_inputs(steps_in[s % P])
         out = one_step(static)
     barrier()
+    # ---- per-kernel breakdown: an extra, untimed pass with events between the launches (no graph)
+    Kb = min(K, 20)
+    bevs = [[torch.cuda.Event(enable_timing=True) for _ in range(6)] for _ in range(Kb)]
+    for s in range(Kb):
+        flush.fill_(float(s))
+        load_inputs(steps_in[s % P])
+        one_step(static, bevs[s])
+    barrier()
+    for e in bevs:
+        for i, k in enumerate(names):
+            kernel_ms[k] += e[i].elapsed_time(e[i + 1]) * K / Kb
     graph = None
     if not args.no_graph:
         side = torch.cuda.Stream()
@@ -288,17 +299,6 @@ def main_ours(args):
         t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
-    # ---- per-kernel breakdown: an extra, untimed pass with events between the launches (no graph)
-    Kb = min(K, 20)
-    bevs = [[torch.cuda.Event(enable_timing=True) for _ in range(6)] for _ in range(Kb)]
-    for s in range(Kb):
-        flush.fill_(float(s))
-        load_inputs(steps_in[(W + s) % P])
-        one_step(static, bevs[s])
-    barrier()
-    for e in bevs:
-        for i, k in enumerate(names):
-            kernel_ms[k] += e[i].elapsed_time(e[i + 1]) * K / Kb
     outs = [(None, None, st_, ss_) for st_, ss_ in zip(statuses, solve_stats)]
     solve_stats = []
     not_opt = 0

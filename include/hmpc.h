@@ -186,7 +186,7 @@ int hmpc_dewh_control_model_f64(int32_t B, const double* params, double* model, 
 
 /* ---- K6 aggregate power: replaces GridAgentMpc.get_grid_device_powers_N_tilde + GridModel D4 = ones
  *      (micro_grid_agents.py:625-646, micro_grid_models.py:143):  P_agg[k] = sum_b P_nom[b] * u[b,k].
- *  Deterministic two-pass tree; partial [ceil(B/256), Nt] scratch from the caller.                     */
+ *  Deterministic two-pass tree; partial [ceil(B/16), Nt] scratch from the caller.                     */
 int hmpc_aggregate_power_f64(int32_t B, int32_t Nt, const double* u, int64_t u_stride_b, int32_t u_stride_k,
                              const double* P_nom, double* partial, double* P_agg, void* stream);
 

@@ -128,8 +128,9 @@ class BatchMpc(object):
         return (np.arange(self.Nt)[:, None] * self.nv + np.arange(a, b)[None, :]).ravel()
 
     # ---- K1
-    def build(self, want=cabi.EVO_NAMES):
-        self.evo = cabi.condense(self.dims, self.mats, want=want, out=None)
+    def build(self, want=cabi.EVO_NAMES, reuse=False):
+        """K1.  reuse=True writes into the tensors of the previous build (no allocation in the control loop)."""
+        self.evo = cabi.condense(self.dims, self.mats, want=want, out=self.evo if (reuse and self.evo) else None)
         return self.evo
 
     def _bounds_dev(self):

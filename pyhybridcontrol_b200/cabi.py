@@ -370,7 +370,7 @@ def aggregate_power(u, P_nom=None):
     """K6 local part: u [B, Nt] (any strides) -> P_agg [Nt] = sum_b P_nom[b] u[b,k]."""
     global launch_count
     B, Nt = u.shape
-    chunks = max(1, (B + 255) // 256)
+    chunks = max(1, (B + 15) // 16)
     partial = torch.empty((chunks, Nt), dtype=torch.float64, device=u.device)
     out = torch.empty((Nt,), dtype=torch.float64, device=u.device)
     _check(_lib.hmpc_aggregate_power_f64(B, Nt, C.c_void_p(u.data_ptr()), u.stride(0), u.stride(1), _ptr(P_nom),

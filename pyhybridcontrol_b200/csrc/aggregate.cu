@@ -2,13 +2,13 @@
 //   P_agg[k] = sum_b P_nom[b] * u[b, k]
 // replaces GridAgentMpc.get_grid_device_powers_N_tilde + the grid model's D4 = ones(1, n_dev)
 // (reference: examples/.../micro_grid_agents.py:625-646, 410-420; micro_grid_models.py:143).
-// Deterministic two-pass tree (no atomics) so that a run is bit-reproducible: pass 1 reduces chunks of 256
+// Deterministic two-pass tree (no atomics) so that a run is bit-reproducible: pass 1 reduces chunks of 16
 // agents (thread <-> horizon step, coalesced along k), pass 2 sums the chunk partials in chunk order.
 // Across GPUs the [Nt] result is all-reduced with NCCL on the same stream by the host layer.
 #include "common.cuh"
 
 namespace hmpc {
-constexpr int kAggChunk = 256;
+constexpr int kAggChunk = 16;   // agents per CTA of pass 1: short dependent chains, many CTAs in flight
 
 __global__ void __launch_bounds__(128) aggregate_partial_kernel(int B, int Nt, const double* __restrict__ u,
                                                                 int64_t sb, int sk, const double* __restrict__ P_nom,
@@ -16,8 +16,15 @@ __global__ void __launch_bounds__(128) aggregate_partial_kernel(int B, int Nt, c
     const int chunk = blockIdx.x;
     const int b0 = chunk * kAggChunk, b1 = min(B, b0 + kAggChunk);
     for (int k = threadIdx.x; k < Nt; k += blockDim.x) {
+        double val[kAggChunk];
+#pragma unroll
+        for (int i = 0; i < kAggChunk; ++i) {           // all loads in flight before the (ordered) summation
+            const int b = b0 + i;
+            val[i] = b < b1 ? (P_nom ? P_nom[b] : 1.0) * u[(int64_t)b * sb + (int64_t)k * sk] : 0.0;
+        }
         double acc = 0.0;
-        for (int b = b0; b < b1; ++b) acc += (P_nom ? P_nom[b] : 1.0) * u[(int64_t)b * sb + (int64_t)k * sk];
+#pragma unroll
+        for (int i = 0; i < kAggChunk; ++i) acc += val[i];
         partial[(int64_t)chunk * Nt + k] = acc;
     }
 }
@@ -27,7 +34,15 @@ __global__ void __launch_bounds__(128) aggregate_final_kernel(int chunks, int Nt
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= Nt) return;
     double acc = 0.0;
-    for (int c = 0; c < chunks; ++c) acc += partial[(int64_t)c * Nt + k];
+    int c = 0;
+    for (; c + 8 <= chunks; c += 8) {
+        double v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = partial[(int64_t)(c + i) * Nt + k];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc += v[i];
+    }
+    for (; c < chunks; ++c) acc += partial[(int64_t)c * Nt + k];
     out[k] = acc;
 }
 

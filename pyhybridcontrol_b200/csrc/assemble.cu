@@ -128,7 +128,7 @@ extern "C" int hmpc_constraint_rhs_f64(const hmpc_dims* dims, int32_t rows, cons
     if (smem > 200 * 1024) return HMPC_ERR_ARG;
     HMPC_CUDA_TRY(cudaFuncSetAttribute(constraint_rhs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int gy = 1;
-    while (d.B * gy < 2 * kNumSM && gy * 8 < rows) gy *= 2;
+    while (d.B * gy < 8 * kNumSM && gy * 8 < rows) gy *= 2;   // small batches: about one row per warp
     constraint_rhs_kernel<<<dim3(d.B, gy), 256, smem, (cudaStream_t)stream>>>(d.B, rows, rows_full, d.nx, nwt, H_x,
                                                                              H_omega, H_5, x0, w, S, rhs);
     HMPC_LAUNCH_CHECK("constraint_rhs_kernel");

@@ -141,12 +141,24 @@ __global__ void __launch_bounds__(256) condense_kernel(const CondenseArgs args) 
 
     // ---- 2a. A^k by running products  Ap[k] = Ap[k-1] A   (reference :264-272)
     double* Ap = sm + p.o_Ap;
-    for (int e = threadIdx.x; e < nx * nx; e += blockDim.x) Ap[e] = (e / nx == e % nx) ? 1.0 : 0.0;
-    __syncthreads();
-    for (int k = 1; k < Nt; ++k) {
-        small_mm(Ap + k * nx * nx, Ap + (k - 1) * nx * nx, sm + p.o_A, nx, nx, nx);
-        __syncthreads();
+    // the recurrence is serial over the horizon: one warp runs it with warp-level barriers only (the block-wide
+    // barrier per step used to be half of this kernel's time at small nx)
+    if (threadIdx.x < 32) {
+        for (int e = threadIdx.x; e < nx * nx; e += 32) Ap[e] = (e / nx == e % nx) ? 1.0 : 0.0;
+        __syncwarp();
+        for (int k = 1; k < Nt; ++k) {
+            const double* Pk = Ap + (k - 1) * nx * nx;
+            const double* Am = sm + p.o_A;
+            for (int e = threadIdx.x; e < nx * nx; e += 32) {
+                const int r = e / nx, c = e - r * nx;
+                double acc = 0.0;
+                for (int l = 0; l < nx; ++l) acc += Pk[r * nx + l] * Am[l * nx + c];
+                Ap[k * nx * nx + e] = acc;
+            }
+            __syncwarp();
+        }
     }
+    __syncthreads();
     // ---- 2b. state lag tables: Gv[k] = A^k Bv, Gw[k] = A^k B4, g5[k] = A^k b5 (all k in parallel)
     double* Gv = sm + p.o_Gv; double* Gw = sm + p.o_Gw; double* c5 = sm + p.o_c5;
     double* g5 = sm + p.o_g5;
@@ -303,10 +315,11 @@ extern "C" int hmpc_condense_f64(const hmpc_dims* dims, const double* const mats
     const size_t smem = (size_t)p.total * sizeof(double);
     if (smem > 220 * 1024) return HMPC_ERR_ARG;  // model too large for the shared-memory lag table
     HMPC_CUDA_TRY(cudaFuncSetAttribute(condense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    // enough CTAs for >= 2 waves of the 148 SMs, at most one CTA per 4 output rows
+    // Row slices per agent: every slice repeats the recurrence (the expensive, latency-bound part of a CTA's life at
+    // small batch), so take just enough CTAs to put work on every SM -- not more; at most one CTA per 4 output rows
     int S = 1;
     const int max_rows = max(1, (d.nx + d.ny + d.nc) * d.Nt / 3);
-    while (d.B * S < 4 * kNumSM && S * 2 * 4 <= max_rows) S *= 2;
+    while (d.B * S < 2 * kNumSM && S * 2 * 4 <= max_rows) S *= 2;
     dim3 grid(d.B, S);
     condense_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(a);
     HMPC_LAUNCH_CHECK("condense_kernel");

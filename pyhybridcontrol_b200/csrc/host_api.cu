@@ -12,19 +12,17 @@ struct hmpc_step_plan {
     int nv, nvt, nwt, mrows;
     cudaStream_t stream;
     cudaEvent_t ev[4];
-    // device
-    double* mats_dev;            // packed copies of the 20 system matrices
+    // device: ONE input arena [x0 | w | cost | lb | ub | is_bin | mats...] and ONE output arena
+    // [v | obj | status | stats], mirrored by pinned host arenas, so that a step is one H2D and one D2H copy
+    double* in_dev;  double* pin_in;  size_t in_elems, in_head_elems;   // head = everything but the matrices
+    double* out_dev; double* pin_out; size_t out_elems;
+    double* mats_dev;            // = in_dev + in_head_elems: packed copies of the 20 system matrices
     int64_t mat_off[HMPC_NUM_MATS];
     int64_t mat_elems[HMPC_NUM_MATS];
     double *H_x, *H_v, *H_w, *H_5, *x0, *w, *rhs, *cost, *lb, *ub, *v, *obj;
     int32_t *status, *stats;
     uint8_t* is_bin;
-    // pinned staging
-    double* pin_in;  size_t pin_in_elems;
-    double* pin_out; size_t pin_out_elems;
-    int32_t* pin_iout;
-    uint8_t* pin_bin;
-    bool condensed;
+    bool condensed, have_H_v;
     // exact stage-DP path (stage_dp.cu) for scalar-state MLDs; the branch-and-cut kernel is the general path
     bool dp_dims_ok;
     hmpc_stage_dp_opts dp_opts;
@@ -71,28 +69,28 @@ extern "C" int hmpc_step_plan_create(const hmpc_dims* dims, const hmpc_milp_opts
         tot += p->mat_elems[i] * B;
     }
     auto dalloc = [&](double** ptr, int64_t n) { return cudaMalloc((void**)ptr, sizeof(double) * (size_t)(n > 0 ? n : 1)); };
-    HMPC_CUDA_TRY(dalloc(&p->mats_dev, tot));
+    const int64_t bin_elems = (p->nvt + 7) / 8;   // is_bin bytes, rounded up to whole doubles
+    p->in_head_elems = (size_t)(B * d.nx + B * p->nwt + B * p->nvt + 2 * p->nvt + bin_elems);
+    p->in_elems = p->in_head_elems + (size_t)tot;
+    p->out_elems = (size_t)(B * p->nvt + B + (B * 9 + 1) / 2);
+    HMPC_CUDA_TRY(dalloc(&p->in_dev, (int64_t)p->in_elems));
+    HMPC_CUDA_TRY(dalloc(&p->out_dev, (int64_t)p->out_elems));
+    HMPC_CUDA_TRY(cudaMallocHost((void**)&p->pin_in, sizeof(double) * p->in_elems));
+    HMPC_CUDA_TRY(cudaMallocHost((void**)&p->pin_out, sizeof(double) * p->out_elems));
+    {
+        double* q = p->in_dev;
+        p->x0 = q; q += B * d.nx; p->w = q; q += B * p->nwt; p->cost = q; q += B * p->nvt;
+        p->lb = q; q += p->nvt; p->ub = q; q += p->nvt; p->is_bin = reinterpret_cast<uint8_t*>(q); q += bin_elems;
+        p->mats_dev = q;
+        double* o = p->out_dev;
+        p->v = o; o += B * p->nvt; p->obj = o; o += B;
+        p->status = reinterpret_cast<int32_t*>(o); p->stats = p->status + B;
+    }
     HMPC_CUDA_TRY(dalloc(&p->H_x, B * p->mrows * d.nx));
     HMPC_CUDA_TRY(dalloc(&p->H_v, B * p->mrows * p->nvt));
     HMPC_CUDA_TRY(dalloc(&p->H_w, B * p->mrows * p->nwt));
     HMPC_CUDA_TRY(dalloc(&p->H_5, B * p->mrows));
-    HMPC_CUDA_TRY(dalloc(&p->x0, B * d.nx));
-    HMPC_CUDA_TRY(dalloc(&p->w, B * p->nwt));
     HMPC_CUDA_TRY(dalloc(&p->rhs, B * p->mrows));
-    HMPC_CUDA_TRY(dalloc(&p->cost, B * p->nvt));
-    HMPC_CUDA_TRY(dalloc(&p->lb, p->nvt));
-    HMPC_CUDA_TRY(dalloc(&p->ub, p->nvt));
-    HMPC_CUDA_TRY(dalloc(&p->v, B * p->nvt));
-    HMPC_CUDA_TRY(dalloc(&p->obj, B));
-    HMPC_CUDA_TRY(cudaMalloc((void**)&p->status, sizeof(int32_t) * B));
-    HMPC_CUDA_TRY(cudaMalloc((void**)&p->stats, sizeof(int32_t) * B * 8));
-    HMPC_CUDA_TRY(cudaMalloc((void**)&p->is_bin, (size_t)(p->nvt > 0 ? p->nvt : 1)));
-    p->pin_in_elems = (size_t)(tot + B * d.nx + B * p->nwt + B * p->nvt + 2 * p->nvt + 8);
-    p->pin_out_elems = (size_t)(B * p->nvt + B + 8);
-    HMPC_CUDA_TRY(cudaMallocHost((void**)&p->pin_in, sizeof(double) * p->pin_in_elems));
-    HMPC_CUDA_TRY(cudaMallocHost((void**)&p->pin_out, sizeof(double) * p->pin_out_elems));
-    HMPC_CUDA_TRY(cudaMallocHost((void**)&p->pin_iout, sizeof(int32_t) * (size_t)B * 9));
-    HMPC_CUDA_TRY(cudaMallocHost((void**)&p->pin_bin, (size_t)(p->nvt > 0 ? p->nvt : 1)));
     hmpc_stage_dp_default_opts(&p->dp_opts);
     p->dp_dims_ok = hmpc_stage_dp_supported(dims) != 0;
     if (p->dp_dims_ok) {
@@ -106,10 +104,10 @@ extern "C" int hmpc_step_plan_create(const hmpc_dims* dims, const hmpc_milp_opts
 extern "C" int hmpc_step_plan_destroy(hmpc_step_plan* p) {
     if (!p) return HMPC_OK;
     cudaStreamSynchronize(p->stream);
-    double* dbl[] = {p->mats_dev, p->H_x, p->H_v, p->H_w, p->H_5, p->x0, p->w, p->rhs, p->cost, p->lb, p->ub, p->v, p->obj};
+    double* dbl[] = {p->in_dev, p->out_dev, p->H_x, p->H_v, p->H_w, p->H_5, p->rhs};
     for (double* q : dbl) cudaFree(q);
-    cudaFree(p->status); cudaFree(p->stats); cudaFree(p->is_bin); cudaFree(p->dp_ws);
-    cudaFreeHost(p->pin_in); cudaFreeHost(p->pin_out); cudaFreeHost(p->pin_iout); cudaFreeHost(p->pin_bin);
+    cudaFree(p->dp_ws);
+    cudaFreeHost(p->pin_in); cudaFreeHost(p->pin_out);
     for (int i = 0; i < 4; ++i) cudaEventDestroy(p->ev[i]);
     cudaStreamDestroy(p->stream);
     delete p;
@@ -121,10 +119,9 @@ extern "C" int hmpc_step_plan_last_solver(const hmpc_step_plan* p) { return p ? 
 extern "C" int hmpc_mpc_step_host_bytes(const hmpc_step_plan* p, int32_t recondense, int64_t* h2d, int64_t* d2h) {
     if (!p) return HMPC_ERR_ARG;
     const int64_t B = p->d.B;
-    int64_t in = 8 * (B * p->d.nx + B * p->nwt + B * p->nvt + 2 * (int64_t)p->nvt) + p->nvt;
-    if (recondense) for (int i = 0; i < HMPC_NUM_MATS; ++i) in += 8 * p->mat_elems[i] * B;
-    if (h2d) *h2d = in;
-    if (d2h) *d2h = 8 * (B * p->nvt + B) + 4 * (B + 8 * B);
+    (void)B;
+    if (h2d) *h2d = 8 * (int64_t)(recondense ? p->in_elems : p->in_head_elems);
+    if (d2h) *d2h = 8 * (int64_t)p->out_elems;
     return HMPC_OK;
 }
 
@@ -141,76 +138,78 @@ extern "C" int hmpc_mpc_step_host_f64(hmpc_step_plan* p, int32_t recondense, con
     if (!recondense && !p->condensed) return HMPC_ERR_ARG;
     if (recondense && (!mats || !mat_stride_b)) return HMPC_ERR_ARG;
     cudaStream_t s = p->stream;
-    // ---- stage inputs in pinned memory (so the copies are true async DMA), then host -> device
-    double* pin = p->pin_in;
-    size_t off = 0;
+    // ---- stage every input in the pinned arena (same layout as the device arena), then ONE host -> device copy
     HMPC_CUDA_TRY(cudaEventRecord(p->ev[0], s));
     const double** dev_mats = p->dev_mats;
     int64_t* dev_stride = p->dev_stride;
+    double* pin = p->pin_in;
+    const bool bc = cost_v_stride_b == 0;
+    {
+        double* q = pin;
+        if (d.nx) memcpy(q, x0, sizeof(double) * (size_t)(B * d.nx));
+        q += B * d.nx;
+        if (p->nwt) memcpy(q, w, sizeof(double) * (size_t)(B * p->nwt));
+        q += B * p->nwt;
+        if (bc || cost_v_stride_b == p->nvt) memcpy(q, cost_v, sizeof(double) * (size_t)((bc ? 1 : B) * (int64_t)p->nvt));
+        else for (int64_t b = 0; b < B; ++b) memcpy(q + b * p->nvt, cost_v + b * cost_v_stride_b, sizeof(double) * (size_t)p->nvt);
+        q += B * p->nvt;
+        memcpy(q, lb_v, sizeof(double) * (size_t)p->nvt); q += p->nvt;
+        memcpy(q, ub_v, sizeof(double) * (size_t)p->nvt); q += p->nvt;
+        memcpy(q, is_bin_v, (size_t)p->nvt);
+    }
+    size_t copy_elems = p->in_head_elems;
     if (recondense) {
+        double* pm = pin + p->in_head_elems;
         for (int i = 0; i < HMPC_NUM_MATS; ++i) {
             const int64_t e = p->mat_elems[i];
             if (!mats[i] || e == 0) { dev_mats[i] = nullptr; dev_stride[i] = 0; continue; }
             const int64_t nb = mat_stride_b[i] == 0 ? 1 : B;
-            if (mat_stride_b[i] == e || nb == 1) memcpy(pin + off, mats[i], sizeof(double) * (size_t)(e * nb));
-            else for (int64_t b = 0; b < B; ++b) memcpy(pin + off + b * e, mats[i] + b * mat_stride_b[i], sizeof(double) * (size_t)e);
-            HMPC_CUDA_TRY(cudaMemcpyAsync(p->mats_dev + p->mat_off[i], pin + off, sizeof(double) * (size_t)(e * nb), cudaMemcpyHostToDevice, s));
+            double* dst = pm + p->mat_off[i];
+            if (mat_stride_b[i] == e || nb == 1) memcpy(dst, mats[i], sizeof(double) * (size_t)(e * nb));
+            else for (int64_t b = 0; b < B; ++b) memcpy(dst + b * e, mats[i] + b * mat_stride_b[i], sizeof(double) * (size_t)e);
             dev_mats[i] = p->mats_dev + p->mat_off[i];
             dev_stride[i] = nb == 1 ? 0 : e;
-            off += (size_t)(e * nb);
         }
+        copy_elems = p->in_elems;
     }
-    auto h2d = [&](double* dst, const double* src, int64_t n) -> cudaError_t {
-        if (n <= 0) return cudaSuccess;
-        memcpy(pin + off, src, sizeof(double) * (size_t)n);
-        cudaError_t e = cudaMemcpyAsync(dst, pin + off, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, s);
-        off += (size_t)n;
-        return e;
-    };
-    HMPC_CUDA_TRY(h2d(p->x0, x0, B * d.nx));
-    HMPC_CUDA_TRY(h2d(p->w, w, B * p->nwt));
-    const bool bc = cost_v_stride_b == 0;
-    if (bc || cost_v_stride_b == p->nvt) HMPC_CUDA_TRY(h2d(p->cost, cost_v, (bc ? 1 : B) * (int64_t)p->nvt));
-    else for (int64_t b = 0; b < B; ++b) {
-        memcpy(pin + off, cost_v + b * cost_v_stride_b, sizeof(double) * (size_t)p->nvt);
-        HMPC_CUDA_TRY(cudaMemcpyAsync(p->cost + b * p->nvt, pin + off, sizeof(double) * (size_t)p->nvt, cudaMemcpyHostToDevice, s));
-        off += (size_t)p->nvt;
-    }
-    HMPC_CUDA_TRY(h2d(p->lb, lb_v, p->nvt));
-    HMPC_CUDA_TRY(h2d(p->ub, ub_v, p->nvt));
-    memcpy(p->pin_bin, is_bin_v, (size_t)p->nvt);
-    HMPC_CUDA_TRY(cudaMemcpyAsync(p->is_bin, p->pin_bin, (size_t)p->nvt, cudaMemcpyHostToDevice, s));
+    HMPC_CUDA_TRY(cudaMemcpyAsync(p->in_dev, pin, sizeof(double) * copy_elems, cudaMemcpyHostToDevice, s));
     HMPC_CUDA_TRY(cudaEventRecord(p->ev[1], s));
     // ---- kernels
+    const bool want_dp = p->dp_dims_ok && p->opts.reserved == 0;
     int rc;
-    if (recondense) {
+    auto condense = [&](bool with_H_v) -> int {
         double* outs[HMPC_NUM_EVO] = {nullptr};
-        outs[HMPC_H_X] = d.nx ? p->H_x : nullptr; outs[HMPC_H_V] = p->H_v; outs[HMPC_H_OMEGA] = p->nwt ? p->H_w : nullptr;
-        outs[HMPC_H_5] = p->H_5;
-        rc = hmpc_condense_f64(&d, dev_mats, dev_stride, outs, s);
+        outs[HMPC_H_X] = d.nx ? p->H_x : nullptr; outs[HMPC_H_V] = with_H_v ? p->H_v : nullptr;
+        outs[HMPC_H_OMEGA] = p->nwt ? p->H_w : nullptr; outs[HMPC_H_5] = p->H_5;
+        const int r = hmpc_condense_f64(&d, dev_mats, dev_stride, outs, s);
+        if (r == HMPC_OK) { p->condensed = true; p->have_H_v = with_H_v; }
+        return r;
+    };
+    if (recondense) {
+        // the stage-DP kernels read the MLD blocks directly; the dense H_v (3/4 of K1's bytes) is only materialised
+        // for the branch-and-cut kernel
+        rc = condense(!want_dp);
         if (rc != HMPC_OK) return rc;
-        p->condensed = true;
     }
     rc = hmpc_constraint_rhs_f64(&d, p->mrows, p->H_x, p->H_w, p->H_5, p->x0, p->w, 0, p->rhs, s);
     if (rc != HMPC_OK) return rc;
     auto solve_bnc = [&]() -> int {
         p->last_solver = 0;
+        if (!p->have_H_v) { const int r = condense(true); if (r != HMPC_OK) return r; }
         return hmpc_milp_solve_f64(d.B, p->nvt, p->mrows, p->cost, bc ? 0 : p->nvt, p->H_v, (int64_t)p->mrows * p->nvt,
                                    p->rhs, p->lb, p->ub, 0, p->is_bin, &p->opts, nullptr, 0, p->v, p->obj, p->status,
                                    p->stats, s);
     };
+    const int32_t* pin_status = reinterpret_cast<const int32_t*>(p->pin_out + B * p->nvt + B);
     auto fetch = [&]() -> int {
         HMPC_CUDA_TRY(cudaEventRecord(p->ev[2], s));
-        HMPC_CUDA_TRY(cudaMemcpyAsync(p->pin_out, p->v, sizeof(double) * (size_t)(B * p->nvt), cudaMemcpyDeviceToHost, s));
-        HMPC_CUDA_TRY(cudaMemcpyAsync(p->pin_out + B * p->nvt, p->obj, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, s));
-        HMPC_CUDA_TRY(cudaMemcpyAsync(p->pin_iout, p->status, sizeof(int32_t) * (size_t)B, cudaMemcpyDeviceToHost, s));
-        HMPC_CUDA_TRY(cudaMemcpyAsync(p->pin_iout + B, p->stats, sizeof(int32_t) * (size_t)B * 8, cudaMemcpyDeviceToHost, s));
+        HMPC_CUDA_TRY(cudaMemcpyAsync(p->pin_out, p->out_dev, sizeof(double) * p->out_elems, cudaMemcpyDeviceToHost, s));
         HMPC_CUDA_TRY(cudaEventRecord(p->ev[3], s));
         HMPC_CUDA_TRY(cudaStreamSynchronize(s));
         return HMPC_OK;
     };
-    if (p->dp_dims_ok && p->opts.reserved == 0) {
-        // scalar-state class: exact stage-DP kernels straight from the MLD blocks (H_v is not read)
+    if (want_dp) {
+        // scalar-state class: exact stage-DP kernels straight from the MLD blocks
         p->last_solver = 1;
         rc = hmpc_stage_dp_solve_f64(&d, dev_mats, dev_stride, p->rhs, p->cost, bc ? 0 : p->nvt, p->lb, p->ub, p->is_bin,
                                      &p->dp_opts, p->dp_ws, p->dp_ws_bytes, p->v, p->obj, p->status, p->stats, s);
@@ -218,12 +217,12 @@ extern "C" int hmpc_mpc_step_host_f64(hmpc_step_plan* p, int32_t recondense, con
         rc = solve_bnc();
     }
     if (rc != HMPC_OK) return rc;
-    // ---- device -> host
+    // ---- ONE device -> host copy
     rc = fetch();
     if (rc != HMPC_OK) return rc;
     if (p->last_solver == 1) {
         bool unsupported = false;
-        for (int64_t b = 0; b < B; ++b) if (p->pin_iout[b] == HMPC_SOLVE_UNSUPPORTED) unsupported = true;
+        for (int64_t b = 0; b < B; ++b) if (pin_status[b] == HMPC_SOLVE_UNSUPPORTED) unsupported = true;
         if (unsupported) {   // some agent's matrices are outside the class: the general kernel takes the batch
             rc = solve_bnc();
             if (rc != HMPC_OK) return rc;
@@ -233,8 +232,8 @@ extern "C" int hmpc_mpc_step_host_f64(hmpc_step_plan* p, int32_t recondense, con
     }
     memcpy(v, p->pin_out, sizeof(double) * (size_t)(B * p->nvt));
     memcpy(obj, p->pin_out + B * p->nvt, sizeof(double) * (size_t)B);
-    memcpy(status, p->pin_iout, sizeof(int32_t) * (size_t)B);
-    memcpy(stats, p->pin_iout + B, sizeof(int32_t) * (size_t)B * 8);
+    memcpy(status, pin_status, sizeof(int32_t) * (size_t)B);
+    memcpy(stats, pin_status + B, sizeof(int32_t) * (size_t)B * 8);
     if (timing_ms) {
         cudaEventElapsedTime(&timing_ms[0], p->ev[0], p->ev[1]);
         cudaEventElapsedTime(&timing_ms[1], p->ev[1], p->ev[2]);

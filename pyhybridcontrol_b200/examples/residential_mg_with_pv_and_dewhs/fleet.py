@@ -46,7 +46,7 @@ class DewhFleet(object):
 
     def build(self, full=False):
         self.batch.mats.update({k: v for k, v in self._mats.items()})
-        return self.batch.build(want=cabi.EVO_NAMES if full else self._want)
+        return self.batch.build(want=cabi.EVO_NAMES if full else self._want, reuse=not full)
 
     def cost_from_prices(self, price):
         """price [Nt] or [B, Nt] (currency per W per step) -> cost on v~ [B, 3*Nt]:
