@@ -46,6 +46,7 @@ def parse_args():
     ap.add_argument("--np", dest="N_p", type=int, default=48)
     ap.add_argument("--cpu-sample", type=int, default=64, help="agent-solves timed for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-budget-s", type=float, default=80.0, help="--impl reference: target wall time of the run")
     ap.add_argument("--solver", default="auto", choices=("auto", "bnc", "stage_dp"),
                     help="auto = exact stage-DP kernels for the scalar-state DEWH class, bnc = general branch-and-cut")
     ap.add_argument("--cells", type=int, default=0, help="stage-DP value-table cells per stage (0 = library default)")
@@ -97,22 +98,31 @@ def run_cpu(args, jobs_per_step, steps, warmup, cores):
 
 
 def main_reference(args):
+    """Reference arm: the reference's CPU path (oracle port: numpy condensing + HiGHS) on
+    all host cores.  Every step solves a BOUNDED SAMPLE of the step's agents, sized from a probe so that the whole
+    run takes about a minute and a half whatever --steps is; throughput is per solve, so the unit is unchanged."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    times = run_cpu(args, lambda s: cpu_jobs(args, s), args.steps, min(args.warmup, 1), cores)
+    K, Wr = args.steps, min(args.warmup, 1)
+    probe = run_cpu(args, lambda s: cpu_jobs(args, s, count=min(args.agents, 2 * cores)), 1, 0, cores)
+    rate = min(args.agents, 2 * cores) / probe[0]
+    n = int(max(min(cores, args.agents), min(args.agents, args.ref_budget_s * rate / (K + Wr))))
+    times = run_cpu(args, lambda s: cpu_jobs(args, s % args.pool, count=n), K, Wr, cores)
     total = sum(times)
-    value = args.agents * len(times) / total
+    value = n * len(times) / total
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * args.agents / value,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args, args.gpus),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": "%d steps x %d agents, numpy condensing + HiGHS 1.12 (scipy.optimize.milp, "
-                                       "gap 0), multiprocessing pool on all host cores" % (len(times), args.agents)},
+                             "sample": "%d steps x %d of the step's %d agents (bounded sample), numpy condensing + HiGHS "
+                                       "1.12 (scipy.optimize.milp, gap 0), multiprocessing pool on all host cores; "
+                                       "ms_per_step = time of a full %d-agent step at the measured rate"
+                                       % (len(times), n, args.agents, args.agents)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "latency_p50_ms": 1e3 * float(np.median(times)), "gpu_launches": 0}
+            "latency_p50_ms": 1e3 * float(np.median(times)) * args.agents / n, "gpu_launches": 0}
     print(json.dumps(line))
 
 
@@ -223,10 +233,20 @@ def main_ours(args):
         T1, cons = fleet.sim_step(inp["x0"][:, 0].contiguous(), u[:, 0].contiguous(), inp["omega"][:, 0].contiguous())
         if ev:
             ev[4].record()
-        p_agg = fleet.aggregate_power(u)
+        p_agg = cabi.aggregate_power(u, fleet.P_nom)          # this rank's agents; ranks are summed by exchange()
         if ev:
             ev[5].record()
         return v, obj, status, stats, T1, p_agg
+
+    def exchange(p_agg):
+        """K6 across ranks: NCCL all-reduce of the [Nt] aggregate power on the step's stream (outside the graph)."""
+        if world > 1:
+            dist.all_reduce(p_agg, op=dist.ReduceOp.SUM)
+        return p_agg
+
+    def note(msg):
+        if os.environ.get("HMPC_BENCH_VERBOSE"):
+            print("[rank %d] %s" % (rank, msg), file=sys.stderr, flush=True)
 
     def barrier():
         torch.cuda.synchronize()
@@ -246,7 +266,9 @@ def main_ours(args):
         flush.fill_(float(s))
         load_inputs(steps_in[s % P])
         out = one_step(static)
+        exchange(out[5])
     barrier()
+    note("warm-up done")
     # ---- per-kernel breakdown: an extra, untimed pass with events between the launches (no graph)
     Kb = min(K, 20)
     bevs = [[torch.cuda.Event(enable_timing=True) for _ in range(6)] for _ in range(Kb)]
@@ -272,6 +294,7 @@ def main_ours(args):
         barrier()
         graph.replay()
         barrier()
+    note("graph captured")
     sampler = ClockSampler(local_rank)
     sampler.start()
     launches0 = cabi.launch_count
@@ -284,12 +307,14 @@ def main_ours(args):
         out = g_out if graph is not None else one_step(static)
         if graph is not None:
             graph.replay()
+        exchange(out[5])
         evs[s][1].record()
         statuses.append(out[2].clone())
         solve_stats.append(out[3].clone())
     barrier()
     t_wall = time.perf_counter() - t_wall0
     sampler.stop_flag = True
+    note("timed region done")
     launches_per_step = 1 + 1 + (2 if use_dp else 1) + 1 + 2      # K1, K2, K3/K4, K5, K6 (two-pass reduction)
     launches = launches_per_step * K if graph is not None else cabi.launch_count - launches0
     step_ms = [e[0].elapsed_time(e[1]) for e in evs]
