@@ -155,14 +155,30 @@ typedef struct {
     int32_t cells;         /* value-table cells per stage, default 8192                */
     int32_t max_nodes;     /* search nodes per agent, default 4,000,000                */
 } hmpc_stage_dp_opts;
+/* Optional convex cost terms of the stage-DP solve -- the reference's Quadratic / L22 / L1 atoms on the state, the
+ * outputs and the slacks (controllers/components/objective_atoms.py:320-363), which make the problem an MIQP:
+ *     cost += sum_k sum_t  wq[k,t] tau_k,t^2 + w1[k,t] |tau_k,t|  +  sum_k sum_i qmu[k,i] mu_k,i^2 ,
+ *     tau_k,t = h[t] p_k + ga[t]' alpha_k + r[k,t]
+ * p_k = forced response of the state (row k of Gamma_v times v); the caller folds h[t] * (free response) and any
+ * constant into r.  All weights must be >= 0 (convex), else the agent reports HMPC_SOLVE_UNSUPPORTED.           */
+typedef struct {
+    int32_t T;                                 /* state terms per stage, 0..4                                 */
+    int32_t reserved;
+    const double* h;   int64_t h_stride_b;     /* [B|1, T]                                                    */
+    const double* ga;  int64_t ga_stride_b;    /* [B|1, T, nb]   NULL = 0                                     */
+    const double* r;                           /* [B, Nt, T]                                                  */
+    const double* wq;  int64_t wq_stride_b;    /* [B|1, Nt, T]   NULL = 0                                     */
+    const double* w1;  int64_t w1_stride_b;    /* [B|1, Nt, T]   NULL = 0                                     */
+    const double* qmu; int64_t qmu_stride_b;   /* [B|1, Nt, nc]  NULL = 0; may be given with T == 0           */
+} hmpc_stage_terms;
 void hmpc_stage_dp_default_opts(hmpc_stage_dp_opts* opts);
 int  hmpc_stage_dp_supported(const hmpc_dims* dims);     /* 1 when the dimensions fit the class */
 int  hmpc_stage_dp_workspace_bytes(const hmpc_dims* dims, const hmpc_stage_dp_opts* opts, size_t* bytes);
 int  hmpc_stage_dp_solve_f64(const hmpc_dims* dims, const double* const mats[HMPC_NUM_MATS],
                              const int64_t mat_stride_b[HMPC_NUM_MATS], const double* rhs,
                              const double* cost_v, int64_t cost_v_stride_b, const double* lb_v, const double* ub_v,
-                             const uint8_t* is_bin_v, const hmpc_stage_dp_opts* opts,
-                             void* workspace, size_t workspace_bytes,
+                             const uint8_t* is_bin_v, const hmpc_stage_terms* terms /* NULL = linear cost */,
+                             const hmpc_stage_dp_opts* opts, void* workspace, size_t workspace_bytes,
                              double* v, double* obj, int32_t* status, int32_t* stats, void* stream);
 
 /* ---- K5 simulation step: replaces MldModel.lsim_k (models/mld_model.py:647-699): mu ignored in cons

@@ -171,9 +171,68 @@ class BatchMpc(object):
         return cabi.linear_cost(d.B, self.nvt, w_v=w_v, w_x=w_x, Gamma_v=self.evo.get("Gamma_v"), xc=xc, w_y=w_y,
                                 L_v=self.evo.get("L_v"), yc=yc)
 
+    def _mat_B(self, name, rows, cols):
+        t = self.mats.get(name)
+        if t is None:
+            return torch.zeros((self.B, rows, cols), dtype=torch.float64, device=self.device)
+        return t.expand(self.B, rows, cols)
+
+    def _stage_terms(self, quad, x0, omega):
+        """Quadratic / L1 atoms -> hmpc_stage_terms tensors + the part that folds into the linear cost.
+
+        quad keys (all optional, weights >= 0, [B|1, Nt, dim] or [Nt, dim]):  x2, x1 (state, squared / absolute),
+        y2, y1 (outputs), mu2 (slacks, squared), u2 / u1, delta2 / delta1 (binaries: b^2 = |b| = b, linear)."""
+        d, B, Nt = self.dims, self.B, self.Nt
+        nb = d.nu + d.ndelta
+
+        def W(key, dim):
+            t = quad.get(key)
+            if t is None:
+                return None
+            t = _dev_tensor(t, self.device).reshape(-1, Nt, dim)
+            if bool((t < 0).any()):
+                raise ValueError("quadratic / L1 weight '%s' must be non-negative (convex cost)" % key)
+            return t.expand(B, Nt, dim)
+        fold = torch.zeros((B, Nt, self.nv), dtype=torch.float64, device=self.device)
+        for key, off, dim in (("u2", 0, d.nu), ("u1", 0, d.nu), ("delta2", d.nu, d.ndelta), ("delta1", d.nu, d.ndelta)):
+            t = W(key, dim) if dim else None
+            if t is not None:
+                fold[:, :, off:off + dim] += t
+        h, ga, r, wq, w1 = [], [], [], [], []
+        zero = torch.zeros((B, Nt), dtype=torch.float64, device=self.device)
+        x2, x1 = W("x2", d.nx), W("x1", d.nx)
+        if x2 is not None or x1 is not None:
+            xfree = cabi.predict(self.evo["Phi_x"], None, self.evo["Gamma_omega"], self.evo["Gamma_5"].reshape(B, -1),
+                                 x0, None, omega).reshape(B, Nt)
+            h.append(torch.ones(B, dtype=torch.float64, device=self.device))
+            ga.append(torch.zeros((B, nb), dtype=torch.float64, device=self.device))
+            r.append(xfree)
+            wq.append(zero if x2 is None else x2[:, :, 0])
+            w1.append(zero if x1 is None else x1[:, :, 0])
+        y2, y1 = W("y2", d.ny), W("y1", d.ny)
+        if y2 is not None or y1 is not None:
+            yfree = cabi.predict(self.evo["L_x"], None, self.evo["L_omega"], self.evo["L_5"].reshape(B, -1), x0, None,
+                                 omega).reshape(B, Nt, d.ny)
+            Cm, Dm = self._mat_B("C", d.ny, d.nx), torch.cat([self._mat_B("D1", d.ny, d.nu), self._mat_B("D2", d.ny, d.ndelta)], dim=2)
+            for rr in range(d.ny):
+                h.append(Cm[:, rr, 0]); ga.append(Dm[:, rr, :]); r.append(yfree[:, :, rr])
+                wq.append(zero if y2 is None else y2[:, :, rr])
+                w1.append(zero if y1 is None else y1[:, :, rr])
+        terms = {}
+        if h:
+            if len(h) > 4:
+                raise NotImplementedError("at most 4 state / output terms per stage")
+            terms = dict(h=torch.stack(h, dim=1), ga=torch.stack(ga, dim=1), r=torch.stack(r, dim=2),
+                         wq=torch.stack(wq, dim=2), w1=torch.stack(w1, dim=2))
+        mu2 = W("mu2", d.nmu) if d.nmu else None
+        if mu2 is not None:
+            terms["qmu"] = mu2
+        return terms, fold.reshape(B, -1)
+
     def solve(self, x0, omega, cost_v=None, w_x=None, w_y=None, scenarios=None, extra_constraints=(),
-              with_std_constraints=True):
-        """One control step for the whole batch.  Returns dict(v, obj, status, stats, c0) of device tensors."""
+              with_std_constraints=True, quad=None):
+        """One control step for the whole batch.  Returns dict(v, obj, status, stats, c0) of device tensors.
+        ``quad``: convex quadratic / L1 weights (see _stage_terms) -- an MIQP, stage-DP path only."""
         if self.evo is None:
             raise RuntimeError("build() must be called before solve()")
         d = self.dims
@@ -203,6 +262,13 @@ class BatchMpc(object):
             rs.append(r)
         lb, ub, isb = self._bounds_dev()
         use_dp = self.solver == "stage_dp" or (self.solver == "auto" and self.stage_dp_ok)
+        terms = None
+        if quad:
+            if not (use_dp and rs):
+                raise NotImplementedError("quadratic / L1 cost atoms run on the stage-DP path only (scalar-state MLDs); "
+                                          "the branch-and-cut kernel is an MILP solver")
+            terms, fold = self._stage_terms(quad, x0, omega)
+            c = c.expand(d.B, self.nvt) + fold
         if use_dp and rs:
             # every constraint set shares the rows of H_v (prefixes for reduced horizons), so the sets fold into
             # the row-wise minimum of their right-hand sides
@@ -211,7 +277,8 @@ class BatchMpc(object):
                 rhs[:, :r.shape[1]] = torch.minimum(rhs[:, :r.shape[1]], r)
             if len(rs) == 1 and rs[0].shape[1] == self.mrows:
                 rhs = rs[0]
-            v, obj, status, stats = cabi.stage_dp_solve(d, self.mats, rhs, c, lb, ub, isb, self.dp_opts)
+            v, obj, status, stats = cabi.stage_dp_solve(d, self.mats, rhs, c.contiguous(), lb, ub, isb, self.dp_opts,
+                                                        terms=terms)
             return dict(v=v, obj=obj + c0, status=status, stats=stats, c0=c0, solver="stage_dp")
         if len(Hs) == 1 and Hs[0].shape[1] == self.mrows:
             H, rhs = self.evo["H_v"], rs[0]

@@ -54,6 +54,13 @@ class StageDpOpts(C.Structure):
     _fields_ = [("mip_rel_gap", C.c_double), ("feas_tol", C.c_double), ("cells", C.c_int32), ("max_nodes", C.c_int32)]
 
 
+class StageTerms(C.Structure):
+    _fields_ = [("T", C.c_int32), ("reserved", C.c_int32), ("h", C.c_void_p), ("h_stride_b", C.c_int64),
+                ("ga", C.c_void_p), ("ga_stride_b", C.c_int64), ("r", C.c_void_p), ("wq", C.c_void_p),
+                ("wq_stride_b", C.c_int64), ("w1", C.c_void_p), ("w1_stride_b", C.c_int64), ("qmu", C.c_void_p),
+                ("qmu_stride_b", C.c_int64)]
+
+
 if not os.path.exists(LIB_PATH):
     raise ImportError("libhmpc.so is not built (%s).  Run `python -c 'import __graft_entry__ as g; g.build()'` or "
                       "`make -C pyhybridcontrol_b200/csrc`.  There is no CPU fallback." % LIB_PATH)
@@ -83,7 +90,8 @@ _lib.hmpc_stage_dp_default_opts.restype = None
 _lib.hmpc_stage_dp_supported.argtypes = [C.POINTER(Dims)]
 _lib.hmpc_stage_dp_workspace_bytes.argtypes = [C.POINTER(Dims), C.POINTER(StageDpOpts), C.POINTER(C.c_size_t)]
 _lib.hmpc_stage_dp_solve_f64.argtypes = [C.POINTER(Dims), _MatArr, _StrideArr, _P, _P, C.c_int64, _P, _P, _P,
-                                         C.POINTER(StageDpOpts), _P, C.c_size_t, _P, _P, _P, _P, _P]
+                                         C.POINTER(StageTerms), C.POINTER(StageDpOpts), _P, C.c_size_t, _P, _P, _P,
+                                         _P, _P]
 _lib.hmpc_lsim_step_f64.argtypes = [C.POINTER(Dims), _MatArr, _StrideArr] + [_P] * 5 + [C.c_double] + [_P] * 4
 _lib.hmpc_dewh_sim_step_f64.argtypes = [C.c_int32] + [_P] * 8
 _lib.hmpc_dewh_control_model_f64.argtypes = [C.c_int32, _P, _P, _P]
@@ -295,8 +303,39 @@ def _dp_workspace(d, o, dev):
     return ws, need.value
 
 
-def stage_dp_solve(d, mats, rhs, cost_v, lb, ub, is_bin, opts=None):
-    """K3s/K4s.  mats as for condense(); rhs [B, nc*Nt]; cost_v [B|1, nv*Nt]; lb/ub [nv*Nt]; is_bin uint8 [nv*Nt]."""
+def _stage_terms(d, terms, dev):
+    """dict(h [B|1,T], ga [B|1,T,nb], r [B,Nt,T], wq/w1 [B|1,Nt,T], qmu [B|1,Nt,nc]) of device tensors -> struct."""
+    st = StageTerms()
+    keep = []
+    if not terms:
+        return None, keep
+    nb = d.nu + d.ndelta
+    T = 0 if terms.get("h") is None else terms["h"].shape[-1]
+    st.T = T
+
+    def put(name, inner):
+        t = terms.get(name)
+        if t is None:
+            return None, 0
+        t = t.to(device=dev, dtype=torch.float64).reshape((-1,) + inner).contiguous()
+        keep.append(t)
+        n = int(np.prod(inner))
+        return t.data_ptr(), (n if t.shape[0] == d.B and d.B > 1 or d.B == 1 else 0)
+    if T:
+        st.h, st.h_stride_b = put("h", (T,))
+        st.ga, st.ga_stride_b = put("ga", (T, nb))
+        r = terms["r"].to(device=dev, dtype=torch.float64).reshape(d.B, d.Nt, T).contiguous()
+        keep.append(r)
+        st.r = r.data_ptr()
+        st.wq, st.wq_stride_b = put("wq", (d.Nt, T))
+        st.w1, st.w1_stride_b = put("w1", (d.Nt, T))
+    st.qmu, st.qmu_stride_b = put("qmu", (d.Nt, d.nc))
+    return st, keep
+
+
+def stage_dp_solve(d, mats, rhs, cost_v, lb, ub, is_bin, opts=None, terms=None):
+    """K3s/K4s.  mats as for condense(); rhs [B, nc*Nt]; cost_v [B|1, nv*Nt]; lb/ub [nv*Nt]; is_bin uint8 [nv*Nt];
+    terms: optional convex state / slack terms (see hmpc_stage_terms) -> an MIQP."""
     global launch_count
     arr, strides, keep = _pack_mats(d, mats)
     nvt = (d.nu + d.ndelta + d.nmu) * d.Nt
@@ -304,13 +343,15 @@ def stage_dp_solve(d, mats, rhs, cost_v, lb, ub, is_bin, opts=None):
     c2 = cost_v.reshape(-1, nvt)
     o = opts if opts is not None else stage_dp_default_opts()
     ws, nbytes = _dp_workspace(d, o, dev)
+    st, keep_terms = _stage_terms(d, terms, dev)
     v = torch.empty((d.B, nvt), dtype=torch.float64, device=dev)
     obj = torch.empty((d.B,), dtype=torch.float64, device=dev)
     status = torch.empty((d.B,), dtype=torch.int32, device=dev)
     stats = torch.empty((d.B, 8), dtype=torch.int32, device=dev)
     _check(_lib.hmpc_stage_dp_solve_f64(C.byref(d), arr, strides, _ptr(rhs) if d.nc else None, _ptr(c2),
                                         nvt if (c2.shape[0] == d.B and d.B > 1) or d.B == 1 else 0,
-                                        _ptr(lb.reshape(-1)), _ptr(ub.reshape(-1)), _ptr(is_bin), C.byref(o),
+                                        _ptr(lb.reshape(-1)), _ptr(ub.reshape(-1)), _ptr(is_bin),
+                                        C.byref(st) if st is not None else None, C.byref(o),
                                         C.c_void_p(ws.data_ptr()), nbytes, _ptr(v), _ptr(obj), _ptr(status),
                                         _ptr(stats), _stream()), "hmpc_stage_dp_solve_f64")
     launch_count += 2

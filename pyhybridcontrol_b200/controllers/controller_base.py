@@ -375,7 +375,7 @@ class ConstraintSolvedController(ControllerBase):
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
         res = batch.solve(x0, w, cost_v=terms["cost_v"], w_x=terms["w_x"], w_y=terms["w_y"], extra_constraints=extra,
-                          with_std_constraints=with_std)
+                          with_std_constraints=with_std, quad=terms.get("quad"))
         ev1.record()
         status = int(res["status"].cpu()[0])
         self._solve_time_solver = ev0.elapsed_time(ev1) * 1e-3

@@ -56,11 +56,32 @@ class MpcController(PredictiveController):
         self._sense = sense
         if self._with_std_objective and self._std_obj_atoms is not None:
             for atom in self._std_obj_atoms.iter_atoms():
-                if atom.atom_type != "Linear":
-                    raise NotImplementedError("cost atom %s on '%s': only Linear atoms run on the GPU path this "
-                                              "round (MIQP / L1 epigraphs: DESIGN.md section 8)" %
-                                              (atom.atom_type, atom.var_name))
+                self._check_atom(atom)
         self._finish_build()
+
+    def _check_atom(self, atom):
+        """Linear atoms run on both solve kernels; Quadratic / L22 / L1 atoms (an MIQP) run on the stage-DP kernels
+        when the MLD is in their class, with per-step diagonal weights and no rate form."""
+        if atom.atom_type == "Linear":
+            return
+        batch = self._mld_evo_matrices.batch
+        why = None
+        if atom.atom_type == "Linf":
+            why = "Linf atoms are not supported"
+        elif not batch.stage_dp_ok:
+            why = "the MLD is outside the stage-DP class (scalar state, binary inputs) and branch-and-cut is an MILP solver"
+        elif atom.is_rate_atom:
+            why = "non-linear rate atoms couple consecutive stages"
+        elif atom.var_name in ("v", "z", "omega"):
+            why = "only x, y, u, delta and mu carry non-linear atoms"
+        elif self._sense.lower().startswith("max"):
+            why = "maximising a convex term is not a convex problem"
+        elif atom.weight_type == "matrix":
+            W = atom.weight_N_tilde
+            if np.any(W - np.diag(np.diag(W)) != 0.0):
+                why = "matrix weights must be diagonal (stage-separable)"
+        if why:
+            raise NotImplementedError("cost atom %s on '%s': %s" % (atom.atom_type, atom.var_name, why))
 
     def _cost_terms(self, k):
         info = self.mld_info_k
@@ -70,12 +91,27 @@ class MpcController(PredictiveController):
         cost_v = np.zeros((1, info.nv * Nt))
         w_x = w_y = None
         const = 0.0
+        quad = {}
         if self._with_std_objective and self._std_obj_atoms is not None:
             prev = self.variables_k_neg1 or {}
             for atom in self._std_obj_atoms.iter_atoms():
                 W = atom.weight_N_tilde
-                g = W.ravel() if atom.weight_type == "vector" else W.sum(axis=0)      # w'e | sum(W e)
                 dim = atom.dim
+                if atom.atom_type != "Linear":
+                    # per-step diagonal weight of e^2 (Quadratic / L22: vector weights enter squared,
+                    # objective_atoms.py:320-336) or of |e| (L1, :338-347)
+                    sq = atom.atom_type in ("Quadratic", "L22")
+                    if atom.weight_type == "vector":
+                        wd = W.ravel() ** 2 if sq else np.abs(W.ravel())
+                    else:
+                        wd = np.diag(W) if sq else np.abs(np.diag(W))
+                    if atom.var_name == "mu" and not sq:
+                        cost_v[0, batch.var_index("mu")] += wd            # mu >= 0: |mu| = mu
+                        continue
+                    key = atom.var_name + ("2" if sq else "1")
+                    quad[key] = quad.get(key, 0.0) + wd.reshape(1, Nt, dim)
+                    continue
+                g = W.ravel() if atom.weight_type == "vector" else W.sum(axis=0)      # w'e | sum(W e)
                 if atom.is_rate_atom:
                     # sum_k g_k' (e_k - e_{k-1}) = sum_k (g_k - g_{k+1})' e_k - g_0' e_{-1}
                     g2 = g.copy()
@@ -97,4 +133,4 @@ class MpcController(PredictiveController):
                 elif name == "omega":
                     const += float(g @ self._omega_tilde_k.ravel())
         return dict(cost_v=sign * cost_v, w_x=None if w_x is None else sign * w_x,
-                    w_y=None if w_y is None else sign * w_y, const=sign * const)
+                    w_y=None if w_y is None else sign * w_y, const=sign * const, quad=quad or None)

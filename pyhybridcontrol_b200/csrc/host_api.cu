@@ -212,7 +212,7 @@ extern "C" int hmpc_mpc_step_host_f64(hmpc_step_plan* p, int32_t recondense, con
         // scalar-state class: exact stage-DP kernels straight from the MLD blocks
         p->last_solver = 1;
         rc = hmpc_stage_dp_solve_f64(&d, dev_mats, dev_stride, p->rhs, p->cost, bc ? 0 : p->nvt, p->lb, p->ub, p->is_bin,
-                                     &p->dp_opts, p->dp_ws, p->dp_ws_bytes, p->v, p->obj, p->status, p->stats, s);
+                                     nullptr, &p->dp_opts, p->dp_ws, p->dp_ws_bytes, p->v, p->obj, p->status, p->stats, s);
     } else {
         rc = solve_bnc();
     }

@@ -27,6 +27,7 @@
 //     the table and lands on (or next to) the optimum; the rest of the search is the optimality proof.
 // Work: Nt * G cell updates (~25 FP64 operations each) + a few hundred scalar nodes per agent -- against
 // ~10^3..10^5 dense simplex pivots of the general branch-and-cut kernel (milp_bnc.cu) on the same problems.
+#include <string.h>
 #include "common.cuh"
 
 namespace hmpc {
@@ -36,6 +37,7 @@ constexpr int kDpMaxNb = 4;
 constexpr int kDpMaxAct = 1 << kDpMaxNb;
 constexpr int kDpMaxNc = 8;
 constexpr int kDpMaxNt = 128;
+constexpr int kDpMaxT = 4;           // extra state terms per stage
 constexpr int kSearchWarps = 4;
 constexpr int kStackCap = 512;        // open nodes per agent
 constexpr double kEdgeEps = 1e-9;     // cell-boundary guard (fraction of a cell)
@@ -50,7 +52,8 @@ struct DpArgs {
     const double* lb; const double* ub;  // [Nt*nv] shared by the batch
     const uint8_t* is_bin;             // [Nt*nv]
     hmpc_stage_dp_opts o;
-    int G, nb, nact, nv;
+    hmpc_stage_terms t;                // optional convex state / slack terms (T == 0 and qmu == NULL: none)
+    int G, nb, nact, nv, T;
     float* table;                      // [B, Nt, G]   (stage 0 unused)
     double* pblk;                      // [B, plan doubles]: the agent's stage data, handed from kernel 1 to kernel 2
     double* v; double* obj; int32_t* status; int32_t* stats;
@@ -61,6 +64,7 @@ struct DpArgs {
 struct DpPlan {
     int ak, iak, cu, qs, rhs, tailmin, amask, e, dscale, galpha, falpha, misc, nd;   // persistent part
     int x_eak, x_foff, x_hq, x_ca, x_shift;
+    int t_h, t_ga, t_r, t_wq, t_w1, qq;
     int scr;                                                                      // load-time scratch [6*Nt]
     int mst;                                                                      // staged MLD blocks [11][64]
     int sc_ca, sc_base, sc_slope, sc_i0, sc_span, sc_flags;                       // per-stage sweep constants
@@ -69,7 +73,7 @@ struct DpPlan {
 
 constexpr int kMstMats = 11, kMstElems = 64;
 
-__host__ __device__ inline DpPlan make_dp_plan(int Nt, int nb, int nc) {
+__host__ __device__ inline DpPlan make_dp_plan(int Nt, int nb, int nc, int T = kDpMaxT) {
     DpPlan p;
     const int nact = 1 << nb;
     int o = 0;
@@ -82,6 +86,9 @@ __host__ __device__ inline DpPlan make_dp_plan(int Nt, int nb, int nc) {
     // action cost, translation of s
     p.x_eak = take(Nt * nc); p.x_foff = take(Nt * nc * nact); p.x_hq = take(Nt * nc); p.x_ca = take(Nt * nact);
     p.x_shift = take(Nt * nact);
+    // optional convex terms: tau = t_h p + t_ga[al] + t_r[k];  cost += t_wq tau^2 + t_w1 |tau|;  slack: qq v^2
+    p.t_h = take(T); p.t_ga = take(T * nact); p.t_r = take(Nt * T); p.t_wq = take(Nt * T); p.t_w1 = take(Nt * T);
+    p.qq = take(Nt * nc);
     p.nd = (o + 1) & ~1;
     o = p.nd;
     p.scr = take(6 * Nt);
@@ -93,20 +100,23 @@ __host__ __device__ inline DpPlan make_dp_plan(int Nt, int nb, int nc) {
     return p;
 }
 
-enum { MISC_S0 = 0, MISC_W, MISC_A, MISC_FLAG, MISC_INVW, MISC_SIMPLE };
+enum { MISC_S0 = 0, MISC_W, MISC_A, MISC_FLAG, MISC_INVW, MISC_SIMPLE, MISC_TERMS };
 
 struct DpCtx {
     int Nt, nb, nc, nact, nmu, nv, G;
     double *ak, *iak, *cu, *qs, *rhs, *tailmin, *amask, *e, *dscale, *galpha, *falpha, *misc, *scr, *mst;
     double *sc_ca, *sc_base, *sc_slope; int *sc_i0, *sc_span, *sc_flags;
     double *x_eak, *x_foff, *x_hq, *x_ca, *x_shift;
+    double *t_h, *t_ga, *t_r, *t_wq, *t_w1, *qq;
+    int T;
     double feas_tol;
 };
 
 __device__ inline DpCtx bind_ctx(const DpArgs& A, unsigned char* smem) {
     DpCtx c;
     c.Nt = A.d.Nt; c.nb = A.nb; c.nc = A.d.nc; c.nact = A.nact; c.nmu = A.d.nmu; c.nv = A.nv; c.G = A.G;
-    const DpPlan p = make_dp_plan(c.Nt, c.nb, c.nc);
+    c.T = A.T;
+    const DpPlan p = make_dp_plan(c.Nt, c.nb, c.nc, c.T);
     double* sd = reinterpret_cast<double*>(smem);
     c.ak = sd + p.ak; c.iak = sd + p.iak; c.cu = sd + p.cu; c.qs = sd + p.qs; c.rhs = sd + p.rhs;
     c.tailmin = sd + p.tailmin; c.amask = sd + p.amask; c.e = sd + p.e; c.dscale = sd + p.dscale;
@@ -115,6 +125,7 @@ __device__ inline DpCtx bind_ctx(const DpArgs& A, unsigned char* smem) {
     c.sc_i0 = reinterpret_cast<int*>(sd + p.sc_i0); c.sc_span = reinterpret_cast<int*>(sd + p.sc_span);
     c.sc_flags = reinterpret_cast<int*>(sd + p.sc_flags);
     c.x_eak = sd + p.x_eak; c.x_foff = sd + p.x_foff; c.x_hq = sd + p.x_hq; c.x_ca = sd + p.x_ca; c.x_shift = sd + p.x_shift;
+    c.t_h = sd + p.t_h; c.t_ga = sd + p.t_ga; c.t_r = sd + p.t_r; c.t_wq = sd + p.t_wq; c.t_w1 = sd + p.t_w1; c.qq = sd + p.qq;
     c.feas_tol = A.o.feas_tol;
     return c;
 }
@@ -187,7 +198,16 @@ __device__ inline void dp_load(const DpArgs& A, int b, DpCtx& c) {
                 c.falpha[i * nact + al] = fa;
             }
         }
+        for (int t = 0; t < c.T; ++t) {
+            c.t_h[t] = A.t.h[(int64_t)b * A.t.h_stride_b + t];
+            for (int al = 0; al < nact; ++al) {
+                double ga = 0.0;
+                if (A.t.ga) for (int j = 0; j < nb; ++j) if (al >> j & 1) ga += A.t.ga[(int64_t)b * A.t.ga_stride_b + t * nb + j];
+                c.t_ga[t * nact + al] = ga;
+            }
+        }
         c.misc[MISC_FLAG] = (double)flag;
+        c.misc[MISC_TERMS] = (c.T > 0 || A.t.qmu) ? 1.0 : 0.0;
     }
     __syncthreads();
     // ---- per-stage data, one stage per thread
@@ -222,6 +242,21 @@ __device__ inline void dp_load(const DpArgs& A, int b, DpCtx& c) {
                 } else if (q < 0.0 && ubm > 0.0) bad = 1;         // free column with negative cost: unbounded
             }
             c.qs[k * nc + i] = qs;
+            // quadratic slack price: Qmu mu^2 = (Qmu / d^2) max(0, violation)^2
+            double qq = 0.0;
+            if (A.t.qmu && nmu) {
+                const double Q = A.t.qmu[(int64_t)b * A.t.qmu_stride_b + k * nc + i], di = c.dscale[i];
+                if (Q < 0.0) bad = 1;
+                if (Q > 0.0) { if (isinf(qs)) qq = 0.0; else qq = Q / (di * di); }
+            }
+            c.qq[k * nc + i] = qq;
+        }
+        for (int t = 0; t < c.T; ++t) {
+            c.t_r[k * c.T + t] = A.t.r[((int64_t)b * Nt + k) * c.T + t];
+            const double wq = A.t.wq ? A.t.wq[(int64_t)b * A.t.wq_stride_b + k * c.T + t] : 0.0;
+            const double w1 = A.t.w1 ? A.t.w1[(int64_t)b * A.t.w1_stride_b + k * c.T + t] : 0.0;
+            if (wq < 0.0 || w1 < 0.0) bad = 1;          // concave term: not a convex stage cost
+            c.t_wq[k * c.T + t] = wq; c.t_w1[k * c.T + t] = w1;
         }
         // shifts, cheapest action, violation-free band of this stage (all in s = p / a^k)
         const double ik = 1.0 / c.ak[k], ik1 = 1.0 / c.ak[k + 1];
@@ -284,12 +319,33 @@ __device__ __forceinline__ double stage_cost(const DpCtx& c, int k, int al, doub
         const double viol = fma(c.e[i], p, c.falpha[i * c.nact + al] - c.rhs[k * c.nc + i]);
         const double qs = c.qs[k * c.nc + i];
         if (isinf(qs)) { if (viol > c.feas_tol) st = INFINITY; }
-        else st = fma(qs, fmax(viol, 0.0), st);
+        else {
+            const double v = fmax(viol, 0.0);
+            st = fma(qs, v, st);
+            st = fma(c.qq[k * c.nc + i] * v, v, st);
+        }
+    }
+    for (int t = 0; t < c.T; ++t) {
+        const double tau = fma(c.t_h[t], p, c.t_ga[t * c.nact + al] + c.t_r[k * c.T + t]);
+        st = fma(c.t_wq[k * c.T + t] * tau, tau, st);
+        st = fma(c.t_w1[k * c.T + t], fabs(tau), st);
     }
     return st;
 }
 
-// ------------------------------------------------------------------------------------------------ kernel 1
+// lower bound over p in [plo, phi] of the convex extra terms of stage k under action al
+__device__ __forceinline__ double terms_lower_bound(const DpCtx& c, int k, int al, double plo, double phi) {
+    double st = 0.0;
+    for (int t = 0; t < c.T; ++t) {
+        const double cst = c.t_ga[t * c.nact + al] + c.t_r[k * c.T + t];
+        const double t1 = fma(c.t_h[t], plo, cst), t2 = fma(c.t_h[t], phi, cst);
+        const double m = (t1 <= 0.0 && t2 >= 0.0) || (t2 <= 0.0 && t1 >= 0.0) ? 0.0 : fmin(fabs(t1), fabs(t2));
+        st = fma(c.t_wq[k * c.T + t] * m, m, st);
+        st = fma(c.t_w1[k * c.T + t], m, st);
+    }
+    return st;
+}
+
 // Hot loop of the backward sweep over the cells [lo, hi) whose translated neighbours are all inside the table:
 // no bound checks, every per-stage constant in registers.  q max(v, 0) is evaluated as (q/2) (v + |v|) -- exact,
 // and |v| is a free operand modifier of the FP64 add.
@@ -360,7 +416,7 @@ __global__ void __launch_bounds__(512) stage_dp_table_kernel(const DpArgs A) {
     const int b = blockIdx.x;
     const int nthr = blockDim.x;
     DpCtx c = bind_ctx(A, smem);
-    const DpPlan plan = make_dp_plan(c.Nt, c.nb, c.nc);
+    const DpPlan plan = make_dp_plan(c.Nt, c.nb, c.nc, c.T);
     // two stage buffers (k+1 / k), each with `pad` guard cells on both sides that hold the out-of-window bound, so
     // that the hot loop needs no bound checks
     const int pad = G_PAD(A.G);
@@ -379,7 +435,7 @@ __global__ void __launch_bounds__(512) stage_dp_table_kernel(const DpArgs A) {
     for (int k = threadIdx.x; k < Nt; k += nthr) {
         const double akk = c.ak[k];
         const int mask = (int)c.amask[k];
-        int fast = mask == (1 << nact) - 1, same = 1;
+        int fast = mask == (1 << nact) - 1 && c.misc[MISC_TERMS] == 0.0, same = 1;
         for (int i = 0; i < nc; ++i) {
             c.sc_slope[k * nc + i] = c.e[i] * akk * w;
             if (isinf(c.qs[k * nc + i])) fast = 0;
@@ -418,7 +474,7 @@ __global__ void __launch_bounds__(512) stage_dp_table_kernel(const DpArgs A) {
             c.x_ca[k * nact + al] = c.sc_ca[k * nact + al];
             c.x_shift[k * nact + al] = c.galpha[al] * c.iak[k + 1];
         }
-        if (!(mask == (1 << nact) - 1)) c.misc[MISC_SIMPLE] = 0.0;      // benign race: same value from every writer
+        if (!(mask == (1 << nact) - 1) || c.misc[MISC_TERMS] != 0.0) c.misc[MISC_SIMPLE] = 0.0;   // benign race: same value from every writer
         for (int i = 0; i < nc; ++i) if (isinf(c.qs[k * nc + i])) c.misc[MISC_SIMPLE] = 0.0;
     }
     __syncthreads();
@@ -458,7 +514,16 @@ __global__ void __launch_bounds__(512) stage_dp_table_kernel(const DpArgs A) {
                         const double viol = fma(cd, s_slope[i], s_base[i * nact + al]);
                         const double q = s_q[i];
                         if (isinf(q)) { if (viol > c.feas_tol) st = INFINITY; }
-                        else st = fma(q, viol > 0.0 ? viol : 0.0, st);
+                        else {
+                            const double v = viol > 0.0 ? viol : 0.0;
+                            st = fma(q, v, st);
+                            st = fma(c.qq[k * nc + i] * v, v, st);
+                        }
+                    }
+                    if (c.T > 0) {
+                        const double plo = c.ak[k] * fma(cd - kEdgeEps, w, S0);
+                        const double phi = c.ak[k] * fma(cd + 1.0 + kEdgeEps, w, S0);
+                        st += terms_lower_bound(c, k, al, plo, phi);
                     }
                     const int span = s_span[al];
                     const long long c0 = (long long)cell + s_i0[al];
@@ -592,7 +657,7 @@ __global__ void __launch_bounds__(kSearchWarps * 32) stage_dp_search_kernel(cons
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.x * kSearchWarps + warp;
     if (b >= A.d.B) return;
-    const DpPlan plan = make_dp_plan(A.d.Nt, A.nb, A.d.nc);
+    const DpPlan plan = make_dp_plan(A.d.Nt, A.nb, A.d.nc, A.T);
     const size_t per_warp = (size_t)plan.nd * 8 + sizeof(Node) * kStackCap + 8 * (kDpMaxNt + 1);
     unsigned char* base = smem + per_warp * warp;
     DpCtx c = bind_ctx(A, base);
@@ -774,9 +839,9 @@ extern "C" int hmpc_stage_dp_workspace_bytes(const hmpc_dims* d, const hmpc_stag
 extern "C" int hmpc_stage_dp_solve_f64(const hmpc_dims* dims, const double* const mats[HMPC_NUM_MATS],
                                        const int64_t mat_stride_b[HMPC_NUM_MATS], const double* rhs,
                                        const double* cost_v, int64_t cost_v_stride_b, const double* lb_v,
-                                       const double* ub_v, const uint8_t* is_bin_v, const hmpc_stage_dp_opts* opts,
-                                       void* workspace, size_t workspace_bytes, double* v, double* obj,
-                                       int32_t* status, int32_t* stats, void* stream) {
+                                       const double* ub_v, const uint8_t* is_bin_v, const hmpc_stage_terms* terms,
+                                       const hmpc_stage_dp_opts* opts, void* workspace, size_t workspace_bytes,
+                                       double* v, double* obj, int32_t* status, int32_t* stats, void* stream) {
     using namespace hmpc;
     if (!dims || !mats || !mat_stride_b || !cost_v || !lb_v || !ub_v || !is_bin_v || !v || !obj || !status || !stats)
         return HMPC_ERR_ARG;
@@ -789,6 +854,13 @@ extern "C" int hmpc_stage_dp_solve_f64(const hmpc_dims* dims, const double* cons
     if (opts) a.o = *opts; else hmpc_stage_dp_default_opts(&a.o);
     if (a.o.cells < 64) return HMPC_ERR_ARG;
     a.G = a.o.cells; a.nb = dims->nu + dims->ndelta; a.nact = 1 << a.nb; a.nv = a.nb + dims->nmu;
+    memset(&a.t, 0, sizeof(a.t));
+    if (terms) {
+        if (terms->T < 0 || terms->T > kDpMaxT) return HMPC_ERR_ARG;
+        if (terms->T > 0 && (!terms->h || !terms->r || (!terms->wq && !terms->w1))) return HMPC_ERR_ARG;
+        a.t = *terms;
+    }
+    a.T = a.t.T;
     a.rhs = rhs; a.cost = cost_v; a.sc = cost_v_stride_b; a.lb = lb_v; a.ub = ub_v; a.is_bin = is_bin_v;
     size_t need = 0;
     hmpc_stage_dp_workspace_bytes(dims, &a.o, &need);
@@ -796,7 +868,7 @@ extern "C" int hmpc_stage_dp_solve_f64(const hmpc_dims* dims, const double* cons
     a.table = reinterpret_cast<float*>(workspace);
     a.pblk = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(workspace) + ((table_bytes(dims->B, dims->Nt, a.G) + 255) & ~(size_t)255));
     a.v = v; a.obj = obj; a.status = status; a.stats = stats;
-    const DpPlan plan = make_dp_plan(dims->Nt, a.nb, dims->nc);
+    const DpPlan plan = make_dp_plan(dims->Nt, a.nb, dims->nc, a.T);
     const size_t smem1 = (size_t)plan.total * 8 + 2 * (size_t)(a.G + 2 * G_PAD(a.G)) * sizeof(float);
     const size_t smem2 = ((size_t)plan.nd * 8 + sizeof(Node) * kStackCap + 8 * (kDpMaxNt + 1)) * kSearchWarps;
     int dev = 0, smem_optin = 0;

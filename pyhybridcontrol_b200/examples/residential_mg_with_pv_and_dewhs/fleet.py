@@ -74,3 +74,30 @@ class DewhFleet(object):
     def aggregate_power(self, u):
         """sum_b P_nom[b] u[b, k] over this rank's agents, then over ranks -> [Nt]."""
         return distributed.allreduce_aggregate(cabi.aggregate_power(u, self.P_nom))
+
+    def closed_loop(self, T0, demand, price, sim_steps, demand_actual=None):
+        """Closed-loop simulation of the shard (reference loop: examples/.../micro_grid_control_simulation.py:184-236
+        with the per-device work of micro_grid_agents.py:699-700, 733-740): at every step k the forecast window
+        demand[:, k:k+Nt] and price[k:k+Nt] give the MPC problem, the first control is applied to the re-parametrised
+        simulation model with the actual draw, and the aggregate power is exchanged.  Everything stays in HBM; the
+        log comes back as device tensors.
+
+        T0 [B] initial temperatures; demand [B, sim_steps + Nt] (L/s); price [sim_steps + Nt] or [B, sim_steps + Nt];
+        demand_actual [B, sim_steps] defaults to demand[:, :sim_steps].
+        -> dict(T [sim_steps + 1, B], u [sim_steps, B], obj [sim_steps, B], status [sim_steps, B],
+                P_agg [sim_steps, Nt], cons [sim_steps, B, 2])"""
+        dev, B, Nt = self.device, self.B, self.Nt
+        T = torch.as_tensor(T0, dtype=torch.float64).to(dev).reshape(B).clone()
+        demand = torch.as_tensor(demand, dtype=torch.float64).to(dev)
+        price = torch.as_tensor(price, dtype=torch.float64).to(dev)
+        actual = demand[:, :sim_steps] if demand_actual is None else torch.as_tensor(demand_actual, dtype=torch.float64).to(dev)
+        log = dict(T=[T.clone()], u=[], obj=[], status=[], P_agg=[], cons=[])
+        self.build()                                   # the control model does not change along the run
+        for k in range(sim_steps):
+            pk = price[k:k + Nt] if price.dim() == 1 else price[:, k:k + Nt]
+            res = self.control_step(T.reshape(B, 1), demand[:, k:k + Nt].contiguous(), self.cost_from_prices(pk))
+            u0 = res["u"][:, 0].contiguous()
+            T, cons = self.sim_step(T, u0, actual[:, k].contiguous())
+            log["T"].append(T.clone()); log["u"].append(u0); log["obj"].append(res["obj"])
+            log["status"].append(res["status"]); log["P_agg"].append(self.aggregate_power(res["u"])); log["cons"].append(cons)
+        return {k: torch.stack(v) for k, v in log.items()}

@@ -132,3 +132,32 @@ def test_lsim_k_aux_and_agents(cuda_device):
     ag.mpc_controller.build()
     fb = ag.mpc_controller.feedback(k=0, x_k=50.5, omega_tilde_k=np.full(7, 0.004))
     assert fb.u[0, 0] in (0.0, 1.0)
+
+
+@pytest.mark.gpu
+def test_mpc_controller_miqp_atoms(cuda_device):
+    """Quadratic / L1 atoms through the reference's cost-atom grammar (objective_atoms.py:453-496): set-point tracking
+    Q_x with a linear q_x, a squared slack penalty and an L1 output term -- an MIQP, checked against enumeration."""
+    from oracle import mld as omld, condense as oc, assemble as oa, solve as osv
+    from pyhybridcontrol_b200.controllers.mpc_controller import MpcController
+    from pyhybridcontrol_b200.examples.residential_mg_with_pv_and_dewhs import synthetic as syn
+    N_p = 8
+    wl = syn.dewh_batch(1, N_p, seed=31)
+    mats = {k: v[0] for k, v in wl["mats"].items()}
+    scale = float(wl["q_u"].mean())
+    atoms = dict(q_u=wl["q_u"][0], q_mu=wl["q_mu"][0], Q_x=0.5 * scale, q_x=-2 * 0.5 * scale * 62.0,
+                 q_L22_mu=[1.2, 0.4], q_L1_y=0.05 * scale)
+    ctrl = MpcController(model=MldSystemModel(mld_numeric=MldModel(nu_l=1, **mats)), N_p=N_p)
+    ctrl.set_std_obj_atoms(**atoms)
+    ctrl.build()
+    obj = ctrl.solve(k=0, x_k=wl["x0"][0], omega_tilde_k=wl["omega"][0])
+    full, d, vt = omld.complete(mats, nu_l=1)
+    prob = oa.build_problem(oc.condense(full, d, N_p + 1), d, vt, N_p + 1, wl["x0"][0], wl["omega"][0], atoms=atoms)
+    st, oref, vref, second = osv.solve_enumerate(prob)
+    assert abs(obj - oref) <= 1e-6 * max(1.0, abs(oref)), (obj, oref)
+    fb = ctrl.feedback(k=0)
+    if second - oref > 1e-6 * max(1.0, abs(oref)):
+        assert fb.u[0, 0] == round(vref[0])
+    with pytest.raises(NotImplementedError):
+        ctrl.set_std_obj_atoms(q_Linf_x=1.0)
+        ctrl.build()

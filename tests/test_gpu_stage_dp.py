@@ -237,3 +237,99 @@ def test_stage_dp_folds_extra_constraint_sets(cuda_device):
     assert (res["stage_dp"][2] == 0).all() and (res["bnc"][2] == 0).all()
     np.testing.assert_allclose(res["stage_dp"][0], res["bnc"][0], rtol=1e-6)
     assert np.array_equal(res["stage_dp"][1][:, ::3], np.round(res["bnc"][1][:, ::3]))
+
+
+def test_closed_loop_fleet_vs_oracle(cuda_device):
+    """BASELINE config 4 in miniature: closed-loop simulation (per-step exact solve + re-parametrised DEWH sim step +
+    aggregate power) of a small fleet, every step checked against the oracle (HiGHS solve, numpy sim step)."""
+    from oracle import mld as omld, condense as oc, assemble as oa, solve as osv, lsim as ol
+    from pyhybridcontrol_b200.examples.residential_mg_with_pv_and_dewhs import synthetic as syn
+    from pyhybridcontrol_b200.examples.residential_mg_with_pv_and_dewhs.fleet import DewhFleet
+    B, N_p, steps = 5, 16, 10
+    Nt = N_p + 1
+    params = [syn.dewh_agent_params(100 + b) for b in range(B)]
+    T0 = np.array([syn.dewh_initial_state(100 + b) for b in range(B)])
+    demand = np.stack([syn.dhw_demand_profile(steps + Nt, seed=100 + b) for b in range(B)])
+    price = syn.price_profile(steps + Nt, seed=3)
+    fleet = DewhFleet(params, N_p, device=cuda_device)
+    log = {k: v.cpu().numpy() for k, v in fleet.closed_loop(T0, demand, price, steps).items()}
+    assert (log["status"] == 0).all()
+    T = T0.copy()
+    for k in range(steps):
+        u0 = np.zeros(B)
+        p_agg = np.zeros(Nt)
+        for b in range(B):
+            p = params[b]
+            mats = syn.dewh_scalars(p, const_heat=True)
+            m = dict(A=[[mats[0]]], B1=[[mats[1]]], B4=[[mats[2]]], b5=[[mats[3]]], E=[[1.0], [-1.0]], F1=[[0.0], [0.0]],
+                     Psi=[[-1.0, 0.0], [0.0, -1.0]], f5=[[p["T_h_max"]], [-p["T_h_min"]]])
+            full, d, vt = omld.complete({kk: np.array(vv, dtype=float) for kk, vv in m.items()}, nu_l=1)
+            q_u = price[k:k + Nt] * p["P_h_Nom"]
+            prob = oa.build_problem(oc.condense(full, d, Nt), d, vt, Nt, np.array([T[b]]), demand[b, k:k + Nt],
+                                    atoms=dict(q_u=q_u, q_mu=[10.0 * q_u.sum(), 1.0 * q_u.sum()]))
+            st, obj, v = osv.solve_milp(prob, polish=True)
+            assert abs(log["obj"][k, b] - obj) <= 1e-6 * max(1.0, abs(obj)), (k, b)
+            u = np.round(v[prob.is_bin])
+            u0[b] = u[0]
+            p_agg += p["P_h_Nom"] * u
+            assert log["u"][k, b] == u0[b], (k, b)
+        np.testing.assert_allclose(log["P_agg"][k], p_agg, rtol=1e-12)
+        for b in range(B):
+            T[b], _, _ = ol.dewh_sim_step(dict(params[b]), T[b], u0[b], demand[b, k])
+        np.testing.assert_allclose(log["T"][k + 1], T, rtol=1e-10)
+
+
+MIQP_CASES = [
+    dict(Q_x=0.5, q_x=-2 * 0.5 * 61.0),                                  # (x - 61)^2 tracking, matrix weight
+    dict(q_L22_x=0.6, q_x=-2 * 0.36 * 63.0, q_L22_mu=[1.5, 0.7]),         # ||w.x||^2 (w enters squared) + ||w.mu||^2
+    dict(q_L1_x=0.3, q_x=-0.5, Q_mu=[[2.0, 0.0], [0.0, 0.5]]),           # |w x| + mu'W mu
+    dict(Q_y=0.4, q_y=-2 * 0.4 * 60.0, q_L22_u=0.2, q_L1_u=0.1),          # outputs; binaries (u^2 = |u| = u)
+]
+
+
+@pytest.mark.parametrize("atoms", MIQP_CASES)
+def test_stage_dp_miqp_atoms_vs_oracle(atoms, cuda_device):
+    """Quadratic / L22 / L1 atoms (reference: controllers/components/objective_atoms.py:320-363) make the problem an
+    MIQP; the stage-DP kernels carry them as convex stage terms.  Checked against exhaustive enumeration with HiGHS
+    QPs (oracle.solve.solve_enumerate) on problems with 9 binaries; set-point tracking terms (Q_x with a linear q_x)
+    compete with the energy cost so that the optimum is not trivial."""
+    from oracle import mld as omld, condense as oc, assemble as oa, solve as osv
+    from pyhybridcontrol_b200.batch import BatchMpc
+    from pyhybridcontrol_b200.examples.residential_mg_with_pv_and_dewhs import synthetic as syn
+    B, N_p = 4, 8
+    wl = syn.dewh_batch(B, N_p, seed=13)
+    Nt = wl["Nt"]
+    bm = BatchMpc(wl["mats"], N_p, nu_l=1, device=cuda_device, solver="stage_dp")
+    bm.build()
+    cost = np.zeros((B, Nt, 3))
+    cost[:, :, 0] = wl["q_u"]
+    cost[:, :, 1:] = wl["q_mu"][:, None, :]
+    scale = float(wl["q_u"].mean())          # state / output weights in units of the energy price
+    quad, lin = {}, {}
+    scaled = {}
+    for key, val in atoms.items():
+        wt, atom, var, rate, post = oa.parse_atom_key(key)
+        w = np.atleast_1d(np.asarray(val, dtype=float)) * (scale if var in ("x", "y") else 1.0)
+        scaled[key] = w if np.ndim(val) else float(w[0])
+        if atom == "Linear":
+            lin[var] = np.tile(w.reshape(1, 1, -1), (B, Nt, 1)).reshape(B, -1)
+            continue
+        w_eff = (w ** 2 if atom in ("Quadratic", "L22") else np.abs(w)) if wt == "vector" else np.diag(np.atleast_2d(w))
+        name = var + ("2" if atom in ("Quadratic", "L22") else "1")
+        quad[name] = quad.get(name, 0) + np.tile(w_eff.reshape(1, 1, -1), (1, Nt, 1))
+    res = bm.solve(wl["x0"], wl["omega"], cost_v=cost.reshape(B, -1), w_x=lin.get("x"), w_y=lin.get("y"), quad=quad)
+    obj, v, st = res["obj"].cpu().numpy(), res["v"].cpu().numpy(), res["status"].cpu().numpy()
+    assert (st == 0).all()
+    nontrivial = 0
+    for b in range(B):
+        full, d, vt = omld.complete({k: m[b] for k, m in wl["mats"].items()}, nu_l=1)
+        at = dict(q_u=wl["q_u"][b], q_mu=wl["q_mu"][b])
+        for key, val in scaled.items():
+            at[key] = at[key] + val if key in at else val
+        prob = oa.build_problem(oc.condense(full, d, Nt), d, vt, Nt, wl["x0"][b], wl["omega"][b], atoms=at)
+        s_, o_, v_, second = osv.solve_enumerate(prob)
+        assert abs(obj[b] - o_) <= 1e-6 * max(1.0, abs(o_)), (b, obj[b], o_)
+        if second - o_ > 1e-6 * max(1.0, abs(o_)):
+            assert np.array_equal(np.round(v[b][::3]), np.round(v_[:3 * Nt][::3])), b
+        nontrivial += int(np.round(v_[:3 * Nt][::3]).sum() > 0)
+    assert nontrivial >= 1
