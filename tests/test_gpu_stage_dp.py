@@ -333,3 +333,72 @@ def test_stage_dp_miqp_atoms_vs_oracle(atoms, cuda_device):
             assert np.array_equal(np.round(v[b][::3]), np.round(v_[:3 * Nt][::3])), b
         nontrivial += int(np.round(v_[:3 * Nt][::3]).sum() > 0)
     assert nontrivial >= 1
+
+
+def test_stage_dp_edge_cases(cuda_device):
+    """Degenerate shapes and limits: a single agent, horizons of one and two steps, an MLD without constraint rows,
+    every binary pinned, a hard row that cannot be met (infeasible), a node budget of one (not proven), three and
+    four binaries per step (8 / 16 actions)."""
+    import torch
+    from pyhybridcontrol_b200 import cabi
+    from pyhybridcontrol_b200.batch import BatchMpc
+    rng = np.random.default_rng(42)
+    dev = cuda_device
+
+    def run(m, Nt, nu, ndelta, nc, soft, B, lb=None, ub=None, dp_opts=None, x0=None):
+        nb, nmu = nu + ndelta, (nc if soft else 0)
+        bm = BatchMpc(m, Nt - 1, Nt, nu_l=nu, device=dev, solver="stage_dp", **({"dp_opts": dp_opts} if dp_opts else {}))
+        if lb is not None:
+            bm.lb_v, bm.ub_v = lb, ub
+        bm.build()
+        cost = np.zeros((B, Nt, nb + nmu))
+        cost[:, :, :nb] = rng.uniform(0.1, 1.0, size=(B, Nt, nb))
+        cost[:, :, nb:] = 10.0
+        x0 = rng.uniform(-0.5, 0.5, size=(B, 1)) if x0 is None else x0
+        om = rng.uniform(-0.5, 0.5, size=(B, Nt))
+        res = bm.solve(x0, om, cost_v=cost.reshape(B, -1))
+        return bm, cost.reshape(B, -1), {k: (v.cpu().numpy() if hasattr(v, "cpu") else v) for k, v in res.items()}
+
+    # (1) B = 1, Nt = 1 and Nt = 2: with positive costs and a wide box the optimum is "all off", objective 0
+    for Nt in (1, 2):
+        m = random_scalar_mld(rng, 1, 1, 0, 2, 1, True)
+        m["f5"] = m["f5"] * 50.0
+        bm, cost, r = run(m, Nt, 1, 0, 2, True, 1)
+        assert r["status"][0] == 0 and abs(r["obj"][0]) < 1e-12 and not r["v"][0].any()
+    # (2) every binary pinned to 1: the cost is the sum of the action costs (+ slack), decisions as pinned
+    Nt = 5
+    m = random_scalar_mld(rng, 3, 1, 0, 2, 1, True)
+    m["f5"] = m["f5"] * 50.0
+    lb = np.tile([1.0, 0.0, 0.0], Nt); ub = np.tile([1.0, np.inf, np.inf], Nt)
+    bm, cost, r = run(m, Nt, 1, 0, 2, True, 3, lb=lb, ub=ub)
+    assert (r["status"] == 0).all() and (r["v"][:, ::3] == 1.0).all()
+    np.testing.assert_allclose(r["obj"], (cost * r["v"]).sum(axis=1), rtol=1e-12)
+    # (3) a hard row that cannot be met -> infeasible, v = nan
+    m = random_scalar_mld(rng, 2, 1, 0, 2, 1, False)
+    m["f5"] = -np.abs(m["f5"]) * 100.0
+    bm, cost, r = run(m, 6, 1, 0, 2, False, 2)
+    assert (r["status"] == 1).all() and np.isinf(r["obj"]).all() and np.isnan(r["v"]).all()
+    # (4) node budget of one expansion: an incumbent exists (the greedy dive) but optimality is not proven
+    from pyhybridcontrol_b200.examples.residential_mg_with_pv_and_dewhs import synthetic as syn
+    wl = syn.dewh_batch(4, 24, seed=2)
+    bm = BatchMpc(wl["mats"], 24, nu_l=1, device=dev, solver="stage_dp", dp_opts=cabi.stage_dp_default_opts(max_nodes=1))
+    bm.build()
+    c = np.zeros((4, 25, 3)); c[:, :, 0] = wl["q_u"]; c[:, :, 1:] = wl["q_mu"][:, None, :]
+    res = bm.solve(wl["x0"], wl["omega"], cost_v=c.reshape(4, -1))
+    assert (res["status"].cpu().numpy() == 2).all() and np.isfinite(res["obj"].cpu().numpy()).all()
+    # (5) 3 and 4 binaries per step against the branch-and-cut kernel
+    for nu, ndelta in ((2, 1), (2, 2)):
+        Nt, nc, B = 5, 3, 6
+        m = random_scalar_mld(rng, B, nu, ndelta, nc, 1, True)
+        nb = nu + ndelta
+        cost = np.zeros((B, Nt, nb + nc)); cost[:, :, :nb] = rng.uniform(-0.2, 1.0, size=(B, Nt, nb)); cost[:, :, nb:] = 8.0
+        x0 = rng.uniform(-1, 1, size=(B, 1)); om = rng.uniform(-1, 1, size=(B, Nt))
+        out = solve_both(m, Nt, nu, ndelta, x0, om, cost.reshape(B, -1), dev)
+        assert (out["stage_dp"]["status"] == 0).all() and (out["bnc"]["status"] == 0).all()
+        np.testing.assert_allclose(out["stage_dp"]["obj"], out["bnc"]["obj"], rtol=1e-7, atol=1e-9)
+    # (6) no constraint rows at all: the solve falls through to the general kernel (nothing to fold)
+    m = dict(A=np.full((2, 1, 1), 0.9), B1=np.ones((2, 1, 1)))
+    bm = BatchMpc(m, 3, 4, nu_l=1, device=dev)
+    bm.build()
+    res = bm.solve(np.zeros((2, 1)), None, cost_v=np.tile([-1.0, 2.0, -3.0, 0.5], (2, 1)))
+    assert res["solver"] == "bnc" and np.allclose(res["obj"].cpu().numpy(), -4.0)
