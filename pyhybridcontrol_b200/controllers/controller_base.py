@@ -376,8 +376,19 @@ class ConstraintSolvedController(ControllerBase):
         ev0.record()
         res = batch.solve(x0, w, cost_v=terms["cost_v"], w_x=terms["w_x"], w_y=terms["w_y"], extra_constraints=extra,
                           with_std_constraints=with_std, quad=terms.get("quad"))
-        ev1.record()
         status = int(res["status"].cpu()[0])
+        if status in (2, 5) and res.get("solver") == "stage_dp" and not terms.get("quad"):
+            # search budget exhausted (or the agent fell outside the class): the general kernel takes over
+            keep = batch.solver
+            batch.solver = "bnc"
+            try:
+                res = batch.solve(x0, w, cost_v=terms["cost_v"], w_x=terms["w_x"], w_y=terms["w_y"],
+                                  extra_constraints=extra, with_std_constraints=with_std)
+            finally:
+                batch.solver = keep
+            status = int(res["status"].cpu()[0])
+        ev1.record()
+        torch.cuda.synchronize()
         self._solve_time_solver = ev0.elapsed_time(ev1) * 1e-3
         self._status_name = cabi.SOLVE_STATUS.get(status, str(status))
         self._stats = dict(zip(cabi.STAT_NAMES, res["stats"].cpu().numpy()[0].tolist()))

@@ -18,15 +18,18 @@
 //   * kernel 1 (stage_dp_table_kernel, one CTA per agent): backward sweep over the stages of a LOWER BOUND
 //     LB_k[cell] of the cost-to-go that is valid for every state in the cell (stage penalties are bounded from
 //     below over the cell, a translated cell overlaps two cells of the next stage and takes their min).  The
-//     current stage lives in shared memory; every stage is streamed to HBM as FP32 rounded DOWN, so the stored
-//     table is still a valid bound.  States outside the grid window get the trivial bound (sum of negative
-//     costs), so the window only affects speed, never correctness.
-//   * kernel 2 (stage_dp_search_kernel, one warp per agent): exact depth-first search over the binary
-//     sequence in time order; states and costs are exact FP64, a node is pruned when
-//     cost so far + LB >= incumbent.  Up to 32 open nodes are expanded per iteration.  The first dive follows
-//     the table and lands on (or next to) the optimum; the rest of the search is the optimality proof.
-// Work: Nt * G cell updates (~25 FP64 operations each) + a few hundred scalar nodes per agent -- against
-// ~10^3..10^5 dense simplex pivots of the general branch-and-cut kernel (milp_bnc.cu) on the same problems.
+//     stage in flight lives in shared memory between guard cells (no bound checks in the hot loop); every stage is
+//     streamed to HBM as FP32 rounded DOWN, so the stored table is still a valid bound.  States outside the grid
+//     window get the trivial bound (sum of negative costs), so the window only affects speed, never correctness.
+//   * kernel 2 (stage_dp_search_kernel, one warp per agent): exact search over the binary sequence in time
+//     order; states and costs are exact FP64, a node is pruned when cost so far + LB >= incumbent.  The unit of
+//     work is the depth-5 subtree under an open node (32 lanes = 32 action sequences, one table read each).  A
+//     greedy dive gives the incumbent (it is optimal on > 99 % of the DEWH instances); the depth-first pass that
+//     follows is the optimality proof.
+// Optional convex stage terms (quadratic / L1 atoms on the state, outputs and slacks) make the problem an MIQP; they
+// run through the general loops of both kernels.
+// Work: Nt * G cell updates (~45 instructions each) + ~15 subtree expansions per agent -- against ~10^3..10^5
+// dense simplex pivots of the general branch-and-cut kernel (milp_bnc.cu) on the same problems.
 #include <string.h>
 #include "common.cuh"
 
