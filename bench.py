@@ -171,7 +171,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.02)
+            time.sleep(0.05)
 
     def summary(self):
         if not self.samples:
@@ -257,7 +257,7 @@ def main_ours(args):
     ring_evobj = [torch.cuda.Event() for _ in range(4)]
 
     def exchange(p_agg, s):
-        if world == 1:
+        if world == 1 or os.environ.get("HMPC_NO_EXCHANGE"):      # (debug switch: isolate the cost of the exchange)
             return p_agg
         main = torch.cuda.current_stream()
         buf = ring[s % 4]
@@ -329,6 +329,7 @@ def main_ours(args):
         for pidx in range(P):
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, pool=pool_id, capture_error_mode="thread_local"):
+                flush.fill_(float(pidx))               # L2 flush: first node of every step's graph
                 load_inputs(steps_in[pidx])
                 go = one_step(static)
             if pool_id is None:
@@ -337,35 +338,57 @@ def main_ours(args):
             g_outs.append(go)
         graph = graphs[0]
         barrier()
-        graph.replay()
+        for g in graphs:                # first launch of a graph uploads it to the device: not part of a step
+            g.replay()
         barrier()
     note("graph captured")
     sampler = ClockSampler(local_rank)
-    sampler.start()
+    if rank == 0:            # one NVML poller per box: NVML queries contend with kernel launches in the driver
+        sampler.start()
     launches0 = cabi.launch_count
     # Timing: ONE pair of events around the K steps (everything on the device between them counts: the steps, the
-    # input copies, the pipelined exchanges, launch gaps) minus the L2 flushes, which are bracketed by their own events.
-    # Per-step events give the latency percentiles.
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
+    # input copies, the pipelined exchanges, launch gaps) minus K L2 flushes.  With graphs the flush is the first node
+    # of the step's graph (one host call per step: with 8 ranks on one box the host's launch rate is what limits the
+    # step rate otherwise) and its duration is calibrated right before the timed region; without graphs every flush
+    # is bracketed by its own events.  Per-step events on every 4th step give the latency percentiles.
+    cal = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    flush.fill_(0.5)
+    cal[0].record()
+    for i in range(20):
+        flush.fill_(float(i))
+    cal[1].record()
+    barrier()
+    flush_one_ms = cal[0].elapsed_time(cal[1]) / 20.0
+    evs = {s: [torch.cuda.Event(enable_timing=True) for _ in range(4)] for s in range(K) if graph is None or s % 4 == 0}
     ev_start, ev_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.perf_counter()
+    host_us = [0.0, 0.0]
     ev_start.record()
     for s in range(K):
-        evs[s][2].record()
-        flush.fill_(float(s))
-        evs[s][3].record()
-        evs[s][0].record()
+        e = evs.get(s)
         if graph is not None:
+            if e:
+                e[0].record()
             out = g_outs[(W + s) % P]
+            th0 = time.perf_counter()
             graphs[(W + s) % P].replay()
+            host_us[0] += time.perf_counter() - th0
         else:
+            e[2].record()
+            flush.fill_(float(s))
+            e[3].record()
+            e[0].record()
             load_inputs(steps_in[(W + s) % P])
             out = one_step(static)
+        th0 = time.perf_counter()
         exchange(out[5], s)
-        evs[s][1].record()
+        host_us[1] += time.perf_counter() - th0
+        if e:
+            e[1].record()
         if s % 8 == 0 or s == K - 1:                  # solver statistics of a sample of the steps
             statuses.append(out[2].clone())
             solve_stats.append(out[3].clone())
+    t_host_loop = time.perf_counter() - t_wall0
     join_exchange()
     ev_end.record()
     barrier()
@@ -374,12 +397,29 @@ def main_ours(args):
     note("timed region done")
     launches_per_step = 1 + 1 + (2 if use_dp else 1) + 1 + 2      # K1, K2, K3/K4, K5, K6 (two-pass reduction)
     launches = launches_per_step * K if graph is not None else cabi.launch_count - launches0
-    step_ms = [e[0].elapsed_time(e[1]) for e in evs]
-    flush_ms = float(sum(e[2].elapsed_time(e[3]) for e in evs))
+    if graph is not None:
+        step_ms = [e[0].elapsed_time(e[1]) - flush_one_ms for e in evs.values()]
+        flush_ms = flush_one_ms * K
+    else:
+        step_ms = [e[0].elapsed_time(e[1]) for e in evs.values()]
+        flush_ms = float(sum(e[2].elapsed_time(e[3]) for e in evs.values()))
     total_ms = float(ev_start.elapsed_time(ev_end)) - flush_ms
     last_obj = out[1].clone()
+    # every rank's own SM clock while its GPU is still warm (one NVML query per rank, outside the timed region)
+    my_mhz = 0.0
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        my_mhz = float(pynvml.nvmlDeviceGetClockInfo(pynvml.nvmlDeviceGetHandleByIndex(local_rank), pynvml.NVML_CLOCK_SM))
+    except Exception:
+        pass
+    rank_mhz = [my_mhz]
     rank_ms = [total_ms / K]
     if world > 1:
+        tm = torch.tensor([my_mhz], dtype=torch.float64, device=dev)
+        allm = [torch.empty_like(tm) for _ in range(world)]
+        dist.all_gather(allm, tm)
+        rank_mhz = [float(x.item()) for x in allm]
         t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
         allt = [torch.empty_like(t) for _ in range(world)]
         dist.all_gather(allt, t)
@@ -453,11 +493,15 @@ def main_ours(args):
         "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "config": dict(workload_config(args, world), solver="stage_dp" if use_dp else "bnc",
                        launch="one CUDA graph per step" if graph is not None else "kernel by kernel",
-                       timing="one event pair around the K steps minus the L2-flush kernels (own events); the NCCL "
-                              "exchange of step s runs on a side stream, pipelined with step s+1, joined before the end",
+                       timing="one event pair around the K steps minus K L2 flushes (%.4f ms each, calibrated before the "
+                              "timed region; the flush is the first node of each step's graph); the NCCL exchange of "
+                              "step s runs on a side stream, pipelined with step s+1, joined before the end"
+                              % flush_one_ms,
                        solver_stats="sampled every 8th step"),
         "latency_p50_ms": float(np.median(step_ms)), "latency_max_ms": float(np.max(step_ms)),
-        "ms_per_step_by_rank": rank_ms,
+        "ms_per_step_by_rank": rank_ms, "sm_mhz_by_rank_after_timed_region": rank_mhz,
+        "host_ms_per_step": {"loop": 1e3 * t_host_loop / K, "graph_launch": 1e3 * host_us[0] / K,
+                             "exchange_enqueue": 1e3 * host_us[1] / K},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": 1e3 * e2e_total / K, "api": "hmpc_mpc_step_host_f64 via cabi.StepPlan.step"},
         "gpu_launches": int(launches),

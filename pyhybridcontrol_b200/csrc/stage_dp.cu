@@ -302,6 +302,13 @@ __device__ inline void dp_load(const DpArgs& A, int b, DpCtx& c) {
         }
         double S0 = fmax(rlo, blo - margin), S1 = fmin(rhi, bhi + margin);
         if (!(S1 > S0)) { S0 = rlo; S1 = rhi; }
+        // keep every translation within the guard cells of the stage buffers (G / 4 on each side), so that the whole
+        // sweep runs through the hot loop: a window narrower than four shifts is widened around its centre (the
+        // extra cells are unreachable or dead; they cost nothing but their share of the sweep)
+        {
+            const double minw = 4.0 * margin * (1.0 + 16.0 / (double)c.G);
+            if (S1 - S0 < minw) { const double mid = 0.5 * (S0 + S1); S0 = mid - 0.5 * minw; S1 = mid + 0.5 * minw; }
+        }
         double w = (S1 - S0) / (double)c.G;
         if (!(w > 0.0) || !isfinite(w)) w = 1.0;
         c.misc[MISC_S0] = S0; c.misc[MISC_W] = w; c.misc[MISC_INVW] = 1.0 / w; c.misc[MISC_SIMPLE] = 1.0;
