@@ -1,0 +1,60 @@
+"""CPU checks of the mathematics behind the stage-DP kernels, on their numpy twin (tools/stage_dp_proto.py: same
+grid, widened cells, FP32 round-down):
+
+* validity  -- the value table never exceeds the true cost-to-go (exhaustive enumeration, short horizons);
+* exactness -- the bound-pruned depth-first search returns the HiGHS optimum and decisions (N_p = 24 and 48).
+The CUDA kernels themselves are checked on the GPU (tests/test_gpu_stage_dp.py, tests/test_gpu_parity.py)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+from stage_dp_proto import StageDp, from_dewh_problem  # noqa: E402
+
+from oracle import mld as omld, condense as oc, assemble as oa, solve as osv  # noqa: E402
+from pyhybridcontrol_b200.examples.residential_mg_with_pv_and_dewhs import synthetic as syn  # noqa: E402
+
+
+def _problem(wl, b):
+    Nt = wl["Nt"]
+    mats = {k: v[b] for k, v in wl["mats"].items()}
+    full, d, vt = omld.complete(mats, nu_l=1)
+    prob = oa.build_problem(oc.condense(full, d, Nt), d, vt, Nt, wl["x0"][b], wl["omega"][b],
+                            atoms=dict(q_u=wl["q_u"][b], q_mu=wl["q_mu"][b]))
+    return mats, prob
+
+
+@pytest.mark.parametrize("cells", [64, 512])
+@pytest.mark.parametrize("x0_shift", [0.0, -12.0])     # nominal start / cold start (slack unavoidable)
+def test_value_table_is_a_lower_bound(cells, x0_shift):
+    N_p = 9
+    wl = syn.dewh_batch(3, N_p, seed=17)
+    wl["x0"] = wl["x0"] + x0_shift
+    rng = np.random.default_rng(cells)
+    for b in range(3):
+        mats, prob = _problem(wl, b)
+        dp = StageDp(*from_dewh_problem(mats, prob, wl["Nt"]), cells=cells)
+        # states actually reachable at stage k (all 2^k prefixes) and random states inside the window
+        for k in range(1, wl["Nt"]):
+            reach = {0.0}
+            for j in range(k):
+                reach |= {s + dp.shift[j] for s in reach}
+            states = list(reach)[:64] + list(dp.S0 + rng.uniform(0, 1, size=8) * dp.G * dp.w)
+            for s in states:
+                lb, true = dp.bound(k, s), dp.cost_to_go_exact(k, s)
+                assert lb <= true + 1e-9 * max(1.0, abs(true)), (b, k, s, lb, true)
+
+
+@pytest.mark.parametrize("N_p,cells", [(24, 256), (24, 4096), (48, 2048)])
+def test_bound_pruned_search_is_exact(N_p, cells):
+    wl = syn.dewh_batch(4, N_p, seed=23)
+    for b in range(4):
+        mats, prob = _problem(wl, b)
+        dp = StageDp(*from_dewh_problem(mats, prob, wl["Nt"]), cells=cells)
+        obj, u, nodes = dp.solve()
+        st, oref, vref = osv.solve_milp(prob, polish=True)
+        assert st == osv.OPTIMAL and abs(obj + prob.c0 - oref) <= 1e-6 * max(1.0, abs(oref)), (b, obj, oref, nodes)
+        assert np.array_equal(u, np.round(vref[prob.is_bin]))
+        assert nodes < 200000
