@@ -138,10 +138,11 @@ def main_reference(args):
 
 # ------------------------------------------------------------------------------------------------ clocks sampler
 class ClockSampler(threading.Thread):
-    def __init__(self, index):
+    def __init__(self, index, enabled=True):
         super(ClockSampler, self).__init__(daemon=True)
         self.index, self.samples, self.reasons, self.stop_flag = index, [], set(), False
         self.max_mhz = None
+        self.enabled, self.started = enabled, False
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -150,6 +151,11 @@ class ClockSampler(threading.Thread):
             self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
         except Exception:
             self.nv = None
+
+    def start_once(self):
+        if self.enabled and not self.started:
+            self.started = True
+            self.start()
 
     def run(self):
         if self.nv is None:
@@ -171,7 +177,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.05)
+            time.sleep(0.01)
 
     def summary(self):
         if not self.samples:
@@ -285,6 +291,7 @@ def main_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank, enabled=(rank == 0))   # one NVML poller per box: queries contend with launches
     # ---- the step as ONE CUDA graph over static input buffers (the per-step inputs are copied in, device to
     #      device, inside the timed region); --no-graph launches the kernels one by one instead
     static = {k: torch.empty_like(steps_in[0][k]) for k in ("x0", "omega", "cost")}
@@ -338,13 +345,12 @@ def main_ours(args):
             g_outs.append(go)
         graph = graphs[0]
         barrier()
+        sampler.start_once()            # clocks are sampled from here on: the same steps run, untimed, right now
         for g in graphs:                # first launch of a graph uploads it to the device: not part of a step
             g.replay()
         barrier()
     note("graph captured")
-    sampler = ClockSampler(local_rank)
-    if rank == 0:            # one NVML poller per box: NVML queries contend with kernel launches in the driver
-        sampler.start()
+    sampler.start_once()
     launches0 = cabi.launch_count
     # Timing: ONE pair of events around the K steps (everything on the device between them counts: the steps, the
     # input copies, the pipelined exchanges, launch gaps) minus K L2 flushes.  With graphs the flush is the first node
