@@ -448,7 +448,7 @@ def main_ours(args):
     value = world * B * K / (total_ms * 1e-3)
 
     # ---- e2e: host buffers through hmpc_mpc_step_host_f64 (numpy in, numpy out, copies inside the timed region)
-    plan = cabi.StepPlan(fleet.batch.dims, cabi.default_opts(reserved=0 if use_dp else 1))
+    plan = cabi.StepPlan(fleet.batch.dims, cabi.default_opts(force_general=0 if use_dp else 1))
     hmats = dict(wl0["mats"])
     hmats["C"] = np.ones((1, 1, 1))
     e2e_times = []

@@ -121,7 +121,7 @@ typedef struct {
     int32_t cut_rounds_root; /* default 30                                                              */
     int32_t cut_rounds_node; /* default 2                                                               */
     int32_t cuts_per_round;  /* default 8                                                               */
-    int32_t reserved;        /* host front door only: 1 = always use this kernel, never the stage-DP path   */
+    int32_t force_general;   /* host front door only: 1 = always use this kernel, never the stage-DP path   */
 } hmpc_milp_opts;
 
 void hmpc_milp_default_opts(hmpc_milp_opts* opts);

@@ -47,7 +47,7 @@ class MilpOpts(C.Structure):
     _fields_ = [("mip_rel_gap", C.c_double), ("int_tol", C.c_double), ("feas_tol", C.c_double),
                 ("big_bound", C.c_double), ("max_nodes", C.c_int32), ("max_pivots", C.c_int32),
                 ("max_cuts", C.c_int32), ("max_rows", C.c_int32), ("cut_rounds_root", C.c_int32),
-                ("cut_rounds_node", C.c_int32), ("cuts_per_round", C.c_int32), ("reserved", C.c_int32)]
+                ("cut_rounds_node", C.c_int32), ("cuts_per_round", C.c_int32), ("force_general", C.c_int32)]
 
 
 class StageDpOpts(C.Structure):

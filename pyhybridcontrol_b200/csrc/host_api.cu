@@ -175,7 +175,7 @@ extern "C" int hmpc_mpc_step_host_f64(hmpc_step_plan* p, int32_t recondense, con
     HMPC_CUDA_TRY(cudaMemcpyAsync(p->in_dev, pin, sizeof(double) * copy_elems, cudaMemcpyHostToDevice, s));
     HMPC_CUDA_TRY(cudaEventRecord(p->ev[1], s));
     // ---- kernels
-    const bool want_dp = p->dp_dims_ok && p->opts.reserved == 0;
+    const bool want_dp = p->dp_dims_ok && p->opts.force_general == 0;
     int rc;
     auto condense = [&](bool with_H_v) -> int {
         double* outs[HMPC_NUM_EVO] = {nullptr};

@@ -778,7 +778,7 @@ extern "C" void hmpc_milp_default_opts(hmpc_milp_opts* o) {
     if (!o) return;
     o->mip_rel_gap = 0.0; o->int_tol = 1e-6; o->feas_tol = 1e-9; o->big_bound = 1e7;
     o->max_nodes = 200000; o->max_pivots = 2000000; o->max_cuts = 512; o->max_rows = 0;
-    o->cut_rounds_root = 30; o->cut_rounds_node = 2; o->cuts_per_round = 8; o->reserved = 0;
+    o->cut_rounds_root = 30; o->cut_rounds_node = 2; o->cuts_per_round = 8; o->force_general = 0;
 }
 
 extern "C" int hmpc_milp_workspace_bytes(int32_t B, int32_t n, int32_t m, const hmpc_milp_opts* opts, size_t* bytes) {

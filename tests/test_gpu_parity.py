@@ -300,7 +300,7 @@ def test_host_front_door_matches_device_path(solver, cuda_device):
     from pyhybridcontrol_b200.examples.residential_mg_with_pv_and_dewhs import synthetic as syn
     wl = syn.dewh_batch(10, 24, seed=6)
     bm, res, cost = _dewh_solve(wl, cuda_device, solver)
-    plan = cabi.StepPlan(bm.dims, cabi.default_opts(reserved=int(solver == "bnc")))
+    plan = cabi.StepPlan(bm.dims, cabi.default_opts(force_general=int(solver == "bnc")))
     hm = dict(wl["mats"])
     hm["C"] = np.ones((1, 1, 1))
     v, obj, st, stats, tm = plan.step(hm, wl["x0"], wl["omega"], cost, bm.lb_v, bm.ub_v, bm.is_bin_v, recondense=True)
