@@ -659,9 +659,11 @@ __device__ __forceinline__ bool expand_simple(const DpCtx& c, const float* __res
 // One warp per agent.  The unit of work is the depth-D subtree below one open node, D = the largest depth with
 // nact^D <= 32: lane l evaluates the action sequence whose base-nact digits are l -- exact stage costs, exact
 // states -- and closes it with the table bound of the state it reaches (one table read per lane per iteration).
-//   phase A: a greedy dive that keeps only the best lane of every subtree -> first incumbent after Nt / D steps;
-//   phase B: exact depth-first search from the root; a sequence survives when cost + bound < incumbent, the best
-//            survivor goes on top of the stack; whole runs of dominated nodes are discarded in one step.
+//   search : depth-first from the root; a sequence survives when cost + bound < incumbent, the best survivor goes
+//            on top of the stack; whole runs of dominated nodes are discarded in one step.  The first descent has no
+//            incumbent yet, so it is a greedy dive that also leaves every sibling (with its exact bound) on the stack;
+//   dive   : on long horizons those siblings would not fit, so a separate greedy dive (best lane of every subtree,
+//            nothing pushed) produces the incumbent first and the search then starts from the root with it.
 __global__ void __launch_bounds__(kSearchWarps * 32) stage_dp_search_kernel(const DpArgs A) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -726,8 +728,12 @@ __global__ void __launch_bounds__(kSearchWarps * 32) stage_dp_search_kernel(cons
     };
     auto argmin_lane = [&](bool flag, double val) -> int { return warp_argmin(flag, val, lane); };
 
-    // ---- phase A: greedy dive
-    {
+    // ---- phase A: greedy dive.  Only when the stack could not hold every sibling of a first dive that runs inside
+    // phase B itself (long horizons): otherwise phase B starts without an incumbent, its first descent IS the dive,
+    // the siblings it pushes carry their exact bounds and are discarded 32 at a time once the incumbent exists --
+    // cheaper than walking the optimal path a second time.
+    const bool two_phase = ((Nt + D - 1) / D) * ((1 << (nb * D)) - 1) + 64 > kStackCap;
+    auto greedy_dive = [&]() {
         int k0 = 0; double s0 = 0.0, cost0 = 0.0; unsigned long long r0 = 0, r1 = 0;
         while (k0 < Nt) {
             double s = s0, cost = cost0, bd; unsigned long long q0 = r0, q1 = r1; bool leaf;
@@ -738,9 +744,10 @@ __global__ void __launch_bounds__(kSearchWarps * 32) stage_dp_search_kernel(cons
             s0 = __shfl_sync(0xffffffffu, s, win); cost0 = __shfl_sync(0xffffffffu, cost, win);
             r0 = __shfl_sync(0xffffffffu, q0, win); r1 = __shfl_sync(0xffffffffu, q1, win);
             k0 += (Nt - k0) < D ? (Nt - k0) : D;
-            if (k0 >= Nt) { best = cost0; bp0 = r0; bp1 = r1; ++improvements; }
+            if (k0 >= Nt && cost0 < best) { best = cost0; bp0 = r0; bp1 = r1; ++improvements; }
         }
-    }
+    };
+    if (two_phase) greedy_dive();
     // ---- phase B: exact search
     int sp = 1;
     if (lane == 0) { Node r; r.s = 0.0; r.cost = 0.0; r.bound = -INFINITY; r.p0 = r.p1 = 0; r.k = 0; r.pad = 0; stack[0] = r; }
@@ -786,6 +793,7 @@ __global__ void __launch_bounds__(kSearchWarps * 32) stage_dp_search_kernel(cons
         max_sp = sp > max_sp ? sp : max_sp;
         __syncwarp();
     }
+    if (limit && !isfinite(best)) greedy_dive();     // budget gone before the first descent finished: best effort
     // ---- write the solution: binaries from the path, mu in closed form along the exact trajectory
     const bool have = isfinite(best);
     if (lane == 0 && have) {
