@@ -451,7 +451,7 @@ def main_ours(args):
     plan = cabi.StepPlan(fleet.batch.dims, cabi.default_opts(force_general=0 if use_dp else 1))
     hmats = dict(wl0["mats"])
     hmats["C"] = np.ones((1, 1, 1))
-    e2e_times = []
+    e2e_times, e2e_dev = [], []
     for s in range(W + K):
         inp = steps_in[s % P]
         flush.fill_(float(s))
@@ -464,6 +464,7 @@ def main_ours(args):
         dt = time.perf_counter() - t0
         if s >= W:
             e2e_times.append(dt)
+            e2e_dev.append(tm)
     h2d, d2h = plan.bytes_per_step(True)
     e2e_total = float(sum(e2e_times))
     if world > 1:
@@ -509,7 +510,9 @@ def main_ours(args):
         "host_ms_per_step": {"loop": 1e3 * t_host_loop / K, "graph_launch": 1e3 * host_us[0] / K,
                              "exchange_enqueue": 1e3 * host_us[1] / K},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": 1e3 * e2e_total / K, "api": "hmpc_mpc_step_host_f64 via cabi.StepPlan.step"},
+                "ms_per_step": 1e3 * e2e_total / K, "api": "hmpc_mpc_step_host_f64 via cabi.StepPlan.step",
+                "device_ms_per_step": dict(zip(("h2d", "kernels", "d2h", "total"),
+                                               [float(x) for x in np.mean(np.array(e2e_dev), axis=0)]))},
         "gpu_launches": int(launches),
         "kernel_ms_per_step": dict({k: v / K for k, v in kernel_ms.items()},
                                    note="untimed eager pass with events between the launches (%d steps)" % Kb),

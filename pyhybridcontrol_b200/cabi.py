@@ -446,38 +446,58 @@ class StepPlan(object):
         self.status = np.empty((d.B,), dtype=np.int32)
         self.stats = np.empty((d.B, 8), dtype=np.int32)
         self.timing = (C.c_float * 4)()
+        self._out_ptrs = (self.v.ctypes.data, self.obj.ctypes.data, self.status.ctypes.data, self.stats.ctypes.data)
+        self._mats_cache = {}
 
     def bytes_per_step(self, recondense):
         a, b = C.c_int64(), C.c_int64()
         _check(_lib.hmpc_mpc_step_host_bytes(self._h, int(recondense), C.byref(a), C.byref(b)), "bytes")
         return a.value, b.value
 
-    def step(self, mats, x0, w, cost_v, lb_v, ub_v, is_bin_v, recondense=True):
-        global launch_count
+    def _pack_host_mats(self, mats):
+        """ctypes views of the host MLD blocks; cached per dict object (the arrays are read at call time, so in-place
+        updates of their contents are picked up)."""
+        key = id(mats)
+        hit = self._mats_cache.get(key)
+        if hit is not None and hit[0] is mats:
+            return hit[1], hit[2]
         d = self.d
         arr, strides, keep = _MatArr(), _StrideArr(), []
+        copied = False
         for i, name in enumerate(MAT_NAMES):
             a = None if mats is None else mats.get(name)
             r, c = _mat_shape(d, name)
             if a is None or r * c == 0:
                 arr[i], strides[i] = None, 0
                 continue
+            copied |= not (isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags.c_contiguous)
             a = np.ascontiguousarray(a, dtype=np.float64).reshape(-1, r, c)
             keep.append(a)
             arr[i] = a.ctypes.data
             strides[i] = 0 if a.shape[0] == 1 and d.B != 1 else r * c
+        self._mats_cache = {} if copied else {key: (mats, arr, strides, keep)}   # converted copies would go stale
+        self._mats_keep = keep
+        return arr, strides
+
+    @staticmethod
+    def _f64(a):
+        return a if (isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags.c_contiguous) else \
+            np.ascontiguousarray(a, dtype=np.float64)
+
+    def step(self, mats, x0, w, cost_v, lb_v, ub_v, is_bin_v, recondense=True):
+        global launch_count
+        d = self.d
+        arr, strides = self._pack_host_mats(mats)
         nvt = d.nv * d.Nt
-        x0 = np.ascontiguousarray(x0, dtype=np.float64)
-        w = np.ascontiguousarray(w, dtype=np.float64)
-        cost_v = np.ascontiguousarray(cost_v, dtype=np.float64).reshape(-1, nvt)
-        lb_v = np.ascontiguousarray(lb_v, dtype=np.float64)
-        ub_v = np.ascontiguousarray(ub_v, dtype=np.float64)
-        is_bin_v = np.ascontiguousarray(is_bin_v, dtype=np.uint8)
+        x0, w, lb_v, ub_v = self._f64(x0), self._f64(w), self._f64(lb_v), self._f64(ub_v)
+        cost_v = self._f64(cost_v).reshape(-1, nvt)
+        if not (isinstance(is_bin_v, np.ndarray) and is_bin_v.dtype == np.uint8 and is_bin_v.flags.c_contiguous):
+            is_bin_v = np.ascontiguousarray(is_bin_v, dtype=np.uint8)
         cs = nvt if cost_v.shape[0] == d.B and d.B > 1 else (0 if d.B > 1 else nvt)
         _check(_lib.hmpc_mpc_step_host_f64(self._h, int(recondense), arr, strides, x0.ctypes.data, w.ctypes.data,
                                            cost_v.ctypes.data, cs, lb_v.ctypes.data, ub_v.ctypes.data,
-                                           is_bin_v.ctypes.data, self.v.ctypes.data, self.obj.ctypes.data,
-                                           self.status.ctypes.data, self.stats.ctypes.data, self.timing),
+                                           is_bin_v.ctypes.data, self._out_ptrs[0], self._out_ptrs[1],
+                                           self._out_ptrs[2], self._out_ptrs[3], self.timing),
                "hmpc_mpc_step_host_f64")
         self.last_solver = ("bnc", "stage_dp")[max(0, _lib.hmpc_step_plan_last_solver(self._h))]
         launch_count += (1 if recondense else 0) + 1 + (2 if self.last_solver == "stage_dp" else 1)
