@@ -356,12 +356,23 @@ __device__ __forceinline__ double terms_lower_bound(const DpCtx& c, int k, int a
     return st;
 }
 
+// TMA bulk copy (cp.async.bulk, shared -> global) of one finished stage of the table: one elected thread issues it,
+// the copy engine streams the 4 G bytes to HBM while the CTA already sweeps the next stage.
+__device__ __forceinline__ void bulk_store_stage(float* gdst, const float* ssrc, unsigned bytes) {
+    const unsigned saddr = (unsigned)__cvta_generic_to_shared(ssrc);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the async proxy
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(saddr), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_source_free() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // Hot loop of the backward sweep over the cells [lo, hi) whose translated neighbours are all inside the table:
 // no bound checks, every per-stage constant in registers.  q max(v, 0) is evaluated as (q/2) (v + |v|) -- exact,
 // and |v| is a free operand modifier of the FP64 add.
 template <int NC, int NACT, bool SAME>
 __device__ __forceinline__ void sweep_interior(const float* __restrict__ cur, float* __restrict__ nxt,
-                                               float* __restrict__ tabk, int lo, int hi, int nthr,
+                                               int lo, int hi, int nthr,
                                                const double* __restrict__ s_slope, const double* __restrict__ s_q,
                                                const double* __restrict__ s_base, const double* __restrict__ s_ca,
                                                const int* __restrict__ s_i0, const int* __restrict__ s_span) {
@@ -405,9 +416,7 @@ __device__ __forceinline__ void sweep_interior(const float* __restrict__ cur, fl
             st += (double)nx;
             best = (al == 0 || st < best) ? st : best;
         }
-        const float r32 = __double2float_rd(best + pen);   // rounded DOWN: the stored table stays a lower bound
-        nxt[cell] = r32;
-        tabk[cell] = r32;
+        nxt[cell] = __double2float_rd(best + pen);   // rounded DOWN: the stored table stays a lower bound
     }
 }
 
@@ -505,8 +514,8 @@ __global__ void __launch_bounds__(512) stage_dp_table_kernel(const DpArgs A) {
         const bool fast = (flags & 1) && NC > 0 && s_maxshift <= pad;
         const int lo = 0, hi = G;
         if (fast) {
-            if (flags & 2) sweep_interior<(NC > 0 ? NC : 1), (NACT > 0 ? NACT : 1), true>(cur, nxt, tabk, lo, hi, nthr, s_slope, s_q, s_base, s_ca, s_i0, s_span);
-            else sweep_interior<(NC > 0 ? NC : 1), (NACT > 0 ? NACT : 1), false>(cur, nxt, tabk, lo, hi, nthr, s_slope, s_q, s_base, s_ca, s_i0, s_span);
+            if (flags & 2) sweep_interior<(NC > 0 ? NC : 1), (NACT > 0 ? NACT : 1), true>(cur, nxt, lo, hi, nthr, s_slope, s_q, s_base, s_ca, s_i0, s_span);
+            else sweep_interior<(NC > 0 ? NC : 1), (NACT > 0 ? NACT : 1), false>(cur, nxt, lo, hi, nthr, s_slope, s_q, s_base, s_ca, s_i0, s_span);
         }
         {
             // ---- general loop: restricted action sets, hard rows, translations that land on a cell boundary or
@@ -545,9 +554,7 @@ __global__ void __launch_bounds__(512) stage_dp_table_kernel(const DpArgs A) {
                     st += (double)nx;
                     best = st < best ? st : best;
                 }
-                const float r32 = __double2float_rd(best);
-                nxt[cell] = r32;
-                tabk[cell] = r32;
+                nxt[cell] = __double2float_rd(best);
             }
         }
         // guard cells of the stage just written: the bound of states outside the window at stage k
@@ -555,9 +562,14 @@ __global__ void __launch_bounds__(512) stage_dp_table_kernel(const DpArgs A) {
             const float out_k = __double2float_rd(c.tailmin[k]);
             for (int i = threadIdx.x; i < pad; i += nthr) { nxt[-1 - i] = out_k; nxt[G + i] = out_k; }
         }
+        // the buffer the NEXT stage overwrites is the source of the bulk copy issued one stage ago: it must have
+        // been read completely before anybody passes the barrier
+        if (threadIdx.x == 0) bulk_wait_source_free();
         __syncthreads();
+        if (threadIdx.x == 0) bulk_store_stage(tabk, nxt, (unsigned)G * sizeof(float));   // stage k -> HBM, asynchronously
         float* t = cur; cur = nxt; nxt = t;
     }
+    if (threadIdx.x == 0) bulk_wait_all();
 }
 
 // ------------------------------------------------------------------------------------------------ kernel 2
@@ -870,7 +882,7 @@ extern "C" int hmpc_stage_dp_solve_f64(const hmpc_dims* dims, const double* cons
     a.d = *dims;
     for (int i = 0; i < HMPC_NUM_MATS; ++i) { a.mats[i] = mats[i]; a.stride[i] = mat_stride_b[i]; }
     if (opts) a.o = *opts; else hmpc_stage_dp_default_opts(&a.o);
-    if (a.o.cells < 64) return HMPC_ERR_ARG;
+    if (a.o.cells < 64 || a.o.cells % 64 != 0) return HMPC_ERR_ARG;   // bulk copies move whole 16-byte units
     a.G = a.o.cells; a.nb = dims->nu + dims->ndelta; a.nact = 1 << a.nb; a.nv = a.nb + dims->nmu;
     memset(&a.t, 0, sizeof(a.t));
     if (terms) {
