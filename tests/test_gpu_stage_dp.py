@@ -402,3 +402,34 @@ def test_stage_dp_edge_cases(cuda_device):
     bm.build()
     res = bm.solve(np.zeros((2, 1)), None, cost_v=np.tile([-1.0, 2.0, -3.0, 0.5], (2, 1)))
     assert res["solver"] == "bnc" and np.allclose(res["obj"].cpu().numpy(), -4.0)
+
+
+def test_host_front_door_falls_back_to_general_kernel(cuda_device):
+    """hmpc_mpc_step_host_f64 tries the stage-DP kernels first (the dimensions fit); when an agent reports
+    HMPC_SOLVE_UNSUPPORTED (here: a Psi that couples two rows) the whole batch is re-solved by the branch-and-cut
+    kernel inside the same call, with H_v condensed on demand."""
+    from pyhybridcontrol_b200 import cabi
+    from pyhybridcontrol_b200.batch import BatchMpc
+    from pyhybridcontrol_b200.examples.residential_mg_with_pv_and_dewhs import synthetic as syn
+    B, N_p = 3, 10
+    wl = syn.dewh_batch(B, N_p, seed=8)
+    Nt = wl["Nt"]
+    mats = {k: v.copy() for k, v in wl["mats"].items()}
+    mats["Psi"][1, 0, 1] = -0.25
+    mats["C"] = np.ones((1, 1, 1))
+    cost = np.zeros((B, Nt, 3))
+    cost[:, :, 0] = wl["q_u"]
+    cost[:, :, 1:] = wl["q_mu"][:, None, :]
+    ref = BatchMpc({k: v for k, v in mats.items() if k != "C"}, N_p, nu_l=1, device=cuda_device, solver="bnc")
+    ref.build()
+    r = ref.solve(wl["x0"], wl["omega"], cost_v=cost.reshape(B, -1))
+    plan = cabi.StepPlan(ref.dims)
+    v, obj, st, stats, tm = plan.step(mats, wl["x0"], wl["omega"], cost.reshape(B, -1), ref.lb_v, ref.ub_v, ref.is_bin_v,
+                                      recondense=True)
+    assert plan.last_solver == "bnc" and (st == 0).all()
+    np.testing.assert_allclose(obj, r["obj"].cpu().numpy(), rtol=1e-12)
+    # and again without re-condensing (H_v is there now)
+    v2, obj2, st2, _, _ = plan.step(None, wl["x0"], wl["omega"], cost.reshape(B, -1), ref.lb_v, ref.ub_v, ref.is_bin_v,
+                                    recondense=False)
+    assert np.array_equal(obj2, obj)
+    plan.close()
