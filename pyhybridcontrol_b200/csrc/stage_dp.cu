@@ -389,7 +389,7 @@ __device__ __forceinline__ void sweep_interior(const float* __restrict__ cur, fl
     int cell = lo + threadIdx.x;
     double cd = (double)cell;
     const double dstep = (double)nthr;
-#pragma unroll 2
+#pragma unroll 4
     for (; cell < hi; cell += nthr, cd += dstep) {
         double pen = 0.0;
         if (SAME) {
