@@ -482,6 +482,7 @@ def main_ours(args):
         return
 
     fp64_peak = cabi.fp64_peak_tflops()
+    tab_bytes = 8 if dp_opts.table_fp64 else 4
     solve_ms = kernel_ms["solve"] / K
     cond_ms = kernel_ms["condense"] / K
     peaks = {}
@@ -519,22 +520,23 @@ def main_ours(args):
         "roofline": {"kernel": "stage_dp_table_kernel + stage_dp_search_kernel" if use_dp else "milp_bnc_kernel",
                      "bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak,
                      "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak if fp64_peak else None,
-                     "traffic": (B * (Nt - 1) * dp_opts.cells * 4) if use_dp else None,
+                     "traffic": (B * (Nt - 1) * dp_opts.cells * tab_bytes) if use_dp else None,
                      "peak_source": "hmpc_fp64_peak_probe (DFMA micro-benchmark, measured in this run)",
                      "share_of_step": solve_ms / (total_ms / K),
                      "note": ("value-table sweep + exact search: algorithmic FP64 FMAs counted by the kernels "
-                              "(cells x actions x (4 + 3 rows)); `traffic` = FP32 table bytes streamed to HBM per "
+                              "(cells x actions x (4 + 3 rows)); `traffic` = value-table bytes streamed to HBM per "
                               "launch (hbm_write_gbs below); SURVEY 8(d) names the FP64 pipe / latency, not HBM, "
                               "as the bound of the solve") if use_dp else
                              ("latency-bound tree search: algorithmic FMAs (pivots, row transforms) counted by the "
                               "kernel itself; SURVEY 8(d) names FP64 pipe / latency, not HBM, as the bound"),
-                     "hbm_write_gbs": (B * (Nt - 1) * dp_opts.cells * 4 / (solve_ms * 1e-3) / 1e9) if use_dp else None},
+                     "hbm_write_gbs": (B * (Nt - 1) * dp_opts.cells * tab_bytes / (solve_ms * 1e-3) / 1e9) if use_dp else None},
         "roofline_condense": {"kernel": "condense_kernel", "bound": "hbm", "achieved": cond_bytes / (cond_ms * 1e-3) / 1e9,
                               "peak": hbm_peak, "unit": "GB/s",
                               "frac": cond_bytes / (cond_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
                               "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                               "bytes_per_launch": cond_bytes},
-        "solver": ({"kernel": "stage_dp", "cells": int(dp_opts.cells), "not_optimal": not_opt,
+        "solver": ({"kernel": "stage_dp", "cells": int(dp_opts.cells), "table": "fp64" if dp_opts.table_fp64 else "fp32",
+                    "not_optimal": not_opt,
                     "nodes_mean": float(np.concatenate([x[:, 0] for x in solve_stats]).mean()),
                     "nodes_max": int(np.concatenate([x[:, 0] for x in solve_stats]).max())} if use_dp else
                    {"kernel": "bnc", "not_optimal": not_opt, "pivots_mean": float(piv.mean()),

@@ -154,6 +154,11 @@ typedef struct {
     double  feas_tol;      /* tolerance of hard (slack-free) rows, default 1e-9        */
     int32_t cells;         /* value-table cells per stage, default 8192                */
     int32_t max_nodes;     /* search nodes per agent, default 4,000,000                */
+    int32_t table_fp64;    /* 1 (default): FP64 value table -- sequences that TIE with the incumbent (piecewise-constant
+                              tariffs) are pruned at mip_rel_gap = 0;  0: FP32 table rounded down -- half the
+                              workspace and shared memory, ~5-10 % faster, but ties are explored unless
+                              mip_rel_gap >= 4e-6                                                               */
+    int32_t reserved;
 } hmpc_stage_dp_opts;
 /* Optional convex cost terms of the stage-DP solve -- the reference's Quadratic / L22 / L1 atoms on the state, the
  * outputs and the slacks (controllers/components/objective_atoms.py:320-363), which make the problem an MIQP:

@@ -51,7 +51,8 @@ class MilpOpts(C.Structure):
 
 
 class StageDpOpts(C.Structure):
-    _fields_ = [("mip_rel_gap", C.c_double), ("feas_tol", C.c_double), ("cells", C.c_int32), ("max_nodes", C.c_int32)]
+    _fields_ = [("mip_rel_gap", C.c_double), ("feas_tol", C.c_double), ("cells", C.c_int32), ("max_nodes", C.c_int32),
+                ("table_fp64", C.c_int32), ("reserved", C.c_int32)]
 
 
 class StageTerms(C.Structure):

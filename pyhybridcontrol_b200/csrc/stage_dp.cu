@@ -19,7 +19,8 @@
 //     LB_k[cell] of the cost-to-go that is valid for every state in the cell (stage penalties are bounded from
 //     below over the cell, a translated cell overlaps two cells of the next stage and takes their min).  The
 //     stage in flight lives in shared memory between guard cells (no bound checks in the hot loop); every stage is
-//     streamed to HBM as FP32 rounded DOWN, so the stored table is still a valid bound.  States outside the grid
+//     streamed to HBM by a TMA bulk copy -- as FP64 (default: sequences that tie with the incumbent are then pruned
+//     at gap 0) or as FP32 rounded DOWN (half the workspace; still a valid bound).  States outside the grid
 //     window get the trivial bound (sum of negative costs), so the window only affects speed, never correctness.
 //   * kernel 2 (stage_dp_search_kernel, one warp per agent): exact search over the binary sequence in time
 //     order; states and costs are exact FP64, a node is pruned when cost so far + LB >= incumbent.  The unit of
@@ -356,9 +357,18 @@ __device__ __forceinline__ double terms_lower_bound(const DpCtx& c, int k, int a
     return st;
 }
 
+// Table storage: FP32 rounded DOWN (default: half the HBM stream and shared memory) or FP64 (exact: sequences that
+// tie with the incumbent are then pruned instead of explored, see DESIGN.md section 4.2 "known limits").
+template <typename TT> __device__ __forceinline__ TT to_table(double v);
+template <> __device__ __forceinline__ float to_table<float>(double v) { return __double2float_rd(v); }
+template <> __device__ __forceinline__ double to_table<double>(double v) { return v; }
+template <typename TT> __device__ __forceinline__ TT table_min(TT a, TT b);
+template <> __device__ __forceinline__ float table_min<float>(float a, float b) { return fminf(a, b); }
+template <> __device__ __forceinline__ double table_min<double>(double a, double b) { return a < b ? a : b; }
+
 // TMA bulk copy (cp.async.bulk, shared -> global) of one finished stage of the table: one elected thread issues it,
 // the copy engine streams the 4 G bytes to HBM while the CTA already sweeps the next stage.
-__device__ __forceinline__ void bulk_store_stage(float* gdst, const float* ssrc, unsigned bytes) {
+__device__ __forceinline__ void bulk_store_stage(void* gdst, const void* ssrc, unsigned bytes) {
     const unsigned saddr = (unsigned)__cvta_generic_to_shared(ssrc);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the async proxy
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(saddr), "r"(bytes) : "memory");
@@ -370,8 +380,8 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 // Hot loop of the backward sweep over the cells [lo, hi) whose translated neighbours are all inside the table:
 // no bound checks, every per-stage constant in registers.  q max(v, 0) is evaluated as (q/2) (v + |v|) -- exact,
 // and |v| is a free operand modifier of the FP64 add.
-template <int NC, int NACT, bool SAME>
-__device__ __forceinline__ void sweep_interior(const float* __restrict__ cur, float* __restrict__ nxt,
+template <int NC, int NACT, bool SAME, typename TT>
+__device__ __forceinline__ void sweep_interior(const TT* __restrict__ cur, TT* __restrict__ nxt,
                                                int lo, int hi, int nthr,
                                                const double* __restrict__ s_slope, const double* __restrict__ s_q,
                                                const double* __restrict__ s_base, const double* __restrict__ s_ca,
@@ -410,13 +420,13 @@ __device__ __forceinline__ void sweep_interior(const float* __restrict__ cur, fl
                     st = fma(hq[i], v + fabs(v), st);
                 }
             }
-            const float* src = cur + (cell + i0[al]);
-            float nx = src[0];
-            if (two[al]) nx = fminf(nx, src[1]);
+            const TT* src = cur + (cell + i0[al]);
+            TT nx = src[0];
+            if (two[al]) nx = table_min<TT>(nx, src[1]);
             st += (double)nx;
             best = (al == 0 || st < best) ? st : best;
         }
-        nxt[cell] = __double2float_rd(best + pen);   // rounded DOWN: the stored table stays a lower bound
+        nxt[cell] = to_table<TT>(best + pen);   // FP32: rounded DOWN, so the stored table stays a lower bound
     }
 }
 
@@ -429,7 +439,7 @@ __device__ __forceinline__ void sweep_interior(const float* __restrict__ cur, fl
 //                  (span 0 = identity: the "no input" action maps a cell onto itself exactly)
 //   flags[k]       bit0 fast (every action allowed, no hard row, no boundary-case translation),
 //                  bit1 samepen (row violations do not depend on the action: F = 0, G D = 0)
-template <int NC, int NACT>
+template <int NC, int NACT, typename TT>
 __global__ void __launch_bounds__(512) stage_dp_table_kernel(const DpArgs A) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int b = blockIdx.x;
@@ -439,15 +449,15 @@ __global__ void __launch_bounds__(512) stage_dp_table_kernel(const DpArgs A) {
     // two stage buffers (k+1 / k), each with `pad` guard cells on both sides that hold the out-of-window bound, so
     // that the hot loop needs no bound checks
     const int pad = G_PAD(A.G);
-    float* buf0 = reinterpret_cast<float*>(smem + (size_t)plan.total * 8);
+    TT* buf0 = reinterpret_cast<TT*>(smem + (size_t)plan.total * 8);
     dp_load(A, b, c);
     const int G = c.G, Nt = c.Nt;
     const int nc = NC > 0 ? NC : c.nc, nact = NACT > 0 ? NACT : c.nact;
     const double S0 = c.misc[MISC_S0], w = c.misc[MISC_W];
-    float* tab = A.table + (int64_t)b * Nt * G;
-    float* cur = buf0 + pad;                  // stage k+1
-    float* nxt = buf0 + (G + 2 * pad) + pad;  // stage k (being written)
-    for (int cell = threadIdx.x - pad; cell < G + pad; cell += nthr) cur[cell] = 0.f;      // LB of the terminal stage
+    TT* tab = reinterpret_cast<TT*>(A.table) + (int64_t)b * Nt * G;
+    TT* cur = buf0 + pad;                  // stage k+1
+    TT* nxt = buf0 + (G + 2 * pad) + pad;  // stage k (being written)
+    for (int cell = threadIdx.x - pad; cell < G + pad; cell += nthr) cur[cell] = (TT)0;      // LB of the terminal stage
     __shared__ int s_maxshift;
     if (threadIdx.x == 0) s_maxshift = 0;
     __syncthreads();
@@ -504,8 +514,8 @@ __global__ void __launch_bounds__(512) stage_dp_table_kernel(const DpArgs A) {
     }
     if (c.misc[MISC_FLAG] != 0.0) return;
     for (int k = Nt - 1; k >= 1; --k) {
-        const float out_next = __double2float_rd(c.tailmin[k + 1]);
-        float* tabk = tab + (int64_t)k * G;
+        const TT out_next = to_table<TT>(c.tailmin[k + 1]);
+        TT* tabk = tab + (int64_t)k * G;
         const int flags = c.sc_flags[k];
         const double* s_ca = c.sc_ca + k * nact; const double* s_base = c.sc_base + k * nc * nact;
         const double* s_slope = c.sc_slope + k * nc; const double* s_q = c.qs + k * nc;
@@ -514,8 +524,8 @@ __global__ void __launch_bounds__(512) stage_dp_table_kernel(const DpArgs A) {
         const bool fast = (flags & 1) && NC > 0 && s_maxshift <= pad;
         const int lo = 0, hi = G;
         if (fast) {
-            if (flags & 2) sweep_interior<(NC > 0 ? NC : 1), (NACT > 0 ? NACT : 1), true>(cur, nxt, lo, hi, nthr, s_slope, s_q, s_base, s_ca, s_i0, s_span);
-            else sweep_interior<(NC > 0 ? NC : 1), (NACT > 0 ? NACT : 1), false>(cur, nxt, lo, hi, nthr, s_slope, s_q, s_base, s_ca, s_i0, s_span);
+            if (flags & 2) sweep_interior<(NC > 0 ? NC : 1), (NACT > 0 ? NACT : 1), true, TT>(cur, nxt, lo, hi, nthr, s_slope, s_q, s_base, s_ca, s_i0, s_span);
+            else sweep_interior<(NC > 0 ? NC : 1), (NACT > 0 ? NACT : 1), false, TT>(cur, nxt, lo, hi, nthr, s_slope, s_q, s_base, s_ca, s_i0, s_span);
         }
         {
             // ---- general loop: restricted action sets, hard rows, translations that land on a cell boundary or
@@ -546,28 +556,28 @@ __global__ void __launch_bounds__(512) stage_dp_table_kernel(const DpArgs A) {
                     }
                     const int span = s_span[al];
                     const long long c0 = (long long)cell + s_i0[al];
-                    auto at = [&](long long i) -> float { return (i < 0 || i >= G) ? out_next : cur[i]; };
-                    float nx = at(c0);
-                    if (span & 1) nx = fminf(nx, at(c0 + 1));
-                    if (span & 2) nx = fminf(nx, at(c0 - 1));
-                    if (span & 4) nx = fminf(nx, at(c0 + 2));
+                    auto at = [&](long long i) -> TT { return (i < 0 || i >= G) ? out_next : cur[i]; };
+                    TT nx = at(c0);
+                    if (span & 1) nx = table_min<TT>(nx, at(c0 + 1));
+                    if (span & 2) nx = table_min<TT>(nx, at(c0 - 1));
+                    if (span & 4) nx = table_min<TT>(nx, at(c0 + 2));
                     st += (double)nx;
                     best = st < best ? st : best;
                 }
-                nxt[cell] = __double2float_rd(best);
+                nxt[cell] = to_table<TT>(best);
             }
         }
         // guard cells of the stage just written: the bound of states outside the window at stage k
         {
-            const float out_k = __double2float_rd(c.tailmin[k]);
+            const TT out_k = to_table<TT>(c.tailmin[k]);
             for (int i = threadIdx.x; i < pad; i += nthr) { nxt[-1 - i] = out_k; nxt[G + i] = out_k; }
         }
         // the buffer the NEXT stage overwrites is the source of the bulk copy issued one stage ago: it must have
         // been read completely before anybody passes the barrier
         if (threadIdx.x == 0) bulk_wait_source_free();
         __syncthreads();
-        if (threadIdx.x == 0) bulk_store_stage(tabk, nxt, (unsigned)G * sizeof(float));   // stage k -> HBM, asynchronously
-        float* t = cur; cur = nxt; nxt = t;
+        if (threadIdx.x == 0) bulk_store_stage(tabk, nxt, (unsigned)G * sizeof(TT));   // stage k -> HBM, asynchronously
+        TT* t = cur; cur = nxt; nxt = t;
     }
     if (threadIdx.x == 0) bulk_wait_all();
 }
@@ -619,8 +629,12 @@ __device__ __forceinline__ int warp_argmin(bool flag, double val, int lane) {
 // Branch-free evaluation of lane's action sequence (depth D, NB binaries per stage, NC soft rows, every action
 // allowed): the D states are a short FMA chain, the table read of the final state is issued before the D
 // independent stage costs are computed, so its latency is hidden behind them.
+__device__ __forceinline__ double table_read(const void* tab, bool fp64, int64_t idx) {
+    return fp64 ? __ldg(reinterpret_cast<const double*>(tab) + idx) : (double)__ldg(reinterpret_cast<const float*>(tab) + idx);
+}
+
 template <int NC, int NB, int D>
-__device__ __forceinline__ bool expand_simple(const DpCtx& c, const float* __restrict__ tab, int k0, int lane, double S0,
+__device__ __forceinline__ bool expand_simple(const DpCtx& c, const void* __restrict__ tab, bool fp64, int k0, int lane, double S0,
                                               double invw, double& s, double& cost, unsigned long long& q0,
                                               unsigned long long& q1, double cut, double& bd, bool& leaf) {
     constexpr int NACT = 1 << NB;
@@ -637,12 +651,12 @@ __device__ __forceinline__ bool expand_simple(const DpCtx& c, const float* __res
         al[t] = (lane >> (t * NB)) & (NACT - 1);
         st[t + 1] = st[t] + (t < De ? c.x_shift[k * NACT + al[t]] : 0.0);
     }
-    float lbf = 0.f;
+    double lbf = 0.0;
     bool inwin = false;
     if (!leaf) {
         const double fl = floor((st[D] - S0) * invw);
         inwin = fl >= 0.0 && fl < (double)c.G;
-        if (ok && inwin) lbf = __ldg(tab + (int64_t)(k0 + D) * c.G + (int)fl);
+        if (ok && inwin) lbf = table_read(tab, fp64, (int64_t)(k0 + D) * c.G + (int)fl);
     }
 #pragma unroll
     for (int t = 0; t < D; ++t) {
@@ -662,7 +676,7 @@ __device__ __forceinline__ bool expand_simple(const DpCtx& c, const float* __res
     ok = ok && cost < cut;
     bd = cost;
     if (!leaf) {
-        bd = cost + (inwin ? (double)lbf : c.tailmin[k0 + D]);
+        bd = cost + (inwin ? lbf : c.tailmin[k0 + D]);
         ok = ok && bd < cut;
     }
     return ok;
@@ -702,7 +716,9 @@ __global__ void __launch_bounds__(kSearchWarps * 32) stage_dp_search_kernel(cons
         return;
     }
     const double S0 = c.misc[MISC_S0], invw = c.misc[MISC_INVW], a = c.misc[MISC_A];
-    const float* tab = A.table + (int64_t)b * Nt * c.G;
+    const bool fp64 = A.o.table_fp64 != 0;
+    const void* tab = fp64 ? (const void*)(reinterpret_cast<const double*>(A.table) + (int64_t)b * Nt * c.G)
+                           : (const void*)(A.table + (int64_t)b * Nt * c.G);
     const int D = nb == 1 ? 5 : (nb == 2 ? 2 : 1);      // nact^D <= 32
 
     double best = INFINITY;
@@ -714,7 +730,7 @@ __global__ void __launch_bounds__(kSearchWarps * 32) stage_dp_search_kernel(cons
     // evaluate lane's action sequence below node (k0, s, cost, path); returns ok, and (k1, s, cost, path, bd)
     auto expand = [&](int k0, double& s, double& cost, unsigned long long& q0, unsigned long long& q1, double cut,
                       double& bd, bool& leaf) -> bool {
-        if (simple21) return expand_simple<2, 1, 5>(c, tab, k0, lane, S0, invw, s, cost, q0, q1, cut, bd, leaf);
+        if (simple21) return expand_simple<2, 1, 5>(c, tab, fp64, k0, lane, S0, invw, s, cost, q0, q1, cut, bd, leaf);
         const int De = (Nt - k0) < D ? (Nt - k0) : D;
         bool ok = lane < (1 << (nb * De));
         for (int t = 0; t < De; ++t) {
@@ -731,7 +747,7 @@ __global__ void __launch_bounds__(kSearchWarps * 32) stage_dp_search_kernel(cons
         if (ok && !leaf) {
             const int k1 = k0 + De;
             const double fl = floor((s - S0) * invw);
-            const double lbv = (fl >= 0.0 && fl < (double)c.G) ? (double)__ldg(tab + (int64_t)k1 * c.G + (int)fl)
+            const double lbv = (fl >= 0.0 && fl < (double)c.G) ? table_read(tab, fp64, (int64_t)k1 * c.G + (int)fl)
                                                                : c.tailmin[k1];
             bd = cost + lbv;
             ok = bd < cut;
@@ -836,13 +852,13 @@ __global__ void __launch_bounds__(kSearchWarps * 32) stage_dp_search_kernel(cons
     }
 }
 
-static size_t table_bytes(int B, int Nt, int G) { return (size_t)B * Nt * G * sizeof(float); }
+static size_t table_bytes(int B, int Nt, int G, bool fp64) { return (size_t)B * Nt * G * (fp64 ? sizeof(double) : sizeof(float)); }
 
 }  // namespace hmpc
 
 extern "C" void hmpc_stage_dp_default_opts(hmpc_stage_dp_opts* o) {
     if (!o) return;
-    o->mip_rel_gap = 0.0; o->feas_tol = 1e-9; o->cells = 8192; o->max_nodes = 4000000;
+    o->mip_rel_gap = 0.0; o->feas_tol = 1e-9; o->cells = 8192; o->max_nodes = 4000000; o->table_fp64 = 1; o->reserved = 0;
 }
 
 extern "C" int hmpc_stage_dp_supported(const hmpc_dims* d) {
@@ -862,7 +878,7 @@ extern "C" int hmpc_stage_dp_workspace_bytes(const hmpc_dims* d, const hmpc_stag
     if (opts) o = *opts; else hmpc_stage_dp_default_opts(&o);
     if (o.cells < 64) return HMPC_ERR_ARG;
     const DpPlan plan = make_dp_plan(d->Nt, d->nu + d->ndelta, d->nc);
-    *bytes = ((table_bytes(d->B, d->Nt, o.cells) + 255) & ~(size_t)255) + (size_t)d->B * plan.nd * sizeof(double) + 256;
+    *bytes = ((table_bytes(d->B, d->Nt, o.cells, o.table_fp64 != 0) + 255) & ~(size_t)255) + (size_t)d->B * plan.nd * sizeof(double) + 256;
     return HMPC_OK;
 }
 
@@ -896,16 +912,19 @@ extern "C" int hmpc_stage_dp_solve_f64(const hmpc_dims* dims, const double* cons
     hmpc_stage_dp_workspace_bytes(dims, &a.o, &need);
     if (!workspace || workspace_bytes < need) return HMPC_ERR_WORKSPACE;
     a.table = reinterpret_cast<float*>(workspace);
-    a.pblk = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(workspace) + ((table_bytes(dims->B, dims->Nt, a.G) + 255) & ~(size_t)255));
+    a.pblk = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(workspace) + ((table_bytes(dims->B, dims->Nt, a.G, a.o.table_fp64 != 0) + 255) & ~(size_t)255));
     a.v = v; a.obj = obj; a.status = status; a.stats = stats;
     const DpPlan plan = make_dp_plan(dims->Nt, a.nb, dims->nc, a.T);
-    const size_t smem1 = (size_t)plan.total * 8 + 2 * (size_t)(a.G + 2 * G_PAD(a.G)) * sizeof(float);
+    const bool fp64 = a.o.table_fp64 != 0;
+    const size_t smem1 = (size_t)plan.total * 8 + 2 * (size_t)(a.G + 2 * G_PAD(a.G)) * (fp64 ? sizeof(double) : sizeof(float));
     const size_t smem2 = ((size_t)plan.nd * 8 + sizeof(Node) * kStackCap + 8 * (kDpMaxNt + 1)) * kSearchWarps;
     int dev = 0, smem_optin = 0;
     HMPC_CUDA_TRY(cudaGetDevice(&dev));
     HMPC_CUDA_TRY(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     if (smem1 > (size_t)smem_optin || smem2 > (size_t)smem_optin) return HMPC_ERR_ARG;
-    auto table_kernel = (dims->nc == 2 && a.nact == 2) ? stage_dp_table_kernel<2, 2> : stage_dp_table_kernel<0, 0>;
+    const bool dewh_shape = dims->nc == 2 && a.nact == 2;
+    auto table_kernel = fp64 ? (dewh_shape ? stage_dp_table_kernel<2, 2, double> : stage_dp_table_kernel<0, 0, double>)
+                             : (dewh_shape ? stage_dp_table_kernel<2, 2, float> : stage_dp_table_kernel<0, 0, float>);
     HMPC_CUDA_TRY(cudaFuncSetAttribute(table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
     HMPC_CUDA_TRY(cudaFuncSetAttribute(stage_dp_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
     cudaStream_t s = (cudaStream_t)stream;

@@ -433,3 +433,36 @@ def test_host_front_door_falls_back_to_general_kernel(cuda_device):
                                     recondense=False)
     assert np.array_equal(obj2, obj)
     plan.close()
+
+
+def test_stage_dp_fp64_table_prunes_exact_ties(cuda_device):
+    """Piecewise-constant tariff (the reference's time-of-use price vector, examples/.../tariff_generator.py): many
+    heating patterns cost exactly the same.  With the FP64 table a sequence that ties with the incumbent is pruned at
+    mip_rel_gap = 0 (bound == incumbent up to 1e-16); the FP32 table is looser by its rounding and explores them.
+    Both return the same proven optimum."""
+    from pyhybridcontrol_b200 import cabi
+    from pyhybridcontrol_b200.batch import BatchMpc
+    from pyhybridcontrol_b200.examples.residential_mg_with_pv_and_dewhs import synthetic as syn
+    from pyhybridcontrol_b200.examples.residential_mg_with_pv_and_dewhs.parameters import TOU_LEVELS
+    B, N_p = 24, 48
+    wl = syn.dewh_batch(B, N_p, seed=1)
+    Nt = wl["Nt"]
+    hour = (np.arange(Nt) % 96) / 4.0
+    level = np.full(Nt, TOU_LEVELS["low_off_peak"])
+    level[((hour >= 6) & (hour < 7)) | ((hour >= 10) & (hour < 18)) | ((hour >= 20) & (hour < 22))] = TOU_LEVELS["low_stnd"]
+    level[((hour >= 7) & (hour < 10)) | ((hour >= 18) & (hour < 20))] = TOU_LEVELS["low_peak"]
+    q_u = (level / 3600.0 / 100.0 / 1000.0 * 900.0)[None, :] * np.array([p["P_h_Nom"] for p in wl["params"]])[:, None]
+    cost = np.zeros((B, Nt, 3))
+    cost[:, :, 0] = q_u
+    cost[:, :, 1] = 10 * q_u.sum(1)[:, None]
+    cost[:, :, 2] = q_u.sum(1)[:, None]
+    out = {}
+    for fp64 in (0, 1):
+        bm = BatchMpc(wl["mats"], N_p, nu_l=1, device=cuda_device, solver="stage_dp",
+                      dp_opts=cabi.stage_dp_default_opts(table_fp64=fp64, max_nodes=2000000))
+        bm.build()
+        r = bm.solve(wl["x0"], wl["omega"], cost_v=cost.reshape(B, -1))
+        out[fp64] = (r["obj"].cpu().numpy(), r["status"].cpu().numpy(), r["stats"].cpu().numpy()[:, 0])
+    assert (out[0][1] == 0).all() and (out[1][1] == 0).all()
+    np.testing.assert_allclose(out[1][0], out[0][0], rtol=1e-9)
+    assert out[1][2].mean() < 40 and out[1][2].mean() * 5 < out[0][2].mean()

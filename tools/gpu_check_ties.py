@@ -21,15 +21,15 @@ price = level / 3600.0 / 100.0 / 1000.0 * 900.0
 P = np.array([p["P_h_Nom"] for p in wl["params"]])
 q_u = price[None, :] * P[:, None]
 cost = np.zeros((B, Nt, 3)); cost[:, :, 0] = q_u; cost[:, :, 1] = 10 * q_u.sum(1)[:, None]; cost[:, :, 2] = q_u.sum(1)[:, None]
-for gap in (0.0, 1e-5, 1e-4):
-    for cells in (8192, 16384):
+for gap, fp64 in ((0.0, 0), (0.0, 1), (1e-5, 0)):
+    for cells in (8192,):
         bm = BatchMpc(wl["mats"], N_p, nu_l=1, device="cuda:0", solver="stage_dp",
-                      dp_opts=cabi.stage_dp_default_opts(cells=cells, mip_rel_gap=gap, max_nodes=2000000))
+                      dp_opts=cabi.stage_dp_default_opts(cells=cells, mip_rel_gap=gap, max_nodes=2000000, table_fp64=fp64))
         bm.build()
         for rep in range(2):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(); res = bm.solve(wl["x0"], wl["omega"], cost_v=cost.reshape(B, -1)); e1.record(); torch.cuda.synchronize()
         st = res["stats"].cpu().numpy(); s = res["status"].cpu().numpy()
-        print("flat TOU tariff: gap %.0e cells %d: %.3f ms, status %s, nodes mean %.1f p50 %.0f max %d, obj sum %.9f" % (
-            gap, cells, e0.elapsed_time(e1), np.bincount(s, minlength=3).tolist(), st[:, 0].mean(), np.median(st[:, 0]), st[:, 0].max(),
+        print("flat TOU tariff: table %s gap %.0e cells %d: %.3f ms, status %s, nodes mean %.1f p50 %.0f max %d, obj sum %.9f" % (
+            "fp64" if fp64 else "fp32", gap, cells, e0.elapsed_time(e1), np.bincount(s, minlength=3).tolist(), st[:, 0].mean(), np.median(st[:, 0]), st[:, 0].max(),
             res["obj"].sum().item()))

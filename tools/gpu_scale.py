@@ -43,7 +43,7 @@ for B in Bs:
     lb = torch.zeros(nvt, dtype=torch.float64, device=dev)
     ub = torch.tensor(np.tile([1.0, np.inf, np.inf], Nt), dtype=torch.float64, device=dev)
     isb = torch.tensor(np.tile([1, 0, 0], Nt).astype(np.uint8), device=dev)
-    o = cabi.stage_dp_default_opts(cells=cells)
+    o = cabi.stage_dp_default_opts(cells=cells, table_fp64=int(os.environ.get("TABLE_FP64", "0")))
     ts = []
     for r in range(4):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
