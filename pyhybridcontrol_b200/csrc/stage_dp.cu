@@ -915,12 +915,15 @@ extern "C" int hmpc_stage_dp_solve_f64(const hmpc_dims* dims, const double* cons
     a.pblk = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(workspace) + ((table_bytes(dims->B, dims->Nt, a.G, a.o.table_fp64 != 0) + 255) & ~(size_t)255));
     a.v = v; a.obj = obj; a.status = status; a.stats = stats;
     const DpPlan plan = make_dp_plan(dims->Nt, a.nb, dims->nc, a.T);
-    const bool fp64 = a.o.table_fp64 != 0;
-    const size_t smem1 = (size_t)plan.total * 8 + 2 * (size_t)(a.G + 2 * G_PAD(a.G)) * (fp64 ? sizeof(double) : sizeof(float));
-    const size_t smem2 = ((size_t)plan.nd * 8 + sizeof(Node) * kStackCap + 8 * (kDpMaxNt + 1)) * kSearchWarps;
     int dev = 0, smem_optin = 0;
     HMPC_CUDA_TRY(cudaGetDevice(&dev));
     HMPC_CUDA_TRY(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    auto smem_table = [&](bool f64) { return (size_t)plan.total * 8 + 2 * (size_t)(a.G + 2 * G_PAD(a.G)) * (f64 ? sizeof(double) : sizeof(float)); };
+    // an FP64 table that does not fit the two stage buffers into shared memory (cells > ~9000) falls back to FP32
+    if (a.o.table_fp64 && smem_table(true) > (size_t)smem_optin) a.o.table_fp64 = 0;
+    const bool fp64 = a.o.table_fp64 != 0;
+    const size_t smem1 = smem_table(fp64);
+    const size_t smem2 = ((size_t)plan.nd * 8 + sizeof(Node) * kStackCap + 8 * (kDpMaxNt + 1)) * kSearchWarps;
     if (smem1 > (size_t)smem_optin || smem2 > (size_t)smem_optin) return HMPC_ERR_ARG;
     const bool dewh_shape = dims->nc == 2 && a.nact == 2;
     auto table_kernel = fp64 ? (dewh_shape ? stage_dp_table_kernel<2, 2, double> : stage_dp_table_kernel<0, 0, double>)
