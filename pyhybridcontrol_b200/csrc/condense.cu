@@ -321,7 +321,10 @@ extern "C" int hmpc_condense_f64(const hmpc_dims* dims, const double* const mats
     const int max_rows = max(1, (d.nx + d.ny + d.nc) * d.Nt / 3);
     while (d.B * S < 2 * kNumSM && S * 2 * 4 <= max_rows) S *= 2;
     dim3 grid(d.B, S);
-    condense_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(a);
+    // many agents: 128-thread CTAs (fewer idle warps in the short recurrence phases, more CTAs per SM) -- measured
+    // 2.4 vs 1.8 TB/s for the four H matrices at 10 k agents; few agents: 256 threads shorten the write phase
+    const int threads = (int64_t)d.B * S >= 8 * kNumSM ? 128 : 256;
+    condense_kernel<<<grid, threads, smem, (cudaStream_t)stream>>>(a);
     HMPC_LAUNCH_CHECK("condense_kernel");
     return HMPC_OK;
 }
