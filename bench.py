@@ -44,7 +44,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
     ap.add_argument("--agents", type=int, default=100, help="agents per GPU (weak scaling)")
     ap.add_argument("--np", dest="N_p", type=int, default=48)
-    ap.add_argument("--cpu-sample", type=int, default=64, help="agent-solves timed for cpu_baseline")
+    ap.add_argument("--cpu-sample", type=int, default=256, help="agent-solves timed for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-budget-s", type=float, default=80.0, help="--impl reference: target wall time of the run")
     ap.add_argument("--solver", default="auto", choices=("auto", "bnc", "stage_dp"),
