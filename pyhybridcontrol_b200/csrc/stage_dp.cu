@@ -673,7 +673,7 @@ __device__ __forceinline__ bool expand_simple(const DpCtx& c, const void* __rest
     }
     path_set_bits(q0, q1, k0 * NB, NB * De, (unsigned long long)(lane & ((1 << (NB * De)) - 1)));
     s = st[D];
-    ok = ok && cost < cut;
+    ok = ok && cost + c.tailmin[k0 + De] < cut;      // (the costs still ahead may be negative: tailmin <= 0)
     bd = cost;
     if (!leaf) {
         bd = cost + (inwin ? lbf : c.tailmin[k0 + D]);
@@ -740,7 +740,7 @@ __global__ void __launch_bounds__(kSearchWarps * 32) stage_dp_search_kernel(cons
             cost += stage_cost(c, k, al, c.ak[k] * s);
             s = fma(c.galpha[al], c.iak[k + 1], s);
             path_set(q0, q1, k, nb, al);
-            if (!(cost < cut)) ok = false;
+            if (!(cost + c.tailmin[k + 1] < cut)) ok = false;   // partial cost + the most negative costs still ahead
         }
         leaf = (k0 + De == Nt);
         bd = cost;

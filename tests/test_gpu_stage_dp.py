@@ -466,3 +466,38 @@ def test_stage_dp_fp64_table_prunes_exact_ties(cuda_device):
     assert (out[0][1] == 0).all() and (out[1][1] == 0).all()
     np.testing.assert_allclose(out[1][0], out[0][0], rtol=1e-9)
     assert out[1][2].mean() < 40 and out[1][2].mean() * 5 < out[0][2].mean()
+
+
+def test_stage_dp_fuzz_against_branch_and_cut(cuda_device):
+    """Randomised cross-check of the two solve kernels on 1000 problems of the class with NEGATIVE action costs,
+    inputs of both signs, A on both sides of 1, hard rows and pinned binaries.  (Found in round 1: pruning on the
+    partial cost alone is invalid when the costs still ahead can be negative -- the search now adds their sum.)"""
+    from pyhybridcontrol_b200 import cabi
+    B = 200
+    shapes = [(1, 0, 3, 1, True, 0, 20), (1, 0, 4, 2, False, 0, 12), (2, 1, 4, 1, True, 2, 6), (2, 0, 3, 2, True, 1, 8),
+              (1, 1, 2, 1, True, 0, 10)]
+    checked = 0
+    for seed, (nu, ndelta, nc, ny, soft, hard, Nt) in enumerate(shapes):
+        rng = np.random.default_rng(2000 + seed)
+        m = random_scalar_mld(rng, B, nu, ndelta, nc, ny, soft, hard)
+        if not soft:
+            m["f5"] = m["f5"] * 3.0
+        nb, nmu = nu + ndelta, (nc if soft else 0)
+        x0 = rng.uniform(-1.5, 1.5, size=(B, 1))
+        om = rng.uniform(-1.0, 1.0, size=(B, Nt))
+        cost = np.zeros((B, Nt, nb + nmu))
+        cost[:, :, :nb] = rng.uniform(-0.4, 1.0, size=(B, Nt, nb))
+        cost[:, :, nb:] = rng.uniform(1.0, 30.0, size=(B, 1, nmu))
+        lb = np.tile(np.r_[np.zeros(nb), np.zeros(nmu)], Nt)
+        ub = np.tile(np.r_[np.ones(nb), np.full(nmu, np.inf)], Nt)
+        for pidx in rng.integers(0, Nt * (nb + nmu), size=3):
+            if pidx % (nb + nmu) < nb:
+                lb[pidx] = ub[pidx] = float(rng.integers(0, 2))
+        out = solve_both(m, Nt, nu, ndelta, x0, om, cost.reshape(B, -1), cuda_device, lb=lb, ub=ub)
+        dp, bnc = out["stage_dp"], out["bnc"]
+        both = (dp["status"] == 0) & (bnc["status"] == 0)
+        assert not (((dp["status"] == 1) & (bnc["status"] == 0)) | ((dp["status"] == 0) & (bnc["status"] == 1))).any()
+        rel = np.abs(dp["obj"][both] - bnc["obj"][both]) / np.maximum(1.0, np.abs(bnc["obj"][both]))
+        assert rel.max() <= 1e-6, (seed, float(rel.max()), int(np.argmax(rel)))
+        checked += int(both.sum())
+    assert checked > 800
