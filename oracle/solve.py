@@ -83,7 +83,64 @@ def solve_enumerate(prob, max_bin=18):
 
 
 def solve_qp(prob, lb=None, ub=None):
-    """Convex QP relaxation through HiGHS' QP solver (private scipy binding)."""
+    """Convex QP relaxation.  HiGHS' QP solver (private scipy binding) first; it gives up (neither optimal nor
+    infeasible) on a fraction of a percent of the sub-problems with many fixed columns, so those are retried with the
+    fixed columns eliminated and, as a last resort, with scipy's SLSQP."""
+    lb = prob.lb if lb is None else lb
+    ub = prob.ub if ub is None else ub
+    st, obj, v = _solve_qp_highs(prob, lb, ub)
+    if st != LIMIT:
+        return st, obj, v
+    fixed = np.isfinite(lb) & (lb == ub)
+    if fixed.any() and not fixed.all():
+        from .assemble import Problem
+        fr = ~fixed
+        xf = lb[fixed]
+        red = Problem(int(fr.sum()))
+        P = prob.P if prob.P is not None else np.zeros((prob.n, prob.n))
+        Ps = 0.5 * (P + P.T)
+        red.P = Ps[np.ix_(fr, fr)]
+        red.c = prob.c[fr] + Ps[np.ix_(fr, fixed)] @ xf
+        red.c0 = prob.c0 + float(prob.c[fixed] @ xf) + 0.5 * float(xf @ Ps[np.ix_(fixed, fixed)] @ xf)
+        red.H = prob.H[:, fr]
+        red.rhs = prob.rhs - prob.H[:, fixed] @ xf
+        red.lb, red.ub = lb[fr], ub[fr]
+        st, obj, vr = _solve_qp_highs(red, red.lb, red.ub)
+        if st == LIMIT:
+            st, obj, vr = _solve_qp_slsqp(red)
+        if st == OPTIMAL:
+            v = np.zeros(prob.n)
+            v[fixed], v[fr] = xf, vr
+            return OPTIMAL, prob.objective(v), v
+        return st, np.inf, None
+    return _solve_qp_slsqp(prob, lb, ub)
+
+
+def _solve_qp_slsqp(prob, lb=None, ub=None):
+    from scipy.optimize import minimize
+    lb = prob.lb if lb is None else lb
+    ub = prob.ub if ub is None else ub
+    P = 0.5 * (prob.P + prob.P.T) if prob.P is not None else np.zeros((prob.n, prob.n))
+    x0 = np.clip(np.zeros(prob.n), np.where(np.isfinite(lb), lb, -1e6), np.where(np.isfinite(ub), ub, 1e6))
+    cons = [{"type": "ineq", "fun": lambda x: prob.rhs - prob.H @ x, "jac": lambda x: -prob.H}] if prob.H.shape[0] else []
+    res = minimize(lambda x: 0.5 * x @ P @ x + prob.c @ x, x0, jac=lambda x: P @ x + prob.c, method="SLSQP",
+                   bounds=list(zip(np.where(np.isfinite(lb), lb, None), np.where(np.isfinite(ub), ub, None))),
+                   constraints=cons, options={"maxiter": 500, "ftol": 1e-14})
+    if res.success and (not prob.H.shape[0] or np.max(prob.H @ res.x - prob.rhs) <= 1e-8):
+        return OPTIMAL, prob.objective(res.x), res.x
+    # interior-point fallback (slow, robust): scipy trust-constr
+    from scipy.optimize import Bounds as _B, LinearConstraint as _LC
+    cons = [_LC(prob.H, -np.inf, prob.rhs)] if prob.H.shape[0] else []
+    res = minimize(lambda x: 0.5 * x @ P @ x + prob.c @ x, x0, jac=lambda x: P @ x + prob.c, hess=lambda x: P,
+                   method="trust-constr", constraints=cons, bounds=_B(lb, ub),
+                   options={"gtol": 1e-11, "xtol": 1e-13, "maxiter": 3000})
+    if res.status in (1, 2) and (not prob.H.shape[0] or np.max(prob.H @ res.x - prob.rhs) <= 1e-7):
+        return OPTIMAL, prob.objective(res.x), res.x
+    return LIMIT, np.inf, None
+
+
+def _solve_qp_highs(prob, lb=None, ub=None):
+    """HiGHS' QP solver through the private scipy binding."""
     from scipy.optimize._highspy import _core as hs
     lb = prob.lb if lb is None else lb
     ub = prob.ub if ub is None else ub
