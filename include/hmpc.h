@@ -204,6 +204,12 @@ int hmpc_dewh_sim_step_f64(int32_t B, const double* params, const double* T, con
                            const double* D_h, double* T1, double* model, uint8_t* cons, void* stream);
 /* control model (const_heat=True): model [B,4] = {A, B1, B4, b5} */
 int hmpc_dewh_control_model_f64(int32_t B, const double* params, double* model, void* stream);
+/* thermostat rule of the example's non-predictive controller: replaces DewhTheromstatController.solve
+ *      (examples/residential_mg_with_pv_and_dewhs/theromstat_control.py:38-62).  band [B,2] (stride 2) or [1,2]
+ *      (stride 0) = {T_h_max_sub_T_h_on, T_h_max_sub_T_h_off} (parameters.py:21-22); T [B]; u_prev [B] is the input
+ *      applied at k-1 (the reference keeps "on" only if it is exactly 1); u [B] out (0.0 / 1.0).         */
+int hmpc_dewh_thermostat_f64(int32_t B, const double* params, const double* band, int64_t band_stride_b,
+                             const double* T, const double* u_prev, double* u, void* stream);
 
 /* ---- K6 aggregate power: replaces GridAgentMpc.get_grid_device_powers_N_tilde + GridModel D4 = ones
  *      (micro_grid_agents.py:625-646, micro_grid_models.py:143):  P_agg[k] = sum_b P_nom[b] * u[b,k].

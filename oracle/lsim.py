@@ -69,6 +69,16 @@ def dewh_sim_step(p, x, u, omega):
     return x1, x, cons
 
 
+def dewh_thermostat(p, T_h, u_prev):
+    """theromstat_control.py:50-62: hysteresis between T_h_max - T_h_max_sub_T_h_on and T_h_max - T_h_max_sub_T_h_off;
+    inside the band the previous input is kept only if it equals 1."""
+    if T_h <= p["T_h_max"] - p["T_h_max_sub_T_h_on"]:
+        return 1
+    if T_h >= p["T_h_max"] - p["T_h_max_sub_T_h_off"]:
+        return 0
+    return 1 if u_prev == 1 else 0
+
+
 def grid_mld(p, num_devices):
     """micro_grid_models.py:137-172: nx=0, ndelta=1, nz=1, nomega=num_devices, ny=1, nc=6."""
     lo, hi, eps = p["P_g_min"], p["P_g_max"], p["eps"]

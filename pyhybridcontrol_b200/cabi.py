@@ -21,8 +21,8 @@ EXPORTS = ("hmpc_version", "hmpc_last_cuda_error", "hmpc_device_info", "hmpc_con
            "hmpc_condense_bytes_per_agent", "hmpc_constraint_rhs_f64", "hmpc_predict_f64", "hmpc_linear_cost_f64",
            "hmpc_milp_default_opts", "hmpc_milp_workspace_bytes", "hmpc_milp_solve_f64", "hmpc_stage_dp_default_opts",
            "hmpc_stage_dp_supported", "hmpc_stage_dp_workspace_bytes", "hmpc_stage_dp_solve_f64", "hmpc_lsim_step_f64",
-           "hmpc_dewh_sim_step_f64", "hmpc_dewh_control_model_f64", "hmpc_aggregate_power_f64",
-           "hmpc_step_plan_create", "hmpc_step_plan_destroy", "hmpc_mpc_step_host_f64", "hmpc_mpc_step_host_bytes",
+           "hmpc_dewh_sim_step_f64", "hmpc_dewh_control_model_f64", "hmpc_dewh_thermostat_f64",
+           "hmpc_aggregate_power_f64", "hmpc_step_plan_create", "hmpc_step_plan_destroy", "hmpc_mpc_step_host_f64", "hmpc_mpc_step_host_bytes",
            "hmpc_step_plan_last_solver",
            "hmpc_fp64_peak_probe")
 
@@ -96,6 +96,7 @@ _lib.hmpc_stage_dp_solve_f64.argtypes = [C.POINTER(Dims), _MatArr, _StrideArr, _
 _lib.hmpc_lsim_step_f64.argtypes = [C.POINTER(Dims), _MatArr, _StrideArr] + [_P] * 5 + [C.c_double] + [_P] * 4
 _lib.hmpc_dewh_sim_step_f64.argtypes = [C.c_int32] + [_P] * 8
 _lib.hmpc_dewh_control_model_f64.argtypes = [C.c_int32, _P, _P, _P]
+_lib.hmpc_dewh_thermostat_f64.argtypes = [C.c_int32, _P, _P, C.c_int64, _P, _P, _P, _P]
 _lib.hmpc_aggregate_power_f64.argtypes = [C.c_int32, C.c_int32, _P, C.c_int64, C.c_int32, _P, _P, _P, _P]
 _lib.hmpc_step_plan_create.argtypes = [C.POINTER(Dims), C.POINTER(MilpOpts), C.POINTER(_P)]
 _lib.hmpc_step_plan_destroy.argtypes = [_P]
@@ -397,6 +398,21 @@ def dewh_sim_step(params, T, u, D_h, want_model=False):
                                        _ptr(cons), _stream()), "hmpc_dewh_sim_step_f64")
     launch_count += 1
     return T1, model, cons
+
+
+def dewh_thermostat(params, band, T, u_prev):
+    """Thermostat rule for a batch: band [B,2] or [1,2] = (T_h_max_sub_T_h_on, T_h_max_sub_T_h_off) -> u [B]."""
+    global launch_count
+    B = T.shape[0]
+    band = band.reshape(-1, 2)
+    if band.shape[0] not in (1, B):
+        raise ValueError("band must be [B,2] or [1,2]")
+    u = torch.empty_like(T)
+    band = band.contiguous()
+    _check(_lib.hmpc_dewh_thermostat_f64(B, _ptr(params), _ptr(band), 2 if band.shape[0] == B else 0, _ptr(T),
+                                         _ptr(u_prev), _ptr(u), _stream()), "hmpc_dewh_thermostat_f64")
+    launch_count += 1
+    return u
 
 
 def dewh_control_model(params):

@@ -120,6 +120,24 @@ __global__ void __launch_bounds__(256) dewh_control_model_kernel(int B, const do
     model[4 * b + 0] = A; model[4 * b + 1] = B1; model[4 * b + 2] = B4; model[4 * b + 3] = b5;
 }
 
+// Hysteresis rule of the example's non-predictive controller (theromstat_control.py:50-62): on at or below
+// T_max - band_on, off at or above T_max - band_off, in between the previous input is kept (exactly 1 keeps "on").
+__global__ void __launch_bounds__(256) dewh_thermostat_kernel(int B, const double* __restrict__ params,
+                                                              const double* __restrict__ band, int64_t band_stride_b,
+                                                              const double* __restrict__ T,
+                                                              const double* __restrict__ u_prev, double* __restrict__ u) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const double T_max = params[(int64_t)b * 12 + 8];
+    const double on = band[b * band_stride_b + 0], off = band[b * band_stride_b + 1];
+    const double x = T[b];
+    double out;
+    if (x <= T_max - on) out = 1.0;
+    else if (x >= T_max - off) out = 0.0;
+    else out = (u_prev[b] == 1.0) ? 1.0 : 0.0;
+    u[b] = out;
+}
+
 }  // namespace hmpc
 
 extern "C" int hmpc_lsim_step_f64(const hmpc_dims* dims, const double* const mats[HMPC_NUM_MATS],
@@ -165,5 +183,17 @@ extern "C" int hmpc_dewh_control_model_f64(int32_t B, const double* params, doub
     if (B == 0) return HMPC_OK;
     dewh_control_model_kernel<<<ceil_div(B, 256), 256, 0, (cudaStream_t)stream>>>(B, params, model);
     HMPC_LAUNCH_CHECK("dewh_control_model_kernel");
+    return HMPC_OK;
+}
+
+extern "C" int hmpc_dewh_thermostat_f64(int32_t B, const double* params, const double* band, int64_t band_stride_b,
+                                        const double* T, const double* u_prev, double* u, void* stream) {
+    using namespace hmpc;
+    if (B < 0 || !params || !band || !T || !u_prev || !u || (band_stride_b != 0 && band_stride_b != 2))
+        return HMPC_ERR_ARG;
+    if (B == 0) return HMPC_OK;
+    dewh_thermostat_kernel<<<ceil_div(B, 256), 256, 0, (cudaStream_t)stream>>>(B, params, band, band_stride_b, T,
+                                                                                u_prev, u);
+    HMPC_LAUNCH_CHECK("dewh_thermostat_kernel");
     return HMPC_OK;
 }

@@ -21,6 +21,8 @@ class DewhFleet(object):
         self.Nt = self.N_p + 1
         self.params = torch.as_tensor(cabi.pack_dewh_params(params), dtype=torch.float64).to(self.device)
         self.P_nom = self.params[:, 6].contiguous()
+        self.band = torch.as_tensor([[p.get("T_h_max_sub_T_h_on", 12.0), p.get("T_h_max_sub_T_h_off", 4.0)]
+                                     for p in params], dtype=torch.float64).to(self.device)
         B = self.B
         one = torch.ones((1, 1, 1), dtype=torch.float64, device=self.device)
         self._mats = dict(
@@ -60,9 +62,9 @@ class DewhFleet(object):
                             (self.soft_bot_mult * tot).expand(-1, self.Nt)], dim=2)
         return cost.reshape(self.B, 3 * self.Nt).contiguous()
 
-    def control_step(self, x0, omega_forecast, cost_v):
+    def control_step(self, x0, omega_forecast, cost_v, extra_constraints=()):
         """-> dict(v, obj, status, stats, u [B, Nt] view)."""
-        res = self.batch.solve(x0, omega_forecast, cost_v=cost_v)
+        res = self.batch.solve(x0, omega_forecast, cost_v=cost_v, extra_constraints=extra_constraints)
         res["u"] = res["v"].view(self.B, self.Nt, 3)[:, :, 0]
         return res
 
@@ -75,29 +77,95 @@ class DewhFleet(object):
         """sum_b P_nom[b] u[b, k] over this rank's agents, then over ranks -> [Nt]."""
         return distributed.allreduce_aggregate(cabi.aggregate_power(u, self.P_nom))
 
-    def closed_loop(self, T0, demand, price, sim_steps, demand_actual=None):
+    CONTROLLERS = ("mpc_pb", "mpc_ce", "mpc_sb_reduced", "mpc_sb_full", "mpc_minmax", "thermo")
+
+    def thermostat(self, T, u_prev):
+        """Rule-based input of the non-predictive controller (theromstat_control.py:38-62) for every tank."""
+        return cabi.dewh_thermostat(self.params, self.band, T, u_prev)
+
+    def _extra_sets(self, controller, k, scenarios, demand_minmax, N_sb_reduced):
+        """Constraint sets a controller variant adds to the standard one at instant k
+        (micro_grid_control_simulation.py:200-227); every set shares the rows of H_v."""
+        Nt = self.Nt
+        if controller in ("mpc_sb_reduced", "mpc_sb_full"):
+            if scenarios is None:
+                raise ValueError("controller '%s' needs `scenarios`" % controller)
+            sc = scenarios(k) if callable(scenarios) else scenarios[:, k:k + Nt, :]
+            sc = torch.as_tensor(sc, dtype=torch.float64).to(self.device).reshape(self.B, Nt, -1).contiguous()
+            if controller == "mpc_sb_reduced":
+                return [dict(omega_scenarios_k=sc, N_tilde=min(int(N_sb_reduced), Nt))]
+            return [dict(omega_scenarios_k=sc)]
+        if controller == "mpc_minmax":
+            if demand_minmax is None:
+                raise ValueError("controller 'mpc_minmax' needs `demand_minmax` = (min profile, max profile)")
+            out = []
+            for prof in demand_minmax:
+                prof = torch.as_tensor(prof, dtype=torch.float64).to(self.device)
+                win = prof[k:k + Nt] if prof.dim() == 1 else prof[:, k:k + Nt]
+                out.append(dict(omega_tilde_k=win.expand(self.B, Nt).contiguous()))
+            return out
+        return []
+
+    def closed_loop(self, T0, demand, price, sim_steps, demand_actual=None, controller="mpc_ce", scenarios=None,
+                    N_sb_reduced=8, demand_minmax=None, u_init=None):
         """Closed-loop simulation of the shard (reference loop: examples/.../micro_grid_control_simulation.py:184-236
         with the per-device work of micro_grid_agents.py:699-700, 733-740): at every step k the forecast window
         demand[:, k:k+Nt] and price[k:k+Nt] give the MPC problem, the first control is applied to the re-parametrised
         simulation model with the actual draw, and the aggregate power is exchanged.  Everything stays in HBM; the
         log comes back as device tensors.
 
+        controller (the campaign's six variants, micro_grid_control_simulation.py:144-152):
+          mpc_pb          forecast = the actual draw (deterministic; needs demand_actual of sim_steps + Nt columns)
+          mpc_ce          forecast = `demand` (certainty equivalent)
+          mpc_sb_reduced  mpc_ce + scenario set (row-wise min over S scenarios) on the first N_sb_reduced steps
+          mpc_sb_full     mpc_ce + scenario set on the whole horizon
+          mpc_minmax      mpc_ce + one set for the min-draw and one for the max-draw profile
+          thermo          thermostat rule, no optimisation (obj is NaN, P_agg has one column)
+
         T0 [B] initial temperatures; demand [B, sim_steps + Nt] (L/s); price [sim_steps + Nt] or [B, sim_steps + Nt];
-        demand_actual [B, sim_steps] defaults to demand[:, :sim_steps].
+        demand_actual [B, >= sim_steps] defaults to demand; scenarios [B, sim_steps + Nt, S] or callable k -> [B, Nt, S];
+        demand_minmax = (min, max) profiles [sim_steps + Nt] or [B, sim_steps + Nt]; u_init [B] input before step 0
+        (thermostat only).
         -> dict(T [sim_steps + 1, B], u [sim_steps, B], obj [sim_steps, B], status [sim_steps, B],
                 P_agg [sim_steps, Nt], cons [sim_steps, B, 2])"""
+        if controller not in self.CONTROLLERS:
+            raise ValueError("controller must be one of %s" % (self.CONTROLLERS,))
         dev, B, Nt = self.device, self.B, self.Nt
         T = torch.as_tensor(T0, dtype=torch.float64).to(dev).reshape(B).clone()
         demand = torch.as_tensor(demand, dtype=torch.float64).to(dev)
         price = torch.as_tensor(price, dtype=torch.float64).to(dev)
-        actual = demand[:, :sim_steps] if demand_actual is None else torch.as_tensor(demand_actual, dtype=torch.float64).to(dev)
+        actual = demand if demand_actual is None else torch.as_tensor(demand_actual, dtype=torch.float64).to(dev)
+        forecast = demand
+        if controller == "mpc_pb":
+            if actual.shape[1] < sim_steps + Nt:
+                raise ValueError("mpc_pb needs the actual draw over sim_steps + N_tilde steps")
+            forecast = actual
         log = dict(T=[T.clone()], u=[], obj=[], status=[], P_agg=[], cons=[])
+        if controller == "thermo":
+            u_prev = (torch.zeros(B, dtype=torch.float64, device=dev) if u_init is None
+                      else torch.as_tensor(u_init, dtype=torch.float64).to(dev).reshape(B).clone())
+            nan = torch.full((B,), float("nan"), dtype=torch.float64, device=dev)
+            ok = torch.zeros(B, dtype=torch.int32, device=dev)
+            for k in range(sim_steps):
+                u0 = self.thermostat(T, u_prev)
+                T, cons = self.sim_step(T, u0, actual[:, k].contiguous())
+                log["T"].append(T.clone()); log["u"].append(u0); log["obj"].append(nan); log["status"].append(ok)
+                log["P_agg"].append(self.aggregate_power(u0.reshape(B, 1))); log["cons"].append(cons)
+                u_prev = u0
+            return {k: torch.stack(v) for k, v in log.items()}
         self.build()                                   # the control model does not change along the run
         for k in range(sim_steps):
             pk = price[k:k + Nt] if price.dim() == 1 else price[:, k:k + Nt]
-            res = self.control_step(T.reshape(B, 1), demand[:, k:k + Nt].contiguous(), self.cost_from_prices(pk))
+            extra = self._extra_sets(controller, k, scenarios, demand_minmax, N_sb_reduced)
+            res = self.control_step(T.reshape(B, 1), forecast[:, k:k + Nt].contiguous(), self.cost_from_prices(pk),
+                                    extra_constraints=extra)
             u0 = res["u"][:, 0].contiguous()
             T, cons = self.sim_step(T, u0, actual[:, k].contiguous())
             log["T"].append(T.clone()); log["u"].append(u0); log["obj"].append(res["obj"])
             log["status"].append(res["status"]); log["P_agg"].append(self.aggregate_power(res["u"])); log["cons"].append(cons)
         return {k: torch.stack(v) for k, v in log.items()}
+
+    def campaign(self, controllers, T0, demand, price, sim_steps, **kwargs):
+        """Every named controller variant from the same initial state and data, one after the other
+        (micro_grid_control_simulation.py:157-236 runs them side by side) -> {name: closed_loop log}."""
+        return {name: self.closed_loop(T0, demand, price, sim_steps, controller=name, **kwargs) for name in controllers}
