@@ -127,7 +127,9 @@ class DewhFleet(object):
         demand_minmax = (min, max) profiles [sim_steps + Nt] or [B, sim_steps + Nt]; u_init [B] input before step 0
         (thermostat only).
         -> dict(T [sim_steps + 1, B], u [sim_steps, B], obj [sim_steps, B], status [sim_steps, B],
-                P_agg [sim_steps, Nt], cons [sim_steps, B, 2])"""
+                P_agg [sim_steps, Nt], cons [sim_steps, B, 2], mu_hat [sim_steps, B, 2] (first-step slacks of the
+                plan), omega / omega_hat [sim_steps, B] (actual draw / first forecast value), solve_ms [sim_steps]
+                (device time of the batch solve))"""
         if controller not in self.CONTROLLERS:
             raise ValueError("controller must be one of %s" % (self.CONTROLLERS,))
         dev, B, Nt = self.device, self.B, self.Nt
@@ -140,7 +142,8 @@ class DewhFleet(object):
             if actual.shape[1] < sim_steps + Nt:
                 raise ValueError("mpc_pb needs the actual draw over sim_steps + N_tilde steps")
             forecast = actual
-        log = dict(T=[T.clone()], u=[], obj=[], status=[], P_agg=[], cons=[])
+        log = dict(T=[T.clone()], u=[], obj=[], status=[], P_agg=[], cons=[], mu_hat=[], omega=[], omega_hat=[])
+        events = []
         if controller == "thermo":
             u_prev = (torch.zeros(B, dtype=torch.float64, device=dev) if u_init is None
                       else torch.as_tensor(u_init, dtype=torch.float64).to(dev).reshape(B).clone())
@@ -151,19 +154,72 @@ class DewhFleet(object):
                 T, cons = self.sim_step(T, u0, actual[:, k].contiguous())
                 log["T"].append(T.clone()); log["u"].append(u0); log["obj"].append(nan); log["status"].append(ok)
                 log["P_agg"].append(self.aggregate_power(u0.reshape(B, 1))); log["cons"].append(cons)
+                log["mu_hat"].append(nan.reshape(B, 1).expand(B, 2)); log["omega"].append(actual[:, k])
+                log["omega_hat"].append(forecast[:, k])
                 u_prev = u0
-            return {k: torch.stack(v) for k, v in log.items()}
+            out = {k: torch.stack(v) for k, v in log.items()}
+            out["solve_ms"] = torch.zeros(sim_steps, dtype=torch.float64, device=dev)
+            return out
         self.build()                                   # the control model does not change along the run
         for k in range(sim_steps):
             pk = price[k:k + Nt] if price.dim() == 1 else price[:, k:k + Nt]
             extra = self._extra_sets(controller, k, scenarios, demand_minmax, N_sb_reduced)
+            events.append((torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)))
+            events[-1][0].record()
             res = self.control_step(T.reshape(B, 1), forecast[:, k:k + Nt].contiguous(), self.cost_from_prices(pk),
                                     extra_constraints=extra)
+            events[-1][1].record()
             u0 = res["u"][:, 0].contiguous()
             T, cons = self.sim_step(T, u0, actual[:, k].contiguous())
             log["T"].append(T.clone()); log["u"].append(u0); log["obj"].append(res["obj"])
             log["status"].append(res["status"]); log["P_agg"].append(self.aggregate_power(res["u"])); log["cons"].append(cons)
-        return {k: torch.stack(v) for k, v in log.items()}
+            log["mu_hat"].append(res["v"].view(B, Nt, 3)[:, 0, 1:]); log["omega"].append(actual[:, k])
+            log["omega_hat"].append(forecast[:, k])
+        out = {k: torch.stack(v) for k, v in log.items()}
+        torch.cuda.synchronize(dev)
+        out["solve_ms"] = torch.tensor([a.elapsed_time(b) for a, b in events], dtype=torch.float64, device=dev)
+        return out
+
+    def grid_log(self, log, price, pv=None, resd=None, grid_params=None, device_ids=None):
+        """Grid-agent view of a closed-loop log (micro_grid_agents.py:625-646, 736-756): the stacked device powers
+        omega = [P_h_Nom u of every DEWH ordered by device id, PV y, demand y], the grid MLD step
+        (micro_grid_models.py:137-172) with delta = [y >= 0], z = delta y through K5, and the planned counterparts
+        (``*_hat``) from the first step of the aggregate plan.  pv / resd: dict(omega [steps] actual, omega_hat
+        [steps] forecast, gain) with gain = -P_pv_max P_pv_units / P_res_ave P_res_units.  Single-rank view (the
+        per-device columns are this rank's agents).  -> dict of device tensors for results.grid_log_blocks."""
+        from .parameters import grid_param_struct
+        from .models import grid_mld_matrices
+        gp = dict(grid_param_struct if grid_params is None else grid_params)
+        dev, B = self.device, self.B
+        u = log["u"].to(dev)
+        steps = u.shape[0]
+        order = np.argsort(np.asarray(device_ids)) if device_ids is not None else np.arange(B)
+        order = torch.as_tensor(order, device=dev)
+        cols, cols_hat = [(u * self.P_nom[None, :])[:, order]], [(u * self.P_nom[None, :])[:, order]]
+        for src in (pv, resd):
+            if src is not None:
+                w = torch.as_tensor(src["omega"], dtype=torch.float64).to(dev).reshape(steps, 1)
+                wh = torch.as_tensor(src.get("omega_hat", src["omega"]), dtype=torch.float64).to(dev).reshape(steps, 1)
+                cols.append(float(src["gain"]) * w)
+                cols_hat.append(float(src["gain"]) * wh)
+        out = {}
+        mats = {k: torch.as_tensor(v, dtype=torch.float64).to(dev).unsqueeze(0)
+                for k, v in grid_mld_matrices(gp, sum(c.shape[1] for c in cols)).items()}
+        for tag, parts in (("", cols), ("_hat", cols_hat)):
+            omega = torch.cat(parts, dim=1).contiguous()
+            d = cabi.make_dims(steps, 1, nx=0, nu=0, ndelta=1, nz=1, nmu=0, nomega=omega.shape[1], ny=1, nc=6)
+            zero = torch.zeros((steps, 1), dtype=torch.float64, device=dev)
+            _, y, _ = cabi.lsim_step(d, mats, None, None, zero, zero, omega)    # y = D4 omega does not need delta / z
+            delta = (y >= 0).to(torch.float64)                                  # unique feasible auxiliaries (a12)
+            z = delta * y
+            _, y2, cons = cabi.lsim_step(d, mats, None, None, delta, z, omega)
+            out.update({"omega" + tag: omega, "y" + tag: y2.reshape(steps), "delta" + tag: delta.reshape(steps),
+                        "z" + tag: z.reshape(steps)})
+            if not tag:
+                out["cons"] = cons
+        price = torch.as_tensor(price, dtype=torch.float64).to(dev)
+        out["price"] = price[:steps] if price.dim() == 1 else price[0, :steps]
+        return out
 
     def campaign(self, controllers, T0, demand, price, sim_steps, **kwargs):
         """Every named controller variant from the same initial state and data, one after the other

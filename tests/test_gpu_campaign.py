@@ -139,3 +139,56 @@ def test_campaign_runs_all_six(cuda_device):
         fleet.closed_loop(T0, forecast, price, steps, controller="mpc_sb_full")
     with pytest.raises(ValueError):
         fleet.closed_loop(T0, forecast, price, steps, controller="nope")
+
+
+def test_grid_log_and_result_frame(cuda_device):
+    """closed-loop logs -> grid-agent arrays (K5 on the grid MLD, batch axis = steps) -> the reference's result frame;
+    the grid arrays are checked against the oracle's lsim_k, the frame against the log it was built from."""
+    from oracle import lsim as ol, mld as omld
+    from pyhybridcontrol_b200.examples.residential_mg_with_pv_and_dewhs import results, models
+    from pyhybridcontrol_b200.examples.residential_mg_with_pv_and_dewhs.fleet import DewhFleet
+    from pyhybridcontrol_b200.examples.residential_mg_with_pv_and_dewhs.parameters import (
+        pv_param_struct, res_demand_param_struct, grid_param_struct)
+    B, N_p, steps = 5, 8, 6
+    params, T0, forecast, actual, price, scen, minmax = _fleet_data(B, N_p, steps, seed0=600)
+    ids = [9, 2, 5, 4, 7]
+    rng = np.random.default_rng(3)
+    pv = dict(omega=rng.random(steps), omega_hat=rng.random(steps), gain=models.pv_gain(dict(pv_param_struct, P_pv_units=B)))
+    resd = dict(omega=2 * rng.random(steps), omega_hat=2 * rng.random(steps),
+                gain=models.resd_gain(dict(res_demand_param_struct, P_res_units=B)))
+    fleet = DewhFleet(params, N_p, device=cuda_device)
+    logs = fleet.campaign(("mpc_ce", "thermo"), T0, forecast, price, steps, demand_actual=actual)
+    grid = {k: v.cpu().numpy() for k, v in fleet.grid_log(logs["mpc_ce"], price, pv=pv, resd=resd, device_ids=ids).items()}
+    lg = {k: v.cpu().numpy() for k, v in logs["mpc_ce"].items()}
+    P = np.array([p["P_h_Nom"] for p in params])
+    order = np.argsort(ids)
+    full, d, _ = omld.complete({k: np.array(v, dtype=float) for k, v in ol.grid_mld(grid_param_struct, B + 2).items()})
+    for tag in ("", "_hat"):
+        w = np.concatenate([(lg["u"] * P)[:, order], pv["gain"] * pv["omega" + tag][:, None],
+                            resd["gain"] * resd["omega" + tag][:, None]], axis=1)
+        np.testing.assert_allclose(grid["omega" + tag], w, rtol=1e-15)
+        for k in range(steps):
+            de, z = ol.grid_aux_closed_form(float(np.ones(B + 2) @ w[k]))
+            _, y, cons = ol.lsim_k(full, np.zeros((0, 1)), np.zeros((0, 1)), np.array([[de]]), np.array([[z]]),
+                                   np.zeros((0, 1)), w[k].reshape(-1, 1))
+            assert grid["delta" + tag][k] == de
+            np.testing.assert_allclose(grid["y" + tag][k], float(y.ravel()[0]), rtol=1e-13)
+            np.testing.assert_allclose(grid["z" + tag][k], z, rtol=1e-13)
+            if not tag:
+                assert np.array_equal(grid["cons"][k].astype(bool), np.asarray(cons).ravel())
+    assert grid["cons"].all()                                # the closed-form auxiliaries are feasible
+    blocks = [("dewh", ids, c, results.dewh_log_blocks({k: v.cpu().numpy() for k, v in logs[c].items()}, params, c))
+              for c in ("mpc_ce", "thermo")]
+    blocks += [("pv", [1], "mpc_ce", results.source_log_blocks(pv["omega"], pv["omega_hat"], pv["gain"])),
+               ("resd", [1], "mpc_ce", results.source_log_blocks(resd["omega"], resd["omega_hat"], resd["gain"])),
+               ("grid", [1], "mpc_ce", results.grid_log_blocks(grid))]
+    df = results.grid_sim_dataframe(blocks, steps, time_0="2018-12-10")
+    assert df.shape[0] == steps and df.columns.names == list(results.LEVELS)
+    b = ids.index(5)
+    np.testing.assert_array_equal(df[("dewh", 5, "mpc_ce", "x_k1", 0)].to_numpy(), lg["T"][1:, b])
+    np.testing.assert_array_equal(df[("dewh", 5, "thermo", "u", 0)].to_numpy(), logs["thermo"]["u"].cpu().numpy()[:, b])
+    imp, exp = df[("grid", 1, "mpc_ce", "p_imp", 0)].to_numpy(), df[("grid", 1, "mpc_ce", "p_exp", 0)].to_numpy()
+    np.testing.assert_allclose(imp + exp, grid["y"], rtol=1e-13)
+    assert (imp >= 0).all() and (exp <= 0).all()
+    np.testing.assert_allclose(df[("grid", 1, "mpc_ce", "cost", 0)].to_numpy(), imp * price[:steps], rtol=1e-13)
+    assert (lg["solve_ms"] > 0).all()
