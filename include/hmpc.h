@@ -217,6 +217,54 @@ int hmpc_dewh_thermostat_f64(int32_t B, const double* params, const double* band
 int hmpc_aggregate_power_f64(int32_t B, int32_t Nt, const double* u, int64_t u_stride_b, int32_t u_stride_k,
                              const double* P_nom, double* partial, double* P_agg, void* stream);
 
+/* ---- price coordination for the CENTRALISED micro-grid problem: replaces GridAgentMpc.build_grid / solve_grid_mpc
+ *      (micro_grid_agents.py:691-735), where one MILP holds every device and the price sits on the grid import
+ *      z_k = max(0, y_k), y_k = sum_i P_i u_i,k + other_k (grid MLD, micro_grid_models.py:145-168; q_z,
+ *      micro_grid_control_simulation.py:228-229).  Lagrangian relaxation of a_k = sum_i P_i u_i,k: one iteration =
+ *      price_cost -> the batched agent solve (hmpc_stage_dp_solve_f64 / hmpc_milp_solve_f64) -> sums -> [all-reduce of
+ *      sums across ranks] -> dual_step -> keep_best; nothing returns to the host in between.
+ *  price_cost: cost_v[b, k*nv + col] = lambda[k] * P_nom[b].
+ *  sums [Nt+2] = {P_agg[0..Nt), sum_b obj[b], number of agents with status != 0} (status may be NULL).
+ *  dual_step: state [8] = {best lower bound, best upper bound, this iterate's dual value, this iterate's primal cost,
+ *      1.0 if the upper bound improved, iterations, |subgradient|^2, iterations skipped because an agent failed};
+ *      initialise to {-inf, +inf, 0, 0, 0, 0, 0, 0}.  a_lo / a_hi [Nt] bound the aggregate (0 and sum_i P_i, tightened
+ *      by the grid limits P_g_min - other_k, P_g_max - other_k); a plan outside them has no upper bound.
+ *      lambda_next = clip(lambda + theta (UB - dual) / |g|^2 * g, 0, price); must not alias lambda.
+ *  keep_best: if the upper bound improved, u_best [B,Nt] <- u and lambda_best [Nt] <- lambda (may be NULL).          */
+int hmpc_coupling_price_cost_f64(int32_t B, int32_t Nt, int32_t nv, int32_t col, const double* lambda,
+                                 const double* P_nom, double* cost_v, int64_t cost_stride_b, void* stream);
+int hmpc_coupling_sums_f64(int32_t B, int32_t Nt, const double* u, int64_t u_stride_b, int32_t u_stride_k,
+                           const double* P_nom, const double* obj, const int32_t* status, double* sums, void* stream);
+int hmpc_coupling_dual_step_f64(int32_t Nt, const double* sums, const double* p_other, const double* price,
+                                const double* a_lo, const double* a_hi, double theta, const double* lambda,
+                                double* lambda_next, double* state, void* stream);
+int hmpc_coupling_keep_best_f64(int32_t B, int32_t Nt, const double* u, int64_t u_stride_b, int32_t u_stride_k,
+                                const double* lambda, const double* state, double* u_best, double* lambda_best,
+                                void* stream);
+
+/* best-response descent on the true centralised cost, started from the plan of the price coordination: the agents of
+ * a block [lo, hi) answer their own marginal price with the others fixed,
+ *      c_bk = price_k [ max(0, A_k - P_b u_bk + P_b + other_k) - max(0, A_k - P_b u_bk + other_k) ],
+ * and the block's new plans are kept only if the total (import cost + every agent's penalty) went down, so the
+ * upper bound never gets worse.  One block step = response_cost -> the agent solve on rows [lo, hi) -> merge -> sums
+ * (obj = pen_cur, status NULL) -> accept -> restore.
+ *  response_cost: agg [Nt] = the current aggregate (sums_cur); v_cur / cost_v [B, Nt*nv] with row stride stride_b.
+ *  merge: v_new [hi-lo, Nt*nv], obj_new / status_new [hi-lo] from the solve; rows [lo, hi) of v_cur / pen_cur are saved
+ *      to v_bak / pen_bak and replaced (penalty = objective - energy part; +inf for a failed agent).
+ *  accept: br_state [4] = {total cost of the kept plan, 1.0 if the candidate was accepted, accepted, rejected};
+ *      initialise to {+inf, 0, 0, 0} and merge the whole fleet once to load the starting plan.
+ *  restore: puts rows [lo, hi) back if the candidate was rejected.                                               */
+int hmpc_coupling_response_cost_f64(int32_t B, int32_t Nt, int32_t nv, int32_t col, const double* agg,
+                                    const double* v_cur, const double* P_nom, const double* p_other,
+                                    const double* price, double* cost_v, int64_t stride_b, void* stream);
+int hmpc_coupling_merge_f64(int32_t lo, int32_t hi, int32_t Nt, int32_t nv, int32_t col, const double* v_new,
+                            const double* obj_new, const int32_t* status_new, const double* cost_v, int64_t stride_b,
+                            double* v_cur, double* pen_cur, double* v_bak, double* pen_bak, void* stream);
+int hmpc_coupling_accept_f64(int32_t Nt, const double* sums_cand, const double* p_other, const double* price,
+                             const double* a_lo, const double* a_hi, double* sums_cur, double* br_state, void* stream);
+int hmpc_coupling_restore_f64(int32_t lo, int32_t hi, int32_t nvt, const double* br_state, const double* v_bak,
+                              const double* pen_bak, double* v_cur, int64_t stride_b, double* pen_cur, void* stream);
+
 /* ---- host-buffer front door: one whole control step for a batch (what a ctypes/cgo/JNI caller binds).
  *      Replaces, for every agent of the batch, MpcController.build() + solve()
  *      (controllers/mpc_controller.py:76-101, controllers/controller_base.py:491-540) with Linear cost atoms.

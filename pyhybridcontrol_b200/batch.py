@@ -234,9 +234,11 @@ class BatchMpc(object):
         return terms, fold.reshape(B, -1)
 
     def solve(self, x0, omega, cost_v=None, w_x=None, w_y=None, scenarios=None, extra_constraints=(),
-              with_std_constraints=True, quad=None):
+              with_std_constraints=True, quad=None, rhs=None):
         """One control step for the whole batch.  Returns dict(v, obj, status, stats, c0) of device tensors.
-        ``quad``: convex quadratic / L1 weights (see _stage_terms) -- an MIQP, stage-DP path only."""
+        ``quad``: convex quadratic / L1 weights (see _stage_terms) -- an MIQP, stage-DP path only.
+        ``rhs``: the folded right-hand side a previous call returned (same x0, omega and constraint sets, new
+        cost) -- stage-DP path only; skips K2."""
         if self.evo is None:
             raise RuntimeError("build() must be called before solve()")
         d = self.dims
@@ -252,6 +254,13 @@ class BatchMpc(object):
         else:
             c, c0 = self.linear_cost(cost_v, w_x, w_y, x0, omega)
         Hs, rs = [], []
+        use_dp = self.solver == "stage_dp" or (self.solver == "auto" and self.stage_dp_ok)
+        if rhs is not None:
+            if not use_dp or quad:
+                raise NotImplementedError("a cached right-hand side is taken on the stage-DP MILP path only")
+            lb, ub, isb = self._bounds_dev()
+            v, obj, status, stats = cabi.stage_dp_solve(d, self.mats, rhs, c.contiguous(), lb, ub, isb, self.dp_opts)
+            return dict(v=v, obj=obj + c0, status=status, stats=stats, c0=c0, solver="stage_dp", rhs=rhs)
         if d.nc and with_std_constraints:
             H, r = self.constraint_rows(x0, omega, scenarios=scenarios)
             Hs.append(H)
@@ -265,7 +274,6 @@ class BatchMpc(object):
             Hs.append(H)
             rs.append(r)
         lb, ub, isb = self._bounds_dev()
-        use_dp = self.solver == "stage_dp" or (self.solver == "auto" and self.stage_dp_ok)
         terms = None
         if quad:
             if not (use_dp and rs):
@@ -283,7 +291,7 @@ class BatchMpc(object):
                 rhs = rs[0]
             v, obj, status, stats = cabi.stage_dp_solve(d, self.mats, rhs, c.contiguous(), lb, ub, isb, self.dp_opts,
                                                         terms=terms)
-            return dict(v=v, obj=obj + c0, status=status, stats=stats, c0=c0, solver="stage_dp")
+            return dict(v=v, obj=obj + c0, status=status, stats=stats, c0=c0, solver="stage_dp", rhs=rhs)
         if len(Hs) == 1 and Hs[0].shape[1] == self.mrows:
             H, rhs = self.evo["H_v"], rs[0]
         elif Hs:

@@ -22,7 +22,9 @@ EXPORTS = ("hmpc_version", "hmpc_last_cuda_error", "hmpc_device_info", "hmpc_con
            "hmpc_milp_default_opts", "hmpc_milp_workspace_bytes", "hmpc_milp_solve_f64", "hmpc_stage_dp_default_opts",
            "hmpc_stage_dp_supported", "hmpc_stage_dp_workspace_bytes", "hmpc_stage_dp_solve_f64", "hmpc_lsim_step_f64",
            "hmpc_dewh_sim_step_f64", "hmpc_dewh_control_model_f64", "hmpc_dewh_thermostat_f64",
-           "hmpc_aggregate_power_f64", "hmpc_step_plan_create", "hmpc_step_plan_destroy", "hmpc_mpc_step_host_f64", "hmpc_mpc_step_host_bytes",
+           "hmpc_aggregate_power_f64", "hmpc_coupling_price_cost_f64", "hmpc_coupling_sums_f64",
+           "hmpc_coupling_dual_step_f64", "hmpc_coupling_keep_best_f64", "hmpc_coupling_response_cost_f64",
+           "hmpc_coupling_merge_f64", "hmpc_coupling_accept_f64", "hmpc_coupling_restore_f64", "hmpc_step_plan_create", "hmpc_step_plan_destroy", "hmpc_mpc_step_host_f64", "hmpc_mpc_step_host_bytes",
            "hmpc_step_plan_last_solver",
            "hmpc_fp64_peak_probe")
 
@@ -98,6 +100,14 @@ _lib.hmpc_dewh_sim_step_f64.argtypes = [C.c_int32] + [_P] * 8
 _lib.hmpc_dewh_control_model_f64.argtypes = [C.c_int32, _P, _P, _P]
 _lib.hmpc_dewh_thermostat_f64.argtypes = [C.c_int32, _P, _P, C.c_int64, _P, _P, _P, _P]
 _lib.hmpc_aggregate_power_f64.argtypes = [C.c_int32, C.c_int32, _P, C.c_int64, C.c_int32, _P, _P, _P, _P]
+_lib.hmpc_coupling_price_cost_f64.argtypes = [C.c_int32] * 4 + [_P, _P, _P, C.c_int64, _P]
+_lib.hmpc_coupling_sums_f64.argtypes = [C.c_int32, C.c_int32, _P, C.c_int64, C.c_int32, _P, _P, _P, _P, _P]
+_lib.hmpc_coupling_dual_step_f64.argtypes = [C.c_int32, _P, _P, _P, _P, _P, C.c_double, _P, _P, _P, _P]
+_lib.hmpc_coupling_keep_best_f64.argtypes = [C.c_int32, C.c_int32, _P, C.c_int64, C.c_int32, _P, _P, _P, _P, _P]
+_lib.hmpc_coupling_response_cost_f64.argtypes = [C.c_int32] * 4 + [_P] * 6 + [C.c_int64, _P]
+_lib.hmpc_coupling_merge_f64.argtypes = [C.c_int32] * 5 + [_P] * 4 + [C.c_int64] + [_P] * 5
+_lib.hmpc_coupling_accept_f64.argtypes = [C.c_int32] + [_P] * 8
+_lib.hmpc_coupling_restore_f64.argtypes = [C.c_int32] * 3 + [_P] * 4 + [C.c_int64, _P, _P]
 _lib.hmpc_step_plan_create.argtypes = [C.POINTER(Dims), C.POINTER(MilpOpts), C.POINTER(_P)]
 _lib.hmpc_step_plan_destroy.argtypes = [_P]
 _lib.hmpc_mpc_step_host_f64.argtypes = [_P, C.c_int32, _MatArr, _StrideArr, _P, _P, _P, C.c_int64, _P, _P, _P,
@@ -422,6 +432,85 @@ def dewh_control_model(params):
     _check(_lib.hmpc_dewh_control_model_f64(B, _ptr(params), _ptr(model), _stream()), "hmpc_dewh_control_model_f64")
     launch_count += 1
     return model
+
+
+COUPLING_STATE = ("lower_bound", "upper_bound", "dual", "primal", "improved", "iterations", "gnorm2", "skipped")
+
+
+def coupling_state(device):
+    """fresh state vector of the price coordination (hmpc.h: hmpc_coupling_dual_step_f64)"""
+    return torch.tensor([-float("inf"), float("inf"), 0, 0, 0, 0, 0, 0], dtype=torch.float64, device=device)
+
+
+def coupling_price_cost(lam, P_nom, cost_v, nv, col=0):
+    """cost_v [B, Nt*nv] <- lambda_k * P_nom_b in column `col` of every step (in place)."""
+    global launch_count
+    B, Nt = cost_v.shape[0], lam.shape[0]
+    _check(_lib.hmpc_coupling_price_cost_f64(B, Nt, nv, col, _ptr(lam), _ptr(P_nom), _ptr(cost_v), cost_v.stride(0),
+                                             _stream()), "hmpc_coupling_price_cost_f64")
+    launch_count += 1
+
+
+def coupling_sums(u, P_nom, obj, status, sums):
+    """sums [Nt+2] <- {sum_b P_nom[b] u[b,k], sum_b obj[b], #(status != 0)}; u [B, Nt] with any strides."""
+    global launch_count
+    B, Nt = u.shape
+    _check(_lib.hmpc_coupling_sums_f64(B, Nt, C.c_void_p(u.data_ptr()), u.stride(0), u.stride(1), _ptr(P_nom), _ptr(obj),
+                                       _ptr(status), _ptr(sums), _stream()), "hmpc_coupling_sums_f64")
+    launch_count += 1
+
+
+def coupling_dual_step(sums, p_other, price, a_lo, a_hi, theta, lam, lam_next, state):
+    global launch_count
+    _check(_lib.hmpc_coupling_dual_step_f64(lam.shape[0], _ptr(sums), _ptr(p_other), _ptr(price), _ptr(a_lo), _ptr(a_hi),
+                                            float(theta), _ptr(lam), _ptr(lam_next), _ptr(state), _stream()),
+           "hmpc_coupling_dual_step_f64")
+    launch_count += 1
+
+
+def coupling_keep_best(u, lam, state, u_best, lam_best):
+    global launch_count
+    B, Nt = u.shape
+    _check(_lib.hmpc_coupling_keep_best_f64(B, Nt, C.c_void_p(u.data_ptr()), u.stride(0), u.stride(1), _ptr(lam),
+                                            _ptr(state), _ptr(u_best), _ptr(lam_best), _stream()),
+           "hmpc_coupling_keep_best_f64")
+    launch_count += 1
+
+
+def coupling_response_cost(agg, v_cur, P_nom, p_other, price, cost_v, nv, col=0):
+    """cost_v[b, k*nv+col] <- agent b's marginal import price at step k with the others fixed (in place)."""
+    global launch_count
+    B, Nt = v_cur.shape[0], price.shape[0]
+    assert v_cur.stride(0) == cost_v.stride(0)
+    _check(_lib.hmpc_coupling_response_cost_f64(B, Nt, nv, col, _ptr(agg), _ptr(v_cur), _ptr(P_nom), _ptr(p_other),
+                                                _ptr(price), _ptr(cost_v), cost_v.stride(0), _stream()),
+           "hmpc_coupling_response_cost_f64")
+    launch_count += 1
+
+
+def coupling_merge(lo, hi, Nt, nv, v_new, obj_new, status_new, cost_v, v_cur, pen_cur, v_bak, pen_bak, col=0):
+    global launch_count
+    assert v_cur.stride(0) == cost_v.stride(0)
+    _check(_lib.hmpc_coupling_merge_f64(lo, hi, Nt, nv, col, _ptr(v_new), _ptr(obj_new), _ptr(status_new), _ptr(cost_v),
+                                        cost_v.stride(0), _ptr(v_cur), _ptr(pen_cur), _ptr(v_bak), _ptr(pen_bak),
+                                        _stream()), "hmpc_coupling_merge_f64")
+    launch_count += 1
+
+
+def coupling_accept(sums_cand, p_other, price, a_lo, a_hi, sums_cur, br_state):
+    global launch_count
+    _check(_lib.hmpc_coupling_accept_f64(price.shape[0], _ptr(sums_cand), _ptr(p_other), _ptr(price), _ptr(a_lo),
+                                         _ptr(a_hi), _ptr(sums_cur), _ptr(br_state), _stream()),
+           "hmpc_coupling_accept_f64")
+    launch_count += 1
+
+
+def coupling_restore(lo, hi, br_state, v_bak, pen_bak, v_cur, pen_cur):
+    global launch_count
+    _check(_lib.hmpc_coupling_restore_f64(lo, hi, v_cur.shape[1], _ptr(br_state), _ptr(v_bak), _ptr(pen_bak),
+                                          _ptr(v_cur), v_cur.stride(0), _ptr(pen_cur), _stream()),
+           "hmpc_coupling_restore_f64")
+    launch_count += 1
 
 
 def aggregate_power(u, P_nom=None):

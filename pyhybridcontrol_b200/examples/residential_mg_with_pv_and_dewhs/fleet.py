@@ -62,9 +62,9 @@ class DewhFleet(object):
                             (self.soft_bot_mult * tot).expand(-1, self.Nt)], dim=2)
         return cost.reshape(self.B, 3 * self.Nt).contiguous()
 
-    def control_step(self, x0, omega_forecast, cost_v, extra_constraints=()):
+    def control_step(self, x0, omega_forecast, cost_v, extra_constraints=(), rhs=None):
         """-> dict(v, obj, status, stats, u [B, Nt] view)."""
-        res = self.batch.solve(x0, omega_forecast, cost_v=cost_v, extra_constraints=extra_constraints)
+        res = self.batch.solve(x0, omega_forecast, cost_v=cost_v, extra_constraints=extra_constraints, rhs=rhs)
         res["u"] = res["v"].view(self.B, self.Nt, 3)[:, :, 0]
         return res
 
@@ -76,6 +76,140 @@ class DewhFleet(object):
     def aggregate_power(self, u):
         """sum_b P_nom[b] u[b, k] over this rank's agents, then over ranks -> [Nt]."""
         return distributed.allreduce_aggregate(cabi.aggregate_power(u, self.P_nom))
+
+    def coupled_step(self, x0, omega_forecast, price, p_other, iters=300, theta=1.0, rel_gap=1e-2, check_every=25,
+                     grid_limits=None, extra_constraints=(), response_passes=12, response_groups=8, warm_iters=50):
+        """One control instant of the CENTRALISED micro-grid problem (micro_grid_agents.py:691-735: the price sits on
+        the grid import z_k = max(0, sum_i P_i u_i,k + p_other_k), q_z, and the devices only bring their slack
+        penalties) by price coordination: the batched exact agent solve at the internal price lambda, the aggregate,
+        one dual step -- repeated on the device until the certified gap (upper bound - lower bound) / |upper bound|
+        is below ``rel_gap`` (the reference accepts MIPGap = 1e-2, micro_grid_control_simulation.py:232) or ``iters``
+        is reached.  The state is read back every ``check_every`` iterations only.
+
+        price [Nt]; p_other [Nt] = PV + residential demand outputs (W, PV negative); grid_limits = (P_g_min, P_g_max)
+        bounds on y_k (micro_grid_models.py:145-150), None = not binding.  Across ranks the sums are all-reduced, so
+        every rank walks the same lambda.
+        The coordination's own plans are lumpy (agents with the same preferences flip together), so its best plan is
+        then improved by a best-response descent on the true cost (``response_passes`` passes over blocks of agents,
+        ``response_groups`` blocks at first; 0 passes = off): the upper bound only ever goes down.
+        -> dict(u [B, Nt] plan, plan (v, obj = every agent's penalty, status, stats), lam [Nt] best internal price,
+                lower_bound, upper_bound, dual_upper_bound (before the descent), gap, iterations, skipped,
+                response_solves, response_accepted)"""
+        dev, B, Nt = self.device, self.B, self.Nt
+        price = torch.as_tensor(price, dtype=torch.float64).to(dev).reshape(Nt).contiguous()
+        p_other = torch.as_tensor(p_other, dtype=torch.float64).to(dev).reshape(Nt).contiguous()
+        P_tot = distributed.allreduce_aggregate(self.P_nom.sum().reshape(1).clone())
+        a_lo = torch.zeros(Nt, dtype=torch.float64, device=dev)
+        a_hi = P_tot.expand(Nt).contiguous()
+        if grid_limits is not None:
+            a_lo = torch.maximum(a_lo, float(grid_limits[0]) - p_other)
+            a_hi = torch.minimum(a_hi, float(grid_limits[1]) - p_other)
+        cost = self.cost_from_prices(price)                      # slack penalties as in the decentralised problem
+        lam = [price.clone(), torch.empty_like(price)]
+        state, sums = cabi.coupling_state(dev), torch.empty(Nt + 2, dtype=torch.float64, device=dev)
+        u_best = torch.zeros((B, Nt), dtype=torch.float64, device=dev)
+        lam_best = price.clone()
+        x0 = torch.as_tensor(x0, dtype=torch.float64).to(dev).reshape(B, 1)
+        st, rhs, it = None, None, 0
+        out = dict(response_solves=0, response_accepted=0)
+        best_total, best_plan = float("inf"), None
+
+        def dual_iterations(n):
+            nonlocal st, rhs, it
+            for _ in range(n):
+                cur, nxt = lam[it & 1], lam[1 - (it & 1)]
+                cabi.coupling_price_cost(cur, self.P_nom, cost, 3, 0)
+                res = self.control_step(x0, omega_forecast, cost, extra_constraints=extra_constraints, rhs=rhs)
+                rhs = res.get("rhs")
+                cabi.coupling_sums(res["u"], self.P_nom, res["obj"].contiguous(), res["status"], sums)
+                distributed.allreduce_aggregate(sums)
+                cabi.coupling_dual_step(sums, p_other, price, a_lo, a_hi, theta, cur, nxt, state)
+                cabi.coupling_keep_best(res["u"], cur, state, u_best, lam_best)
+                it += 1
+                if it % int(check_every) == 0:
+                    st = state.cpu().numpy()
+                    if np.isfinite(st[1]) and st[1] - st[0] <= rel_gap * abs(st[1]):
+                        break
+            st = state.cpu().numpy()
+
+        def plan_at_best_price():
+            cabi.coupling_price_cost(lam_best, self.P_nom, cost, 3, 0)
+            return self.control_step(x0, omega_forecast, cost, extra_constraints=extra_constraints, rhs=rhs)
+
+        # phase 1: a first stretch of dual iterations; phase 2: descent from its plan; phase 3: the dual iterations go
+        # on with the better upper bound in Polyak's step length until the gap closes
+        dual_iterations(min(int(iters), int(warm_iters)) if response_passes else int(iters))
+        dual_ub = float(st[1])
+        plan = plan_at_best_price()
+        if response_passes and plan.get("rhs") is not None:
+            br = self._best_response(plan, cost, price, p_other, a_lo, a_hi, response_passes, response_groups)
+            out.update(response_solves=br["solves"], response_accepted=br["accepted"])
+            best_total = br["total"]
+            best_plan = dict(v=br["v"], u=br["v"].view(B, Nt, 3)[:, :, 0], obj=br["pen"], status=plan["status"],
+                             stats=plan["stats"])
+            state[1].clamp_(max=best_total)
+            st = state.cpu().numpy()
+            if not (st[1] - st[0] <= rel_gap * abs(st[1])):
+                dual_iterations(int(iters) - it)
+        if best_plan is None or st[1] < best_total:          # the dual iterates found something better still
+            best_plan = plan_at_best_price()
+            best_plan["u"] = u_best                          # identical to the plan's own u (deterministic solve)
+            best_total = float(st[1])
+        ub = best_total
+        out.update(lam=lam_best, lower_bound=float(st[0]), upper_bound=ub, dual_upper_bound=dual_ub,
+                   gap=float((ub - st[0]) / abs(ub)) if np.isfinite(ub) and ub != 0 else float("inf"),
+                   iterations=int(st[5]), skipped=int(st[7]), u=best_plan["u"], plan=best_plan)
+        return out
+
+    def _best_response(self, plan, cost, price, p_other, a_lo, a_hi, passes, groups):
+        """Descent on the true centralised cost from the coordination's plan (hmpc.h: hmpc_coupling_response_cost_f64
+        ..): blocks of agents answer their marginal price in turn, a block's answer is kept only if the total went
+        down.  The block count doubles (up to one agent per block) whenever a whole pass brings nothing."""
+        dev, B, Nt = self.device, self.B, self.Nt
+        batch, d = self.batch, self.batch.dims
+        lb, ub, isb = batch._bounds_dev()
+        rhs = plan["rhs"]
+        v_cur = torch.zeros((B, 3 * Nt), dtype=torch.float64, device=dev)
+        pen_cur = torch.zeros(B, dtype=torch.float64, device=dev)
+        v_bak, pen_bak = torch.empty_like(v_cur), torch.empty_like(pen_cur)
+        sums_cur = torch.zeros(Nt + 2, dtype=torch.float64, device=dev)
+        sums_cand = torch.empty_like(sums_cur)
+        brs = torch.tensor([float("inf"), 0, 0, 0], dtype=torch.float64, device=dev)
+
+        def evaluate(lo, hi):
+            cabi.coupling_sums(v_cur.view(B, Nt, 3)[:, :, 0], self.P_nom, pen_cur, None, sums_cand)
+            distributed.allreduce_aggregate(sums_cand)
+            cabi.coupling_accept(sums_cand, p_other, price, a_lo, a_hi, sums_cur, brs)
+            cabi.coupling_restore(lo, hi, brs, v_bak, pen_bak, v_cur, pen_cur)
+
+        # load the starting plan: the whole fleet is one block, accepted against +inf
+        cabi.coupling_merge(0, B, Nt, 3, plan["v"], plan["obj"].contiguous(), plan["status"], cost, v_cur, pen_cur, v_bak,
+                            pen_bak)
+        evaluate(0, B)
+        G = max(1, min(int(groups), B))
+        solves, last = 0, float(brs[0].cpu())
+        for _ in range(int(passes)):
+            for g in range(G):
+                lo, hi = distributed.shard_range(B, g, G)
+                if hi == lo:
+                    continue
+                cabi.coupling_response_cost(sums_cur, v_cur, self.P_nom, p_other, price, cost, 3, 0)
+                sub = cabi.make_dims(hi - lo, d.Nt, nx=d.nx, nu=d.nu, ndelta=d.ndelta, nz=d.nz, nmu=d.nmu,
+                                     nomega=d.nomega, ny=d.ny, nc=d.nc)
+                mats = {k: (m[lo:hi] if m.shape[0] == B and B > 1 else m) for k, m in batch.mats.items()}
+                v_new, obj_new, status_new, _ = cabi.stage_dp_solve(sub, mats, rhs[lo:hi], cost[lo:hi], lb, ub, isb,
+                                                                    batch.dp_opts)
+                solves += 1
+                cabi.coupling_merge(lo, hi, Nt, 3, v_new, obj_new, status_new, cost, v_cur, pen_cur, v_bak, pen_bak)
+                evaluate(lo, hi)
+            now = float(brs[0].cpu())                                    # one read-back per pass
+            if not now < last:
+                if G >= B:
+                    break
+                G = min(B, 2 * G)
+            last = now
+        st = brs.cpu().numpy()
+        return dict(v=v_cur, pen=pen_cur, total=float(st[0]), solves=solves, accepted=int(st[2]) - 1)
 
     CONTROLLERS = ("mpc_pb", "mpc_ce", "mpc_sb_reduced", "mpc_sb_full", "mpc_minmax", "thermo")
 
