@@ -57,6 +57,26 @@ __device__ inline double block_sum_128(double v, double* red) {
     return out;
 }
 
+// Grid side of the dual at one step: value of  min over a in [lo, hi] of  pr max(0, a + r) - lam a  and the component
+// of the projected subgradient.  The minimiser is the kink a = -r for 0 < lam < pr, but a whole interval when lam sits
+// on a bound of its box ([lo, kink] at lam = 0, [kink, hi] at lam = pr): the member closest to the agents' aggregate
+// is taken (minimum-norm subgradient), and a component that would push lam out of [0, pr] is dropped (projection).
+// Without this the free-energy hours, where lam = 0 and the agents use a fraction of the surplus, dominate |g|^2
+// and Polyak's step crawls.
+__device__ inline void grid_side(double a, double r, double pr, double lo, double hi, double lam, double& best,
+                                 double& g) {
+    const double kink = fmin(fmax(-r, lo), hi);
+    const double f_lo = pr * fmax(0.0, lo + r) - lam * lo, f_hi = pr * fmax(0.0, hi + r) - lam * hi,
+                 f_k = pr * fmax(0.0, kink + r) - lam * kink;
+    best = fmin(f_k, fmin(f_lo, f_hi));
+    double arg;
+    if (lam <= 0.0) arg = fmin(fmax(a, lo), kink);
+    else if (lam >= pr) arg = fmin(fmax(a, kink), hi);
+    else arg = kink;
+    g = a - arg;
+    if ((lam <= 0.0 && g < 0.0) || (lam >= pr && g > 0.0)) g = 0.0;
+}
+
 __global__ void __launch_bounds__(128) coupling_dual_step_kernel(int Nt, const double* __restrict__ sums,
                                                                  const double* __restrict__ p_other,
                                                                  const double* __restrict__ price,
@@ -74,15 +94,9 @@ __global__ void __launch_bounds__(128) coupling_dual_step_kernel(int Nt, const d
         lam_agg += lam * a;
         imp += pr * fmax(0.0, a + r);
         if (a < lo - 1e-9 * fmax(1.0, fabs(lo)) || a > hi + 1e-9 * fmax(1.0, fabs(hi))) infeasible += 1.0;
-        // grid side: piecewise-linear in a, minimum at an end point or at the kink a = -other
-        const double kink = fmin(fmax(-r, lo), hi);
-        const double f_lo = pr * fmax(0.0, lo + r) - lam * lo, f_hi = pr * fmax(0.0, hi + r) - lam * hi,
-                     f_k = pr * fmax(0.0, kink + r) - lam * kink;
-        double best = f_k, arg = kink;
-        if (f_lo < best) { best = f_lo; arg = lo; }
-        if (f_hi < best) { best = f_hi; arg = hi; }
+        double best, g;
+        grid_side(a, r, pr, lo, hi, lam, best, g);
         dual_agg += best;
-        const double g = a - arg;
         g2 += g * g;
     }
     lam_agg = block_sum_128(lam_agg, red);
@@ -114,14 +128,10 @@ __global__ void __launch_bounds__(128) coupling_dual_step_kernel(int Nt, const d
     const double alpha = s_alpha;
     for (int k = threadIdx.x; k < Nt; k += blockDim.x) {
         if (alpha > 0.0) {
-            const double a = sums[k], r = p_other[k], pr = price[k], lo = a_lo[k], hi = a_hi[k], lam = lambda[k];
-            const double kink = fmin(fmax(-r, lo), hi);
-            const double f_lo = pr * fmax(0.0, lo + r) - lam * lo, f_hi = pr * fmax(0.0, hi + r) - lam * hi,
-                         f_k = pr * fmax(0.0, kink + r) - lam * kink;
-            double best = f_k, arg = kink;
-            if (f_lo < best) { best = f_lo; arg = lo; }
-            if (f_hi < best) { best = f_hi; arg = hi; }
-            lambda_next[k] = fmin(fmax(lam + alpha * (a - arg), 0.0), pr);
+            const double pr = price[k], lam = lambda[k];
+            double best, g;
+            grid_side(sums[k], p_other[k], pr, a_lo[k], a_hi[k], lam, best, g);
+            lambda_next[k] = fmin(fmax(lam + alpha * g, 0.0), pr);
         } else {
             lambda_next[k] = lambda[k];
         }

@@ -141,7 +141,9 @@ class DewhFleet(object):
         dual_iterations(min(int(iters), int(warm_iters)) if response_passes else int(iters))
         dual_ub = float(st[1])
         plan = plan_at_best_price()
-        if response_passes and plan.get("rhs") is not None:
+        closed = np.isfinite(st[1]) and st[1] - st[0] <= rel_gap * abs(st[1])
+        ran_more = False
+        if response_passes and plan.get("rhs") is not None and not closed:
             br = self._best_response(plan, cost, price, p_other, a_lo, a_hi, response_passes, response_groups)
             out.update(response_solves=br["solves"], response_accepted=br["accepted"])
             best_total = br["total"]
@@ -151,8 +153,12 @@ class DewhFleet(object):
             st = state.cpu().numpy()
             if not (st[1] - st[0] <= rel_gap * abs(st[1])):
                 dual_iterations(int(iters) - it)
+                ran_more = True
+        elif not closed and it < int(iters):
+            dual_iterations(int(iters) - it)
+            ran_more = True
         if best_plan is None or st[1] < best_total:          # the dual iterates found something better still
-            best_plan = plan_at_best_price()
+            best_plan = plan_at_best_price() if ran_more else plan
             best_plan["u"] = u_best                          # identical to the plan's own u (deterministic solve)
             best_total = float(st[1])
         ub = best_total
@@ -241,7 +247,7 @@ class DewhFleet(object):
         return []
 
     def closed_loop(self, T0, demand, price, sim_steps, demand_actual=None, controller="mpc_ce", scenarios=None,
-                    N_sb_reduced=8, demand_minmax=None, u_init=None):
+                    N_sb_reduced=8, demand_minmax=None, u_init=None, coupling=None):
         """Closed-loop simulation of the shard (reference loop: examples/.../micro_grid_control_simulation.py:184-236
         with the per-device work of micro_grid_agents.py:699-700, 733-740): at every step k the forecast window
         demand[:, k:k+Nt] and price[k:k+Nt] give the MPC problem, the first control is applied to the re-parametrised
@@ -259,7 +265,10 @@ class DewhFleet(object):
         T0 [B] initial temperatures; demand [B, sim_steps + Nt] (L/s); price [sim_steps + Nt] or [B, sim_steps + Nt];
         demand_actual [B, >= sim_steps] defaults to demand; scenarios [B, sim_steps + Nt, S] or callable k -> [B, Nt, S];
         demand_minmax = (min, max) profiles [sim_steps + Nt] or [B, sim_steps + Nt]; u_init [B] input before step 0
-        (thermostat only).
+        (thermostat only).  coupling = dict(p_other [sim_steps + Nt] PV + residential-demand forecast in W, plus any
+        ``coupled_step`` option): the reference's centralised operation -- the price applies to the grid import, every
+        instant is solved by ``coupled_step`` (obj is then every agent's penalty part, and the log gains
+        coupled_upper_bound / coupled_gap [sim_steps]).
         -> dict(T [sim_steps + 1, B], u [sim_steps, B], obj [sim_steps, B], status [sim_steps, B],
                 P_agg [sim_steps, Nt], cons [sim_steps, B, 2], mu_hat [sim_steps, B, 2] (first-step slacks of the
                 plan), omega / omega_hat [sim_steps, B] (actual draw / first forecast value), solve_ms [sim_steps]
@@ -295,13 +304,25 @@ class DewhFleet(object):
             out["solve_ms"] = torch.zeros(sim_steps, dtype=torch.float64, device=dev)
             return out
         self.build()                                   # the control model does not change along the run
+        if coupling is not None:
+            if price.dim() != 1:
+                raise ValueError("the centralised problem has one import price per step")
+            copts = dict(coupling)
+            p_other = torch.as_tensor(copts.pop("p_other"), dtype=torch.float64).to(dev)
+            coupled = dict(ub=[], gap=[])
         for k in range(sim_steps):
             pk = price[k:k + Nt] if price.dim() == 1 else price[:, k:k + Nt]
             extra = self._extra_sets(controller, k, scenarios, demand_minmax, N_sb_reduced)
             events.append((torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)))
             events[-1][0].record()
-            res = self.control_step(T.reshape(B, 1), forecast[:, k:k + Nt].contiguous(), self.cost_from_prices(pk),
-                                    extra_constraints=extra)
+            if coupling is not None:
+                cs = self.coupled_step(T.reshape(B, 1), forecast[:, k:k + Nt].contiguous(), pk, p_other[k:k + Nt],
+                                       extra_constraints=extra, **copts)
+                res = cs["plan"]
+                coupled["ub"].append(cs["upper_bound"]); coupled["gap"].append(cs["gap"])
+            else:
+                res = self.control_step(T.reshape(B, 1), forecast[:, k:k + Nt].contiguous(), self.cost_from_prices(pk),
+                                        extra_constraints=extra)
             events[-1][1].record()
             u0 = res["u"][:, 0].contiguous()
             T, cons = self.sim_step(T, u0, actual[:, k].contiguous())
@@ -312,6 +333,9 @@ class DewhFleet(object):
         out = {k: torch.stack(v) for k, v in log.items()}
         torch.cuda.synchronize(dev)
         out["solve_ms"] = torch.tensor([a.elapsed_time(b) for a, b in events], dtype=torch.float64, device=dev)
+        if coupling is not None:
+            out["coupled_upper_bound"] = torch.tensor(coupled["ub"], dtype=torch.float64, device=dev)
+            out["coupled_gap"] = torch.tensor(coupled["gap"], dtype=torch.float64, device=dev)
         return out
 
     def grid_log(self, log, price, pv=None, resd=None, grid_params=None, device_ids=None):

@@ -127,6 +127,27 @@ def test_coupling_kernels_vs_numpy(cuda_device):
     assert st[4] == 1.0 and st[5] == 1.0 and st[7] == 0.0
     np.testing.assert_allclose(st[6], g @ g, rtol=1e-12)
     np.testing.assert_allclose(lam_next.cpu().numpy(), want, rtol=1e-10, atol=1e-18)
+    # multipliers on the bounds of their box: minimum-norm member of the subdifferential, projected
+    lam2 = lam.copy()
+    lam2[::3] = 0.0
+    lam2[1::3] = price[1::3]
+    state2 = cabi.coupling_state(dev)
+    lam_next2 = torch.empty(Nt, dtype=torch.float64, device=dev)
+    cabi.coupling_dual_step(t(s), t(r), t(price), t(lo), t(hi), 1.0, t(lam2), lam_next2, state2)
+    kink = np.clip(-r, lo, hi)
+    arg = np.where(lam2 <= 0, np.clip(agg, lo, kink), np.where(lam2 >= price, np.clip(agg, kink, hi), kink))
+    g2v = agg - arg
+    g2v[(lam2 <= 0) & (g2v < 0)] = 0.0
+    g2v[(lam2 >= price) & (g2v > 0)] = 0.0
+    cand2 = np.stack([kink, lo, hi])
+    dual2 = s[Nt] + (price * np.maximum(0, cand2 + r) - lam2 * cand2).min(0).sum()
+    primal2 = (price * np.maximum(0, agg + r)).sum() + s[Nt] - lam2 @ agg
+    st2 = state2.cpu().numpy()
+    np.testing.assert_allclose(st2[2:4], [dual2, primal2], rtol=1e-12)
+    np.testing.assert_allclose(st2[6], g2v @ g2v, rtol=1e-12)
+    np.testing.assert_allclose(lam_next2.cpu().numpy(), np.clip(lam2 + (primal2 - dual2) / (g2v @ g2v) * g2v, 0, price),
+                               rtol=1e-10, atol=1e-18)
+    assert (g2v == 0).sum() > 0
     # keep_best copies only when the bound improved
     u_best, lam_best = torch.zeros((B, Nt), dtype=torch.float64, device=dev), torch.zeros(Nt, dtype=torch.float64, device=dev)
     cabi.coupling_keep_best(vd.view(B, Nt, nv)[:, :, 0], t(lam), state, u_best, lam_best)
@@ -222,3 +243,27 @@ def test_best_response_kernels_vs_numpy(cuda_device):
     cabi.coupling_merge(lo, hi, Nt, nv, t(v_new.reshape(hi - lo, -1)), t(obj_new), t(status, torch.int32), cost, v_cur,
                         pen_cur, v_bak, pen_bak)
     assert np.isinf(pen_cur.cpu().numpy()[lo + 3])
+
+
+def test_closed_loop_with_coordination(cuda_device):
+    """a few closed-loop steps of the centralised operation: every instant certified, and the import bill of the
+    simulated day is lower than the one of the uncoordinated fleet (same tanks, same draws)."""
+    from pyhybridcontrol_b200.examples.residential_mg_with_pv_and_dewhs import synthetic as syn
+    from pyhybridcontrol_b200.examples.residential_mg_with_pv_and_dewhs.fleet import DewhFleet
+    N_h, N_p, steps = 24, 16, 8
+    Nt = N_p + 1
+    params = [syn.dewh_agent_params(700 + b) for b in range(N_h)]
+    T0 = np.array([syn.dewh_initial_state(700 + b) for b in range(N_h)])
+    dem = np.stack([syn.dhw_demand_profile(steps + Nt, seed=700 + b) for b in range(N_h)])
+    price = syn.price_profile(steps + Nt, seed=7)
+    P = np.array([p["P_h_Nom"] for p in params])
+    k = np.arange(steps + Nt)
+    p_other = -0.7 * P.sum() * np.clip(np.sin(k / 12 * np.pi), 0, None) + 0.05 * P.sum()
+    fleet = DewhFleet(params, N_p, device=cuda_device)
+    co = {key: v.cpu().numpy() for key, v in
+          fleet.closed_loop(T0, dem, price, steps, coupling=dict(p_other=p_other, iters=150)).items()}
+    de = {key: v.cpu().numpy() for key, v in fleet.closed_loop(T0, dem, price, steps).items()}
+    assert (co["status"] == 0).all() and (co["coupled_gap"] <= 0.05).all()
+    bill = lambda lg: float((price[:steps] * np.maximum(0, lg["P_agg"][:, 0] + p_other[:steps])).sum())
+    assert bill(co) <= bill(de) * (1 + 1e-12)
+    assert np.isfinite(co["T"]).all() and co["mu_hat"].shape == (steps, N_h, 2)
