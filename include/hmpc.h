@@ -211,6 +211,42 @@ int hmpc_dewh_control_model_f64(int32_t B, const double* params, double* model, 
 int hmpc_dewh_thermostat_f64(int32_t B, const double* params, const double* band, int64_t band_stride_b,
                              const double* T, const double* u_prev, double* u, void* stream);
 
+/* ---- symbolic / callable model front-end: replaces, for B parameter sets at once, the evaluation of every
+ *      non-constant system matrix of a callable MldModel -- CallableMatrix.__call__(param_struct=...)
+ *      (utils/matrix_utils.py:441-470) on the sympy.lambdify'd matrix functions (:339-343), as driven by
+ *      MldModel.to_numeric (models/mld_model.py:791-793) and MldSystemModel.get_mld_numeric / update_param_struct
+ *      (:1072-1081, :1128-1149).  The host compiles the expressions of all matrices into ONE straight-line register
+ *      program (pyhybridcontrol_b200/utils/matrix_utils.py); one thread per agent interprets it.
+ *  program   : DEVICE pointer, 16-byte aligned, n_ins instructions {op, dst, a, b}:
+ *                CONST  dst <- the double whose low / high 32 bits are a / b
+ *                PARAM  dst <- params[agent, a]
+ *                unary  dst <- f(reg a)            (POWI: reg a to the integer power b)
+ *                binary dst <- reg a (op) reg b
+ *                OUT    output slot dst <- reg a
+ *              + - * / are IEEE round-to-nearest and never contracted into an FMA (same rounding as the reference's
+ *              numpy evaluation); exp / log / pow / trig are CUDA's FP64 functions (<= 2 ulp).
+ *              A malformed program (register / slot / parameter index out of range, unknown opcode) makes the
+ *              affected outputs NaN; it never reads or writes out of bounds.
+ *  mat_sizes : HOST array, n_mats <= 20 entries = rows*cols of each evaluated matrix; output slots are numbered
+ *              matrix by matrix, row-major inside a matrix.
+ *  params    : [B, n_params] row-major.
+ *  out       : matrix m occupies out[B*off_m .. B*(off_m + size_m)) as [B, size_m] row-major (off_m = sum of the
+ *              sizes before it), i.e. each matrix is a contiguous [B, rows, cols] block, ready for the mats[] /
+ *              mat_stride_b[] arguments of the entry points above.  Slots no OUT writes stay NaN.
+ *  Limits: n_regs, n_ins and the sizes must fit one CTA's shared memory (16 n_ins + 8*33 (n_params + n_regs + n_out)
+ *  <= 227 KB), else HMPC_ERR_ARG -- split the program per matrix.                                         */
+typedef struct { int32_t op, dst, a, b; } hmpc_expr_ins;
+enum { HMPC_EXPR_CONST = 0, HMPC_EXPR_PARAM = 1, HMPC_EXPR_OUT = 2,
+       HMPC_EXPR_MOV = 10, HMPC_EXPR_NEG, HMPC_EXPR_ABS, HMPC_EXPR_SIGN, HMPC_EXPR_SQRT, HMPC_EXPR_EXP,
+       HMPC_EXPR_LOG, HMPC_EXPR_SIN, HMPC_EXPR_COS, HMPC_EXPR_TAN, HMPC_EXPR_ASIN, HMPC_EXPR_ACOS, HMPC_EXPR_ATAN,
+       HMPC_EXPR_SINH, HMPC_EXPR_COSH, HMPC_EXPR_TANH, HMPC_EXPR_FLOOR, HMPC_EXPR_CEIL, HMPC_EXPR_POWI,
+       HMPC_EXPR_ADD = 40, HMPC_EXPR_SUB, HMPC_EXPR_MUL, HMPC_EXPR_DIV, HMPC_EXPR_POW, HMPC_EXPR_MIN,
+       HMPC_EXPR_MAX, HMPC_EXPR_ATAN2 };
+int hmpc_param_eval_f64(int32_t B, int32_t n_params, int32_t n_regs, int32_t n_ins, const hmpc_expr_ins* program,
+                        int32_t n_mats, const int32_t* mat_sizes, const double* params, double* out, void* stream);
+/* algorithmic bytes per agent of the call above: 8 (n_params + sum of sizes) -- the kernel is HBM-bound */
+int64_t hmpc_param_eval_bytes_per_agent(int32_t n_params, int32_t n_mats, const int32_t* mat_sizes);
+
 /* ---- K6 aggregate power: replaces GridAgentMpc.get_grid_device_powers_N_tilde + GridModel D4 = ones
  *      (micro_grid_agents.py:625-646, micro_grid_models.py:143):  P_agg[k] = sum_b P_nom[b] * u[b,k].
  *  Deterministic two-pass tree; partial [ceil(B/16), Nt] scratch from the caller.                     */

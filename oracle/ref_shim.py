@@ -157,6 +157,30 @@ def load():
     return MldModel, MldEvoMatrices
 
 
+def load_symbolic():
+    """The reference's symbolic / callable front-end, unmodified: returns (MldModel, MldSystemModel, CallableMatrix,
+    example micro_grid_models module, example parameters module).
+
+    wrapt 2.x proxies make ``isinstance(x, CallableMatrix)`` raise inside abc (the class mixes ABCMeta with wrapt's
+    ObjectProxy); the instance / subclass checks of the reference's metaclass are replaced by plain MRO look-ups --
+    an environment alias like the others here, no arithmetic is touched.  Must be called in a process that has NOT
+    called ``load()`` (which swaps CallableMatrix for a placeholder to keep the numeric-only path simple)."""
+    install()
+    import importlib
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        import utils.matrix_utils as rmu  # noqa: reference module
+        rmu.CallableMatrixMeta.__instancecheck__ = lambda cls, inst: cls in type(inst).__mro__
+        rmu.CallableMatrixMeta.__subclasscheck__ = lambda cls, sub: isinstance(sub, type) and cls in sub.__mro__
+        import models.mld_model as mm  # noqa: reference module
+        if getattr(mm, "_hmpc_numeric_only", False):
+            raise RuntimeError("load() already replaced the reference's CallableMatrix in this process")
+        models = importlib.import_module("examples.residential_mg_with_pv_and_dewhs.modelling.micro_grid_models")
+        params = importlib.import_module("examples.residential_mg_with_pv_and_dewhs.modelling.parameters")
+    return mm.MldModel, mm.MldSystemModel, rmu.CallableMatrix, models, params
+
+
 EVO_NAMES = ("Phi_x", "Gamma_v", "Gamma_omega", "Gamma_5",
              "L_x", "L_v", "L_omega", "L_5",
              "H_x", "H_v", "H_omega", "H_5")

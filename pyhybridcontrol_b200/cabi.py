@@ -22,6 +22,7 @@ EXPORTS = ("hmpc_version", "hmpc_last_cuda_error", "hmpc_device_info", "hmpc_con
            "hmpc_milp_default_opts", "hmpc_milp_workspace_bytes", "hmpc_milp_solve_f64", "hmpc_stage_dp_default_opts",
            "hmpc_stage_dp_supported", "hmpc_stage_dp_workspace_bytes", "hmpc_stage_dp_solve_f64", "hmpc_lsim_step_f64",
            "hmpc_dewh_sim_step_f64", "hmpc_dewh_control_model_f64", "hmpc_dewh_thermostat_f64",
+           "hmpc_param_eval_f64", "hmpc_param_eval_bytes_per_agent",
            "hmpc_aggregate_power_f64", "hmpc_coupling_price_cost_f64", "hmpc_coupling_sums_f64",
            "hmpc_coupling_dual_step_f64", "hmpc_coupling_keep_best_f64", "hmpc_coupling_response_cost_f64",
            "hmpc_coupling_merge_f64", "hmpc_coupling_accept_f64", "hmpc_coupling_restore_f64", "hmpc_step_plan_create", "hmpc_step_plan_destroy", "hmpc_mpc_step_host_f64", "hmpc_mpc_step_host_bytes",
@@ -99,6 +100,9 @@ _lib.hmpc_lsim_step_f64.argtypes = [C.POINTER(Dims), _MatArr, _StrideArr] + [_P]
 _lib.hmpc_dewh_sim_step_f64.argtypes = [C.c_int32] + [_P] * 8
 _lib.hmpc_dewh_control_model_f64.argtypes = [C.c_int32, _P, _P, _P]
 _lib.hmpc_dewh_thermostat_f64.argtypes = [C.c_int32, _P, _P, C.c_int64, _P, _P, _P, _P]
+_lib.hmpc_param_eval_f64.argtypes = [C.c_int32] * 4 + [_P, C.c_int32, C.POINTER(C.c_int32), _P, _P, _P]
+_lib.hmpc_param_eval_bytes_per_agent.argtypes = [C.c_int32, C.c_int32, C.POINTER(C.c_int32)]
+_lib.hmpc_param_eval_bytes_per_agent.restype = C.c_int64
 _lib.hmpc_aggregate_power_f64.argtypes = [C.c_int32, C.c_int32, _P, C.c_int64, C.c_int32, _P, _P, _P, _P]
 _lib.hmpc_coupling_price_cost_f64.argtypes = [C.c_int32] * 4 + [_P, _P, _P, C.c_int64, _P]
 _lib.hmpc_coupling_sums_f64.argtypes = [C.c_int32, C.c_int32, _P, C.c_int64, C.c_int32, _P, _P, _P, _P, _P]
@@ -432,6 +436,33 @@ def dewh_control_model(params):
     _check(_lib.hmpc_dewh_control_model_f64(B, _ptr(params), _ptr(model), _stream()), "hmpc_dewh_control_model_f64")
     launch_count += 1
     return model
+
+
+def param_eval(program, n_regs, mat_sizes, params, out=None):
+    """Symbolic / callable model front-end (hmpc.h: hmpc_param_eval_f64).  program: CUDA int32 tensor [n_ins, 4];
+    params: CUDA float64 [B, P]; returns the flat output buffer, matrix m at [B*off_m, B*(off_m+size_m)) as
+    [B, size_m]."""
+    global launch_count
+    if program.dtype != torch.int32 or program.dim() != 2 or program.shape[1] != 4:
+        raise ValueError("program must be an int32 tensor [n_ins, 4]")
+    if params.dtype != torch.float64 or params.dim() != 2:
+        raise ValueError("params must be a float64 tensor [B, P]")
+    B, P = params.shape
+    sizes = (C.c_int32 * len(mat_sizes))(*[int(s) for s in mat_sizes])
+    n_out = int(sum(mat_sizes))
+    if out is None:
+        out = torch.empty((B * n_out,), dtype=torch.float64, device=params.device)
+    elif out.numel() != B * n_out or out.dtype != torch.float64:
+        raise ValueError("out must hold B * sum(mat_sizes) doubles")
+    _check(_lib.hmpc_param_eval_f64(B, P, int(n_regs), program.shape[0], _ptr(program), len(mat_sizes), sizes,
+                                    _ptr(params) if P else None, _ptr(out), _stream()), "hmpc_param_eval_f64")
+    launch_count += 1
+    return out
+
+
+def param_eval_bytes_per_agent(n_params, mat_sizes):
+    sizes = (C.c_int32 * len(mat_sizes))(*[int(s) for s in mat_sizes])
+    return int(_lib.hmpc_param_eval_bytes_per_agent(int(n_params), len(mat_sizes), sizes))
 
 
 COUPLING_STATE = ("lower_bound", "upper_bound", "dual", "primal", "improved", "iterations", "gnorm2", "skipped")

@@ -32,8 +32,9 @@ def test_mld_model_errors_and_versioning():
         MldModel(E=[[1.0]], A=[[1.0]])           # constraint rows without f5
     with pytest.raises(ValueError):
         MldModel(A=[[1.0]], B1=[[1.0]], nu_l=2)
-    with pytest.raises(NotImplementedError):
-        MldModel(A=lambda: 1.0)
+    with pytest.raises(TypeError):
+        MldModel(A="not a matrix")
+    assert MldModel(A=lambda: 1.0).mld_type == "callable"      # functions are traced (tests/test_callable_front_end.py)
     m = MldModel(nu_l=1, **DEWH)
     v0 = m.version
     m.update(f5=[[80.0], [-50.0]])

@@ -1,0 +1,258 @@
+"""GPU: hmpc_param_eval_f64 (csrc/param_eval.cu) and the symbolic / callable model front-end built on it, against
+golden vectors of the UNMODIFIED reference's CallableMatrix / MldSystemModel (tests/golden/make_golden_callable.py),
+the lambdify oracle (oracle/callable.py) and the numpy twin of the interpreter.
+
+Tolerance: + - * / follow the reference's evaluation order and round identically; exp / log / pow / trig come from the
+CUDA math library (<= 2 ulp each) -> 1e-12 relative on expressions without cancellation; BASELINE.json's bar for
+matrices is 1e-10 relative."""
+import numpy as np
+import pytest
+import sympy as sp
+
+import expr_vm_twin as twin
+from test_callable_front_end import FIXTURES, MAT_NAMES, load_fixture
+
+pytestmark = pytest.mark.gpu
+
+
+def _close(got, ref, rtol, what=""):
+    scale = np.maximum(np.abs(ref), 1e-300)
+    bad = ~(np.isclose(got, ref, rtol=rtol, atol=0.0, equal_nan=True))
+    assert not bad.any(), "%s: worst relative error %.3e" % (what, float(np.max((np.abs(got - ref) / scale)[bad])))
+
+
+def _run(prog, params, dev):
+    import torch
+    out = prog.evaluate(torch.as_tensor(np.ascontiguousarray(params), dtype=torch.float64).to(dev))
+    torch.cuda.synchronize()
+    return {k: v.cpu().numpy() for k, v in out.items()}
+
+
+@pytest.mark.parametrize("fixture", FIXTURES)
+def test_kernel_vs_reference_golden(fixture, cuda_device):
+    from pyhybridcontrol_b200.utils.matrix_utils import ExprProgram
+    z, names, mats, pnames = load_fixture(fixture)
+    prog = ExprProgram(mats, param_names=pnames)
+    out = _run(prog, z["params"], cuda_device)
+    ref_twin = twin.run_program(prog, z["params"])
+    rtol = 1e-12 if fixture != "callable_all_ops.npz" else 1e-11     # all_ops subtracts transcendental terms
+    for k in names:
+        assert out[k].shape == z["out_" + k].shape
+        _close(out[k], z["out_" + k], rtol, "%s %s vs reference" % (fixture, k))
+        _close(out[k], ref_twin[k], rtol, "%s %s vs twin" % (fixture, k))
+    if fixture in ("callable_grid_3dev.npz", "callable_pv.npz", "callable_resd.npz"):
+        for k in names:                                    # only + - * : bit-exact
+            assert np.array_equal(out[k], z["out_" + k]), (fixture, k)
+
+
+@pytest.mark.parametrize("B", [1, 31, 32, 33, 100, 4741, 19000, 40001])
+def test_tiles_and_batch_sizes(B, cuda_device):
+    """every tile width (32 / 64 / 128 / 256 threads), partial last tiles, per-matrix [B, size] layout."""
+    from pyhybridcontrol_b200.utils.matrix_utils import ExprProgram
+    z, names, mats, pnames = load_fixture("callable_dewh_sim.npz")
+    prog = ExprProgram(mats, param_names=pnames)
+    rng = np.random.default_rng(B)
+    base = z["params"][0]
+    params = np.tile(base, (B, 1)) * (1.0 + 0.05 * rng.uniform(-1, 1, size=(B, len(pnames))))
+    params[:, pnames.index("T_h")] = rng.uniform(20, 85, B)
+    params[:, pnames.index("D_h")] = rng.uniform(0, 0.08, B)
+    out = _run(prog, params, cuda_device)
+    ref = twin.run_program(prog, params)
+    for k in names:
+        assert out[k].shape == ref[k].shape == (B,) + prog.mat_shapes[prog.mat_names.index(k)]
+        _close(out[k], ref[k], 1e-12, "B=%d %s" % (B, k))
+
+
+def test_random_programs_vs_twin(cuda_device):
+    """random expression trees over every instruction: kernel == numpy twin (NaN / inf patterns included)."""
+    from pyhybridcontrol_b200.utils.matrix_utils import ExprProgram
+    rng = np.random.default_rng(7)
+    syms = sp.symbols("p0:6")
+    unary = [sp.exp, sp.sin, sp.cos, sp.tanh, sp.atan, sp.Abs, sp.sign, sp.floor, sp.ceiling, sp.sinh, sp.cosh,
+             lambda x: sp.sqrt(sp.Abs(x)), lambda x: sp.log(1 + sp.Abs(x)), lambda x: sp.asin(sp.tanh(x)),
+             lambda x: sp.acos(sp.tanh(x)), lambda x: sp.tan(sp.atan(x) / 2)]
+    binary = [lambda x, y: x + y, lambda x, y: x - y, lambda x, y: x * y, lambda x, y: x / (1 + y ** 2), sp.Min, sp.Max,
+              sp.atan2, lambda x, y: (1 + sp.Abs(x)) ** sp.tanh(y)]
+
+    def tree(depth):
+        if depth == 0 or rng.random() < 0.15:
+            return syms[rng.integers(len(syms))] if rng.random() < 0.8 else sp.Float(float(rng.uniform(-3, 3)))
+        if rng.random() < 0.4:
+            return unary[rng.integers(len(unary))](tree(depth - 1) / 2)
+        if rng.random() < 0.15:
+            return tree(depth - 1) ** int(rng.integers(-3, 5))
+        return binary[rng.integers(len(binary))](tree(depth - 1), tree(depth - 1))
+
+    for trial in range(12):
+        mats = {"M%d" % i: sp.Matrix(int(rng.integers(1, 4)), int(rng.integers(1, 4)), lambda r, c: tree(4))
+                for i in range(int(rng.integers(1, 5)))}
+        prog = ExprProgram(mats, param_names=[str(s) for s in syms])
+        assert twin.valid(prog.instructions, prog.n_regs, len(syms), prog.n_out)
+        B = int(rng.integers(1, 700))
+        params = rng.uniform(-2.5, 2.5, size=(B, len(syms)))
+        out = _run(prog, params, cuda_device)
+        ref = twin.run_program(prog, params)
+        for k in mats:
+            fin = np.isfinite(ref[k])
+            assert np.array_equal(np.isnan(out[k]), np.isnan(ref[k])), (trial, k)
+            big = fin & (np.abs(ref[k]) > 1e-6)            # away from cancellations to zero
+            _close(out[k][big], ref[k][big], 1e-9, "trial %d %s" % (trial, k))
+            small = fin & ~big
+            assert np.all(np.abs(out[k][small] - ref[k][small]) <= 1e-12), (trial, k)
+
+
+def test_malformed_program_gives_nan_not_a_crash(cuda_device):
+    import torch
+    from pyhybridcontrol_b200 import cabi
+    from pyhybridcontrol_b200.utils import matrix_utils as mu
+    params = torch.ones((70, 2), dtype=torch.float64, device=cuda_device)
+    good = [[mu.OP_PARAM, 0, 1, 0], [mu.OP_OUT, 0, 0, 0], [mu.OP_OUT, 2, 0, 0]]
+    for bad in ([mu.OP_PARAM, 0, 2, 0], [mu.OP_ADD, 0, 0, 5], [mu.OP_OUT, 3, 0, 0], [99, 0, 0, 0],
+                [mu.OP_CONST, 1, 0, 0], [mu.OP_EXP, 0, -1, 0]):
+        prog = torch.tensor(good + [bad], dtype=torch.int32, device=cuda_device)
+        out = cabi.param_eval(prog, 1, [1, 2], params)
+        torch.cuda.synchronize()
+        assert bool(torch.isnan(out).all()), bad
+        assert np.isnan(twin.run(good + [bad], 1, [1, 2], params.cpu().numpy())).all()
+    prog = torch.tensor(good, dtype=torch.int32, device=cuda_device)
+    out = cabi.param_eval(prog, 1, [1, 2], params).cpu().numpy()
+    assert np.array_equal(out[:70], np.ones(70))                          # matrix 0: [B, 1]
+    m1 = out[70:].reshape(70, 2)                                          # matrix 1: [B, 2], slot 1 never written
+    assert np.isnan(m1[:, 0]).all() and np.array_equal(m1[:, 1], np.ones(70))
+
+
+def test_large_register_file_uses_opt_in_shared_memory(cuda_device):
+    """R = 600 registers x 32 threads x 8 B > 48 KB: the dynamic shared-memory opt-in path."""
+    import torch
+    from pyhybridcontrol_b200 import cabi
+    from pyhybridcontrol_b200.utils import matrix_utils as mu
+    R = 600
+    ins = [[mu.OP_PARAM, 0, 0, 0]]
+    for r in range(1, R):
+        ins.append([mu.OP_ADD, r, r - 1, 0])                              # r_k = (k + 1) * p
+    ins.append([mu.OP_OUT, 0, R - 1, 0])
+    params = torch.arange(1, 41, dtype=torch.float64, device=cuda_device).reshape(40, 1)
+    out = cabi.param_eval(torch.tensor(ins, dtype=torch.int32, device=cuda_device), R, [1], params)
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), R * np.arange(1, 41, dtype=np.float64))
+    with pytest.raises(cabi.HmpcError):                                   # 30000 registers do not fit one CTA
+        cabi.param_eval(torch.tensor(ins, dtype=torch.int32, device=cuda_device), 30000, [1], params)
+
+
+def test_device_models_match_reference_numeric_models(cuda_device):
+    """DewhModel / GridModel / PvModel / ResDemandModel: mld_numeric, get_mld_numeric(other params) and
+    update_param_struct against the reference's MldSystemModel."""
+    from pyhybridcontrol_b200.examples.residential_mg_with_pv_and_dewhs import models as M
+    cases = ((lambda: M.DewhModel(const_heat=True), "callable_dewh_control.npz"),
+             (lambda: M.DewhModel(const_heat=False), "callable_dewh_sim.npz"),
+             (lambda: M.GridModel(num_devices=3), "callable_grid_3dev.npz"),
+             (lambda: M.PvModel(), "callable_pv.npz"), (lambda: M.ResDemandModel(), "callable_resd.npz"))
+    for make, fixture in cases:
+        z, names, _, pnames = load_fixture(fixture)
+        model = make()
+        num = model.mld_numeric
+        assert num.mld_type == "numeric" and model.mld_callable.mld_type == "callable"
+        for k in MAT_NAMES:
+            ref = z["num_" + k]
+            got = np.asarray(num[k])
+            assert got.shape == ref.shape or (got.size == 0 and ref.size == 0), (fixture, k, got.shape, ref.shape)
+            if ref.size:
+                _close(got, ref, 1e-10, "%s mld_numeric.%s" % (fixture, k))
+        for key in ("nx", "nu", "ndelta", "nz", "nomega", "ny", "nmu", "nv", "n_constraints", "nu_l", "ndelta_l"):
+            assert int(num.mld_info[key]) == int(z["info_" + key]), (fixture, key)
+        other = dict(zip(pnames, z["params"][1]))
+        got = model.get_mld_numeric(param_struct_subset=other)
+        assert got is not model.mld_numeric
+        for k in names:
+            _close(np.asarray(got[k]), z["other_" + k], 1e-10, "%s get_mld_numeric %s" % (fixture, k))
+        v0 = model.version
+        model.update_param_struct(param_struct_subset=other)
+        assert model.version != v0
+        for k in names:
+            _close(np.asarray(model.mld_numeric[k]), z["other_" + k], 1e-10, "%s update_param_struct %s" % (fixture, k))
+        assert model.get_mld_numeric() is model.mld_numeric
+        with pytest.raises(ValueError, match="Invalid keys"):
+            model.get_mld_numeric(param_struct_subset=dict(not_a_parameter=1.0))
+
+
+def test_fleet_models_in_one_launch_match_dedicated_kernels(cuda_device):
+    """get_mld_numeric_batch for a fleet == the hand-written DEWH kernels (hmpc_dewh_control_model_f64 and the model
+    output of hmpc_dewh_sim_step_f64) and the oracle's closed form, per agent."""
+    import torch
+    from pyhybridcontrol_b200 import cabi
+    from pyhybridcontrol_b200.examples.residential_mg_with_pv_and_dewhs import models as M, synthetic as syn
+    B = 300
+    plist = [syn.dewh_agent_params(i) for i in range(B)]
+    keys = ("C_w", "A_h", "U_h", "m_h", "T_w", "T_inf", "P_h_Nom", "T_h_min", "T_h_max", "T_h_Nom", "ts")
+    table = np.array([[p[k] for k in keys] + [0.0] for p in plist])
+    ptab = torch.as_tensor(table).to(cuda_device)
+    over = {k: table[:, i] for i, k in enumerate(keys) if k in ("U_h", "m_h", "P_h_Nom", "T_h_min", "T_h_max")}
+    ctrl = M.DewhModel(const_heat=True)
+    mats = ctrl.get_mld_numeric_batch(overrides=over)
+    kern = cabi.dewh_control_model(ptab).cpu().numpy()
+    for i, k in enumerate(("A", "B1", "B4", "b5")):
+        assert tuple(mats[k].shape) == (B, 1, 1)
+        _close(mats[k].reshape(B).cpu().numpy(), kern[:, i], 1e-12, "control " + k)
+        _close(mats[k].reshape(B).cpu().numpy(), np.array([syn.dewh_scalars(p)[i] for p in plist]), 1e-12, "oracle " + k)
+    assert tuple(mats["f5"].shape) == (B, 2, 1) and tuple(mats["E"].shape) == (1, 2, 1)
+    assert np.array_equal(mats["f5"].cpu().numpy()[:, :, 0], np.stack([table[:, 8], -table[:, 7]], axis=1))
+    assert "B2" not in mats and np.array_equal(mats["Psi"].cpu().numpy()[0], -np.eye(2))
+
+    rng = np.random.default_rng(1)
+    T = rng.uniform(30, 80, B)
+    D = rng.uniform(0, 0.05, B)
+    sim = M.DewhModel(const_heat=False)
+    smats = sim.get_mld_numeric_batch(overrides=dict(over, T_h=T, D_h=D))
+    _, model, _ = cabi.dewh_sim_step(ptab, torch.as_tensor(T).to(cuda_device), torch.zeros(B, dtype=torch.float64,
+                                     device=cuda_device), torch.as_tensor(D).to(cuda_device), want_model=True)
+    model = model.cpu().numpy()
+    for i, k in enumerate(("A", "B1", "B4", "b5")):
+        _close(smats[k].reshape(B).cpu().numpy(), model[:, i], 1e-11, "sim " + k)
+    with pytest.raises(ValueError, match="Invalid keys"):
+        ctrl.get_mld_numeric_batch(overrides=dict(bogus=np.ones(B)))
+    with pytest.raises(ValueError):
+        ctrl.get_mld_numeric_batch(overrides=dict(U_h=np.ones(3), m_h=np.ones(4)))
+
+
+def test_controller_on_a_symbolic_model_and_batch_from_front_end(cuda_device):
+    """MpcController(model=DewhModel()) builds and solves like the numeric model; BatchMpc fed with
+    get_mld_numeric_batch solves a fleet to the same optimum as with host-made matrices."""
+    import torch
+    from pyhybridcontrol_b200.batch import BatchMpc
+    from pyhybridcontrol_b200.controllers.mpc_controller import MpcController
+    from pyhybridcontrol_b200.models.mld_model import MldModel, MldSystemModel
+    from pyhybridcontrol_b200.examples.residential_mg_with_pv_and_dewhs import models as M, synthetic as syn
+    N_p, B = 12, 24
+    wl = syn.dewh_batch(B, N_p, seed=5)
+    keys = ("U_h", "m_h", "P_h_Nom", "T_h_min", "T_h_max")
+    over = {k: np.array([p[k] for p in wl["params"]]) for k in keys}
+    mats = M.DewhModel(const_heat=True).get_mld_numeric_batch(overrides=over)
+    cost = np.zeros((B, 3 * (N_p + 1)))
+    cost[:, 0::3] = wl["q_u"]
+    cost[:, 1::3] = wl["q_mu"][:, :1]
+    cost[:, 2::3] = wl["q_mu"][:, 1:]
+    res = {}
+    for tag, mm in (("front_end", mats), ("host", wl["mats"])):
+        bm = BatchMpc(mm, N_p, nu_l=1, B=B, device=cuda_device)
+        bm.build()
+        out = bm.solve(torch.as_tensor(wl["x0"]).to(cuda_device), torch.as_tensor(wl["omega"]).to(cuda_device),
+                       cost_v=torch.as_tensor(cost).to(cuda_device))
+        assert bool((out["status"] == 0).all())
+        res[tag] = (out["obj"].cpu().numpy(), out["v"].cpu().numpy().reshape(B, N_p + 1, 3)[:, :, 0])
+    _close(res["front_end"][0], res["host"][0], 1e-9, "fleet objective")
+    assert np.array_equal(res["front_end"][1], res["host"][1])
+
+    p0 = wl["params"][0]
+    sym_ctrl = MpcController(model=M.DewhModel(param_struct=p0, const_heat=True), N_p=N_p)
+    num_ctrl = MpcController(model=MldSystemModel(mld_numeric=MldModel(
+        nu_l=1, **{k: v[0] for k, v in wl["mats"].items()})), N_p=N_p)
+    objs = []
+    for ctrl in (sym_ctrl, num_ctrl):
+        ctrl.set_std_obj_atoms(q_u=wl["q_u"][0], q_mu=wl["q_mu"][0])
+        ctrl.build()
+        objs.append(ctrl.solve(k=0, x_k=wl["x0"][0], omega_tilde_k=wl["omega"][0]))
+    assert abs(objs[0] - objs[1]) <= 1e-9 * max(1.0, abs(objs[1]))
+    assert res["host"][0][0] == pytest.approx(objs[1], rel=1e-9)
+    # a parameter change re-evaluates the model and asks for a rebuild (controller_base.py:503-505)
+    sym_ctrl.control_model.update_param_struct(T_h_max=p0["T_h_max"] + 5.0)
+    assert sym_ctrl.build_required
