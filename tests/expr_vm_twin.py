@@ -46,8 +46,17 @@ def valid(instructions, n_regs, n_params, n_out):
     return True
 
 
-def run(instructions, n_regs, mat_sizes, params):
-    """params [B, P] -> flat buffer laid out like hmpc_param_eval_f64's out (matrix m = [B, size_m] block)."""
+# instructions whose CUDA implementation is a library function (<= 2 ulp), not a correctly rounded IEEE operation
+LIBRARY_OPS = frozenset((mu.OP_EXP, mu.OP_LOG, mu.OP_SIN, mu.OP_COS, mu.OP_TAN, mu.OP_ASIN, mu.OP_ACOS, mu.OP_ATAN,
+                         mu.OP_SINH, mu.OP_COSH, mu.OP_TANH, mu.OP_POW, mu.OP_ATAN2))
+
+
+def run(instructions, n_regs, mat_sizes, params, noise=None, noise_ulps=2):
+    """params [B, P] -> flat buffer laid out like hmpc_param_eval_f64's out (matrix m = [B, size_m] block).
+
+    ``noise``: a numpy Generator -- every library-function result is moved by a random integer number of ulps in
+    [-noise_ulps, noise_ulps] -- or an int: every such result is moved by that many ulps.  Several such runs give the envelope inside which two correct implementations of the
+    same program may differ (a badly conditioned expression, e.g. acos(tanh(big)), amplifies one ulp a lot)."""
     params = np.asarray(params, dtype=np.float64)
     B, P = params.shape
     n_out = int(sum(mat_sizes))
@@ -68,6 +77,11 @@ def run(instructions, n_regs, mat_sizes, params):
                     regs[dst] = _UNARY[op](regs[a])
                 else:
                     regs[dst] = _BINARY[op](regs[a], regs[b])
+                if noise is not None and op in LIBRARY_OPS:
+                    ulps = noise if isinstance(noise, int) else noise.integers(-noise_ulps, noise_ulps + 1, size=B)
+                    regs[dst] = regs[dst] * (1.0 + ulps * 2.0 ** -52)
+                    if op in (mu.OP_SIN, mu.OP_COS, mu.OP_TANH):          # no implementation leaves [-1, 1]
+                        regs[dst] = np.clip(regs[dst], -1.0, 1.0)
     out, off = np.empty(B * n_out), 0
     for sz in mat_sizes:
         out[B * off:B * (off + sz)] = slots[off:off + sz].T.reshape(-1)
@@ -75,12 +89,28 @@ def run(instructions, n_regs, mat_sizes, params):
     return out
 
 
-def run_program(prog, params):
+def run_program(prog, params, noise=None, noise_ulps=2):
     """ExprProgram + params [B, P] -> dict name -> [B, rows, cols]."""
-    flat = run(prog.instructions, prog.n_regs, prog.mat_sizes, params)
+    flat = run(prog.instructions, prog.n_regs, prog.mat_sizes, params, noise=noise, noise_ulps=noise_ulps)
     B = np.asarray(params).shape[0]
     out, off = {}, 0
     for name, (r, c), sz in zip(prog.mat_names, prog.mat_shapes, prog.mat_sizes):
         out[name] = flat[B * off:B * (off + sz)].reshape(B, r, c)
         off += sz
     return out
+
+
+def envelope(prog, params, runs=8, seed=0, noise_ulps=2):
+    """dict name -> [B, rows, cols]: largest deviation from the noise-free run over the coherent runs (every library
+    result moved by -2, -1, +1, +2 ulp: catches every single sensitive operation) and ``runs`` random ones."""
+    ref = run_program(prog, params)
+    rng = np.random.default_rng(seed)
+    env = {k: np.zeros_like(v) for k, v in ref.items()}
+    modes = [u for u in range(-noise_ulps, noise_ulps + 1) if u] + [rng] * runs
+    for mode in modes:
+        out = run_program(prog, params, noise=mode, noise_ulps=noise_ulps)
+        for k in env:
+            with np.errstate(all="ignore"):
+                dev = np.abs(out[k] - ref[k])
+            env[k] = np.fmax(env[k], np.where(np.isfinite(dev), dev, np.inf))
+    return ref, env
