@@ -12,6 +12,8 @@ What it restates (all citations relative to /root/reference):
                           objective_atoms.py:308-363,453-496, controllers/controller_base.py:440-452,467-472)
 * ``oracle.lsim``      -- one-step MLD simulation + DEWH sim model (models/mld_model.py:647-699,
                           examples/.../micro_grid_models.py:27-100, micro_grid_agents.py:389-408)
+* ``oracle.callable``  -- symbolic / callable model evaluation: sympy.lambdify of every matrix, called per agent
+                          (utils/matrix_utils.py:339-343, 372-380, 441-470; models/mld_model.py:791-793, 1128-1149)
 * ``oracle.solve``     -- the MI(Q)P solve the reference hands to cvxpy -> Gurobi/CPLEX
                           (controllers/controller_base.py:509-512).  Those solvers are third-party,
                           unpinned and not installed; the offline backend is HiGHS 1.12.0 as vendored by
@@ -24,6 +26,9 @@ so per the task rules:
 * condensing + lsim_k: **pinned** against outputs of the unmodified reference itself, run in the build
   container under ``oracle/ref_shim.py``; vectors committed in ``tests/golden/`` together with the
   generating script ``tests/golden/make_golden.py``.
+* symbolic / callable models: **pinned** against the unmodified reference's CallableMatrix / MldSystemModel /
+  DewhModel / GridModel / PvModel / ResDemandModel (``ref_shim.load_symbolic``); vectors ``tests/golden/callable_*.npz``,
+  generating script ``tests/golden/make_golden_callable.py``.
 * problem assembly + MI(Q)P solve: **parity unpinned** -- cvxpy/Gurobi cannot run here; the restatement is
   anchored on the reference's call sites (cited per function) and cross-checked HiGHS vs enumeration.
 """
