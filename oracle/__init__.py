@@ -14,6 +14,8 @@ What it restates (all citations relative to /root/reference):
                           examples/.../micro_grid_models.py:27-100, micro_grid_agents.py:389-408)
 * ``oracle.callable``  -- symbolic / callable model evaluation: sympy.lambdify of every matrix, called per agent
                           (utils/matrix_utils.py:339-343, 372-380, 441-470; models/mld_model.py:791-793, 1128-1149)
+* ``oracle.mini_cvxpy`` / ``oracle.ref_shim`` -- not restatements: the stand-in for cvxpy's modelling layer and
+                          the compat shim that let the UNMODIFIED reference run here to produce the golden vectors
 * ``oracle.solve``     -- the MI(Q)P solve the reference hands to cvxpy -> Gurobi/CPLEX
                           (controllers/controller_base.py:509-512).  Those solvers are third-party,
                           unpinned and not installed; the offline backend is HiGHS 1.12.0 as vendored by
@@ -29,6 +31,15 @@ so per the task rules:
 * symbolic / callable models: **pinned** against the unmodified reference's CallableMatrix / MldSystemModel /
   DewhModel / GridModel / PvModel / ResDemandModel (``ref_shim.load_symbolic``); vectors ``tests/golden/callable_*.npz``,
   generating script ``tests/golden/make_golden_callable.py``.
-* problem assembly + MI(Q)P solve: **parity unpinned** -- cvxpy/Gurobi cannot run here; the restatement is
-  anchored on the reference's call sites (cited per function) and cross-checked HiGHS vs enumeration.
+* problem assembly, ``solve`` / ``feedback`` / ``sim_step_k`` flows: **pinned** against the unmodified reference's
+  own code (EvoVariables, ObjectiveAtoms, gen_evo_constraints, MpcController.build / solve / feedback, sim_step_k with
+  its auxiliary feasibility problem), run in the build container under ``ref_shim.load_controllers``: cvxpy's
+  MODELLING layer is replaced by ``oracle/mini_cvxpy.py`` (cvxpy is third-party, not installed, unpinned by the
+  reference -- API usage implies 1.0.x; the stand-in restates its documented semantics: column-major reshape, ``*``
+  rules, atoms) and its MILP backend by HiGHS.  Vectors ``tests/golden/assembly_*.npz``, generating script
+  ``tests/golden/make_golden_assembly.py``, checker ``tests/test_oracle_assembly_pinned.py``.
+* the mixed-integer SOLVER itself (Gurobi / CPLEX): **unpinned** -- not installable; HiGHS 1.12.0 (scipy) stands in,
+  cross-checked against exhaustive enumeration.
+* input side (profile windows, scenario draws, prices, tariff) and result frame: **pinned**
+  (``tests/golden/profiles_inputs.npz``, ``simlog_campaign.npz``).
 """

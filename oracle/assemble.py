@@ -12,7 +12,13 @@ optimisation problem it hands to cvxpy:
 * cost-atom grammar and semantics                      : controllers/components/objective_atoms.py:453-496, 308-363,
   weights :79-206, rate variables :297-305
 
-Parity status: UNPINNED (cvxpy cannot run here) -- anchored on the call sites cited above.
+Parity status: PINNED against the unmodified reference's own assembly code (EvoVariables, ObjectiveAtoms,
+gen_evo_constraints, set_constraints, MpcController.build), run in the build container under
+``oracle/ref_shim.load_controllers`` with ``oracle/mini_cvxpy.py`` standing in for cvxpy's modelling layer (cvxpy is a
+third-party dependency that is not installed and not pinned by the reference; the stand-in restates its documented
+shape / operator semantics).  Vectors: ``tests/golden/assembly_*.npz`` (``tests/golden/make_golden_assembly.py``);
+checker: ``tests/test_oracle_assembly_pinned.py`` -- variable layout, every row and right-hand side, bounds,
+integrality, cost vector, and the objective value at random points for every atom type.
 
 The result is the canonical form used by every solver in this repo:
 

@@ -181,6 +181,32 @@ def load_symbolic():
     return mm.MldModel, mm.MldSystemModel, rmu.CallableMatrix, models, params
 
 
+def load_controllers():
+    """The reference's whole per-step path, unmodified, with ``oracle/mini_cvxpy.py`` standing in for cvxpy's
+    modelling layer: returns a namespace with MldModel, MldSystemModel, MpcController, the controller_base module,
+    the example's models / agents / parameters modules and the cvxpy stand-in.  Must be the FIRST loader called in
+    the process (the stand-in has to be registered before the reference imports cvxpy)."""
+    import importlib
+    import types as _types
+    import warnings
+    import numpy as np
+    from oracle import mini_cvxpy
+    cvx = mini_cvxpy.install()
+    MldModel, MldSystemModel, CallableMatrix, models, params = load_symbolic()
+    if "dims" not in getattr(np.unravel_index, "__doc__", "") and not getattr(np, "_hmpc_unravel_alias", False):
+        _unravel = np.unravel_index          # numpy 2 renamed unravel_index(dims=) to shape=
+        np.unravel_index = lambda indices, shape=None, order="C", dims=None: _unravel(
+            indices, shape if shape is not None else dims, order=order)
+        np._hmpc_unravel_alias = True
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        cb = importlib.import_module("controllers.controller_base")
+        mpc = importlib.import_module("controllers.mpc_controller")
+        agents = importlib.import_module("examples.residential_mg_with_pv_and_dewhs.modelling.micro_grid_agents")
+    return _types.SimpleNamespace(MldModel=MldModel, MldSystemModel=MldSystemModel, MpcController=mpc.MpcController,
+                                  controller_base=cb, models=models, params=params, agents=agents, cvx=cvx)
+
+
 EVO_NAMES = ("Phi_x", "Gamma_v", "Gamma_omega", "Gamma_5",
              "L_x", "L_v", "L_omega", "L_5",
              "H_x", "H_v", "H_omega", "H_5")

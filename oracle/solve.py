@@ -11,8 +11,12 @@ installed or pinned by the reference; the offline backend here is **HiGHS 1.12.0
 * ``solve_miqp``      -- quadratic cost: depth-first branch-and-bound over HiGHS QP relaxations
                          (private ``scipy.optimize._highspy._core``; HiGHS itself has no MIQP mode).
 
-Parity status: UNPINNED by the reference (it has no tests); HiGHS and enumeration are checked against each
-other in tests/test_oracle_solve.py.
+Parity status: the reference has no tests and its solver (Gurobi / CPLEX through cvxpy) cannot run here, so the
+SOLVER stays unpinned; what is pinned is everything around it -- the unmodified reference's ``MpcController.solve`` /
+``feedback`` / ``sim_step_k`` run in the build container with HiGHS behind ``oracle/mini_cvxpy.py``, and
+``tests/test_oracle_assembly_pinned.py`` holds this module to the objectives, first-step values and the 14-instant
+closed loop they produce (``tests/golden/assembly_*.npz``).  HiGHS and enumeration are checked against each other in
+tests/test_oracle_solve.py.
 """
 import itertools
 
