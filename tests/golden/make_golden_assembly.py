@@ -91,6 +91,8 @@ def run_case(name, mld, N_p, x_k, omega_tilde, atoms, extra=(), disable_soft=Fal
     P = 12
     pts = rng.uniform(-1.0, 2.0, size=(P, n))
     pts[:, cf["integrality"]] = rng.integers(0, 2, size=(P, int(cf["integrality"].sum())))
+    nonneg = (cf["lb"] == 0.0) & ~cf["integrality"]
+    pts[:, nonneg] = np.abs(pts[:, nonneg])                 # inside the variable bounds (slacks >= 0)
     data["points_x"] = pts
     data["points_f"] = np.array([prob.objective_at(p, variables) for p in pts])
     if solve and cf["objective_is_affine"]:
@@ -184,6 +186,12 @@ def main():
     atoms.update(Q_x=np.array([[0.3]]), q_L22_y_N_p=np.array([0.2]), Q_x_f=np.array([[2.0]]), q_L1_du=np.array([0.7]),
                  q_L1_x=np.array([0.05]), Q_mu=np.diag([0.4, 0.1]), q_x_N_p=np.array([0.01]), q_Linf_mu=np.array([0.3, 0.2]))
     run_case("dewh_N6_all_atoms", dewh, 6, x, w, atoms, k_neg1=dict(u=[1.0]), seed=5, solve=False)
+    x, w, atoms = dewh_inputs(6)
+    # the non-linear atoms the stage-DP kernels take (per-step diagonal weights, no rate form, no Linf)
+    atoms.update(Q_x=np.array([[0.3]]), q_L22_y_N_p=np.array([0.2]), Q_x_f=np.array([[2.0]]), q_L1_x=np.array([0.05]),
+                 Q_mu=np.diag([0.4, 0.1]), q_L1_u=np.array([0.3]), q_L22_u=np.array([0.5]), q_L1_mu=np.array([0.2, 0.6]),
+                 Q_L1_y=np.array([[0.15]]), q_y=rng.uniform(-0.01, 0.01, 7))
+    run_case("dewh_N6_stage_dp_atoms", dewh, 6, x, w, atoms, seed=10, solve=False)
     x, w, atoms = dewh_inputs(6)
     atoms.update(q_du=np.array([0.2]), q_y=rng.uniform(-0.01, 0.01, 7), q_x_f=np.array([-0.02]), q_v_N_p=np.array([0.0, 0.1, 0.2]))
     run_case("dewh_N6_linear_xy_rate", dewh, 6, x, w, atoms, k_neg1=dict(u=[1.0]), seed=6)
