@@ -38,6 +38,9 @@ so per the task rules:
   reference -- API usage implies 1.0.x; the stand-in restates its documented semantics: column-major reshape, ``*``
   rules, atoms) and its MILP backend by HiGHS.  Vectors ``tests/golden/assembly_*.npz``, generating script
   ``tests/golden/make_golden_assembly.py``, checker ``tests/test_oracle_assembly_pinned.py``.
+* the centralised micro-grid problem (``oracle.coupled``): **pinned** against the reference's own
+  GridAgentMpc.build_grid / solve_grid_mpc / sim_step_k loop (``tests/golden/microgrid_loop.npz``,
+  ``tests/golden/make_golden_microgrid.py``, ``tests/test_oracle_microgrid_pinned.py``).
 * the mixed-integer SOLVER itself (Gurobi / CPLEX): **unpinned** -- not installable; HiGHS 1.12.0 (scipy) stands in,
   cross-checked against exhaustive enumeration.
 * input side (profile windows, scenario draws, prices, tariff) and result frame: **pinned**

@@ -11,7 +11,12 @@ device's constraints and objectives, and the grid's omega~ is the stack of the d
           grid MLD rows per step (micro_grid_models.py:145-168):  F2 delta_k + F3 z_k + G y_k <= f5,
           y_k = sum_i P_h_Nom_i u_i,k + (PV and residential-demand outputs, which are data)
 
-Parity status: UNPINNED (cvxpy + Gurobi cannot run here); solved with HiGHS (oracle.solve.solve_milp).
+Parity status: PINNED against the unmodified reference's own centralised problem -- GridAgentMpc.build_grid /
+solve_grid_mpc / sim_step_k with four heaters, PV and demand, two controllers, three instants, run in the build
+container under oracle/ref_shim.load_controllers (cvxpy's modelling layer = oracle/mini_cvxpy.py, HiGHS for Gurobi);
+vectors tests/golden/microgrid_loop.npz (tests/golden/make_golden_microgrid.py), checker
+tests/test_oracle_microgrid_pinned.py: optimal objectives to 1e-6, the reference's plan re-priced in this model, device
+and grid simulation steps.  Solved with HiGHS (oracle.solve.solve_milp).
 """
 import numpy as np
 

@@ -1,0 +1,88 @@
+"""CPU: the oracle's CENTRALISED micro-grid problem (oracle/coupled.py), device simulation steps and grid bookkeeping
+against the UNMODIFIED reference's own example loop on a small micro-grid -- GridAgentMpc.build_grid / solve_grid_mpc /
+sim_step_k with four water heaters, a PV plant and a residential demand, a certainty-equivalent and a perfect-forecast
+controller, three instants (tests/golden/microgrid_loop.npz, tests/golden/make_golden_microgrid.py; cvxpy's modelling
+layer = oracle/mini_cvxpy.py, MILP backend = HiGHS).  The forecast / actual / price windows come from the product's
+input-side module (examples/.../profiles.py), so this also checks that module inside the loop."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import assemble as oa
+from oracle import condense as oc
+from oracle import coupled as ocp
+from oracle import lsim as ol
+from oracle import mld as omld
+from oracle import solve as osv
+from pyhybridcontrol_b200.examples.residential_mg_with_pv_and_dewhs import profiles as P
+
+G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "microgrid_loop.npz"))
+KEYS = ("C_w", "A_h", "U_h", "m_h", "T_w", "T_inf", "P_h_Nom", "T_h_min", "T_h_max", "T_h_Nom", "ts")
+
+
+@pytest.mark.parametrize("ci", range(len(G["controllers"])))
+def test_centralised_loop_against_the_reference(ci):
+    cname, det = str(G["controllers"][ci]), bool(G["deterministic"][ci])
+    N_h, N_p, steps, lag = int(G["N_h"]), int(G["N_p"]), int(G["steps"]), int(G["lag"])
+    Nt = N_p + 1
+    params = [dict(zip(KEYS, row)) for row in G["dewh_params"]]
+    P_nom = np.array([p["P_h_Nom"] for p in params])
+    grid_params = dict(zip(("P_g_min", "P_g_max", "eps"), G["grid_params"]))
+    dewh = P.OmegaProfiles(G["dewh_profiles"][:, :, None], 900.0)
+    pv = P.OmegaProfiles(G["pv_profile"], 900.0)
+    resd = P.OmegaProfiles(G["resd_profile"], 900.0)
+    price = P.PriceProfile(G["price"], 900.0)
+    assert dewh.lag == lag
+    models = []
+    for p in params:
+        full, dims, vt = omld.complete(ol.dewh_mld(p, const_heat=True), nu_l=1)
+        models.append((oc.condense(full, dims, Nt), dims, vt))
+    T = G["x0"].astype(float).copy()
+    for k in range(steps):
+        pk = price.price_tilde_k(k, Nt)
+        w = dewh.omega_tilde_k_hat(k, Nt, deterministic=det)
+        p_other = float(G["pv_gain"]) * pv.omega_tilde_k_hat(k, Nt, deterministic=det)[0] + \
+            float(G["resd_gain"]) * resd.omega_tilde_k_hat(k, Nt, deterministic=det)[0]
+        max_cost = pk.sum() * 3000.0                       # the script uses the base P_h_Nom for every heater (:196)
+        q_mu = np.array([max_cost * G["soft"][0], max_cost * G["soft"][1]])
+        np.testing.assert_allclose(T, G[cname + "_T"][k], rtol=1e-12)
+        agents = [oa.build_problem(evo, dims, vt, Nt, [T[i]], w[i], atoms=dict(q_mu=q_mu))
+                  for i, (evo, dims, vt) in enumerate(models)]
+        prob, offs, n_agents = ocp.build_coupled_problem(agents, P_nom, p_other, pk, grid_params)
+        status, obj, v = osv.solve_milp(prob, polish=True)
+        ref = float(G[cname + "_obj"][k])
+        assert status == osv.OPTIMAL and abs(obj - ref) <= 1e-6 * max(1.0, abs(ref)), (k, obj, ref)
+        # the reference's own plan costs the same in the oracle's model (so ties cannot hide a modelling difference)
+        U_ref = np.round(G[cname + "_u_plan"][k])
+        assert abs(ocp.coupled_cost(agents, U_ref, P_nom, p_other, pk) - ref) <= 1e-6 * max(1.0, abs(ref))
+        z_ref = G[cname + "_z_plan"][k]
+        np.testing.assert_allclose(z_ref, np.maximum(0.0, P_nom @ U_ref + p_other), rtol=1e-9, atol=1e-6)
+        # simulation step of every device with the reference's first controls and the actual disturbances
+        u0 = np.round(G[cname + "_u"][k])
+        assert np.array_equal(u0, U_ref[:, 0])
+        w_act = dewh.omega_k_act(k)[:, 0]
+        T_next = np.array([ol.dewh_sim_step(params[i], T[i], u0[i], w_act[i])[0] for i in range(N_h)])
+        np.testing.assert_allclose(T_next, G[cname + "_T_next"][k], rtol=1e-9)
+        powers = np.concatenate([P_nom * u0, [float(G["pv_gain"]) * pv.omega_k_act(k)[0, 0]],
+                                 [float(G["resd_gain"]) * resd.omega_k_act(k)[0, 0]]])
+        np.testing.assert_allclose(powers, G[cname + "_grid_omega"][k], rtol=1e-12)       # devices ordered (type, id)
+        y = powers.sum()
+        delta, z = ol.grid_aux_closed_form(y)
+        assert abs(y - G[cname + "_grid_y"][k]) <= 1e-9 * max(1.0, abs(y))
+        assert float(delta) == G[cname + "_grid_delta"][k] and abs(float(z) - G[cname + "_grid_z"][k]) <= 1e-6
+        cost_k = float(z) * price.price_tilde_k(k, 1)[0]
+        assert abs(cost_k - G[cname + "_cost"][k]) <= 1e-9 * max(1.0, abs(cost_k)) + 1e-9
+        T = T_next
+
+
+def test_reference_frame_shape():
+    """the frame of the reference's loop: grid first, then the devices by (type, id), every controller's columns"""
+    cols = [c.split("|") for c in G["frame_columns"]]
+    assert G["frame_values"].shape == (int(G["steps"]), len(cols))
+    order = []
+    for c in cols:
+        if (c[0], c[1]) not in order:
+            order.append((c[0], c[1]))
+    assert order == [("grid", "1")] + [("dewh", str(i)) for i in range(1, int(G["N_h"]) + 1)] + [("pv", "1"), ("resd", "1")]
+    assert {c[2] for c in cols} == {str(c) for c in G["controllers"]}
