@@ -86,3 +86,48 @@ def test_reference_frame_shape():
             order.append((c[0], c[1]))
     assert order == [("grid", "1")] + [("dewh", str(i)) for i in range(1, int(G["N_h"]) + 1)] + [("pv", "1"), ("resd", "1")]
     assert {c[2] for c in cols} == {str(c) for c in G["controllers"]}
+
+
+def test_result_frame_of_the_real_loop():
+    """examples/.../results.py rebuilds the frame the reference's REAL loop produced (two controllers on every device):
+    the inputs are the frame's own primary columns (temperatures, controls, disturbances, planned slacks, grid
+    quantities); every derived column (y, v, x_hat / y_hat / u_hat / v_hat, p_imp, p_exp, cost, the grid's v), the
+    column order and the device order must come out identical.  Solve-time columns are excluded (wall-clock)."""
+    from pyhybridcontrol_b200.examples.residential_mg_with_pv_and_dewhs import results
+    cols = [tuple(c.split("|")) for c in G["frame_columns"]]
+    vals = G["frame_values"]
+    steps, N_h, lag = int(G["steps"]), int(G["N_h"]), int(G["lag"])
+    params = [dict(zip(KEYS, row)) for row in G["dewh_params"]]
+
+    def col(dev, dev_id, cname, var, idx=0):
+        return vals[:, cols.index((dev, str(dev_id), cname, var, str(idx)))]
+
+    blocks = []
+    for cname in (str(c) for c in G["controllers"]):
+        ids = list(range(1, N_h + 1))
+        T = np.stack([np.append(col("dewh", i, cname, "x_hat"), col("dewh", i, cname, "x_k1")[-1]) for i in ids], axis=1)
+        log = dict(T=T, u=np.stack([col("dewh", i, cname, "u") for i in ids], axis=1),
+                   omega=np.stack([col("dewh", i, cname, "omega") for i in ids], axis=1),
+                   omega_hat=np.stack([col("dewh", i, cname, "omega_hat") for i in ids], axis=1),
+                   mu_hat=np.stack([np.stack([col("dewh", i, cname, "mu_hat", j) for j in (0, 1)], axis=1) for i in ids], axis=1),
+                   cons=np.stack([np.stack([col("dewh", i, cname, "cons", j) for j in (0, 1)], axis=1) for i in ids], axis=1))
+        for i in ids[:-1]:                                # the loop's own continuity: x_k1 of step k is x_hat of k + 1
+            np.testing.assert_allclose(col("dewh", i, cname, "x_k1")[:-1], col("dewh", i, cname, "x_hat")[1:], rtol=1e-12)
+        blocks.append(("dewh", ids, cname, results.dewh_log_blocks(log, params, cname)))
+        for dev, gain in (("pv", float(G["pv_gain"])), ("resd", float(G["resd_gain"]))):
+            blocks.append((dev, [1], cname, results.source_log_blocks(col(dev, 1, cname, "omega"),
+                                                                      col(dev, 1, cname, "omega_hat"), gain)))
+        n_dev = N_h + 2
+        grid = dict(y=col("grid", 1, cname, "y"), delta=col("grid", 1, cname, "delta"), z=col("grid", 1, cname, "z"),
+                    omega=np.stack([col("grid", 1, cname, "omega", j) for j in range(n_dev)], axis=1),
+                    cons=np.stack([col("grid", 1, cname, "cons", j) for j in range(6)], axis=1),
+                    y_hat=col("grid", 1, cname, "y_hat"), delta_hat=col("grid", 1, cname, "delta_hat"),
+                    z_hat=col("grid", 1, cname, "z_hat"),
+                    omega_hat=np.stack([col("grid", 1, cname, "omega_hat", j) for j in range(n_dev)], axis=1),
+                    price=G["price"][lag:lag + steps])
+        blocks.append(("grid", [1], cname, results.grid_log_blocks(grid)))
+    df = results.grid_sim_dataframe(blocks, steps)
+    got_cols = [tuple(str(x) for x in c) for c in df.columns.tolist()]
+    assert got_cols == cols
+    keep = np.array([not c[3].startswith("time_") for c in cols])
+    np.testing.assert_allclose(df.to_numpy(dtype=float)[:, keep], vals[:, keep], rtol=1e-12, atol=1e-9)
