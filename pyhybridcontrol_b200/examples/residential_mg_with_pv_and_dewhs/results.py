@@ -90,11 +90,17 @@ def dewh_log_blocks(log, params, controller):
 
 def source_log_blocks(omega, omega_hat, gain, is_mpc=True, times=None):
     """PV / residential-demand device (nx = nu = 0, y = gain * omega; micro_grid_models.py:176-240):
-    PV gain = -P_pv_max * P_pv_units, demand gain = P_res_ave * P_res_units."""
+    PV gain = -P_pv_max * P_pv_units, demand gain = P_res_ave * P_res_units.
+
+    The ``*_hat`` columns are there for every controller type: the ``NoController`` these devices get next to a
+    thermostat (micro_grid_control_simulation.py:175-177) is a plain ConstraintSolvedController
+    (controllers/no_controller.py) and logs its forecast like an MPC controller does -- seen in the frame of the
+    reference's real loop (tests/golden/microgrid_loop.npz).  ``is_mpc=False`` with ``omega_hat=None`` leaves them
+    out."""
     omega = np.asarray(omega, dtype=np.float64).reshape(-1)
     steps = omega.size
     blocks = [("omega", omega), ("y", gain * omega)]
-    if is_mpc:
+    if is_mpc or omega_hat is not None:
         omega_hat = np.asarray(omega_hat, dtype=np.float64).reshape(-1)
         blocks += [("omega_hat", omega_hat), ("y_hat", gain * omega_hat)]
     times = np.zeros((steps, 2)) if times is None else np.asarray(times, dtype=np.float64)
@@ -112,7 +118,7 @@ def grid_log_blocks(grid, is_mpc=True, times=None):
     v = np.stack([delta, z], axis=1)
     blocks = [("delta", delta), ("z", z), ("omega", np.asarray(grid["omega"], dtype=np.float64)[:, None, :]), ("y", y),
               ("v", v[:, None, :]), ("cons", np.asarray(grid["cons"], dtype=np.float64)[:, None, :])]
-    if is_mpc:
+    if is_mpc or "y_hat" in grid:                          # a NoController grid logs its forecast too (see above)
         yh, dh, zh = (np.asarray(grid[k + "_hat"], dtype=np.float64).reshape(-1) for k in ("y", "delta", "z"))
         blocks += [("delta_hat", dh), ("z_hat", zh),
                    ("omega_hat", np.asarray(grid["omega_hat"], dtype=np.float64)[:, None, :]), ("y_hat", yh),

@@ -66,10 +66,18 @@ def main():
     grid.add_device(resd)
     dewhs = [d for d in grid.devices if isinstance(d, ag.DewhAgentMpc)]
 
-    controllers = dict(mpc_ce=False, mpc_pb=True)                              # name -> is_deterministic
+    import importlib
+    thermo_mod = importlib.import_module("examples.residential_mg_with_pv_and_dewhs.theromstat_control")
+    no_ctrl = importlib.import_module("controllers.no_controller").NoController
+    controllers = dict(mpc_ce=False, mpc_pb=True, thermo=False)               # name -> is_deterministic
     for cname in controllers:
         for dev in itertools.chain([grid], grid.devices):
-            dev.add_controller(cname, R.MpcController, N_p=N_p)
+            if cname != "thermo":
+                dev.add_controller(cname, R.MpcController, N_p=N_p)
+            elif isinstance(dev, ag.DewhAgentMpc):                           # micro_grid_control_simulation.py:169-177
+                dev.add_controller(cname, thermo_mod.DewhTheromstatController, N_p=0, N_tilde=1)
+            else:
+                dev.add_controller(cname, no_ctrl, N_p=0, N_tilde=1)
     for d, x in zip(dewhs, x0):
         d.x_k = x
     keys = ("C_w", "A_h", "U_h", "m_h", "T_w", "T_inf", "P_h_Nom", "T_h_min", "T_h_max", "T_h_Nom", "ts")
@@ -87,6 +95,8 @@ def main():
     for k in range(steps):
         prices_tilde = grid.get_price_tilde_k(k=k)
         for cname in controllers:
+            if cname == "thermo":
+                continue
             for dev in itertools.chain([grid], grid.devices):
                 if isinstance(dev, ag.DewhAgentMpc):
                     max_cost = np.sum(prices_tilde[cname]) * R.params.dewh_param_struct.P_h_Nom
@@ -98,7 +108,8 @@ def main():
         grid.solve_grid_mpc(k=k, verbose=False, TimeLimit=20, MIPGap=0.0)
         plans = {c: dict(u=[np.asarray(d.controllers[c].variables.u.var_N_tilde.value).ravel() for d in dewhs],
                          z=np.asarray(grid.controllers[c].variables.z.var_N_tilde.value).ravel(),
-                         obj=float(grid.controllers[c].problem.value)) for c in controllers}
+                         obj=float(grid.controllers[c].problem.value)) for c in controllers if c != "thermo"}
+        plans["thermo"] = dict(u=[np.full(Nt, np.nan)] * N_h, z=np.full(Nt, np.nan), obj=np.nan)
         T_before = {c: [float(np.asarray(d.controllers[c].x_k.value if hasattr(d.controllers[c].x_k, "value")
                                          else d.controllers[c].x_k).ravel()[0]) for d in dewhs] for c in controllers}
         grid.sim_step_k(k=k)

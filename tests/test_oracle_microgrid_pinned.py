@@ -21,7 +21,10 @@ G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "
 KEYS = ("C_w", "A_h", "U_h", "m_h", "T_w", "T_inf", "P_h_Nom", "T_h_min", "T_h_max", "T_h_Nom", "ts")
 
 
-@pytest.mark.parametrize("ci", range(len(G["controllers"])))
+MPC = [i for i, c in enumerate(G["controllers"]) if str(c).startswith("mpc")]
+
+
+@pytest.mark.parametrize("ci", MPC)
 def test_centralised_loop_against_the_reference(ci):
     cname, det = str(G["controllers"][ci]), bool(G["deterministic"][ci])
     N_h, N_p, steps, lag = int(G["N_h"]), int(G["N_p"]), int(G["steps"]), int(G["lag"])
@@ -76,6 +79,32 @@ def test_centralised_loop_against_the_reference(ci):
         T = T_next
 
 
+def test_thermostat_loop_against_the_reference():
+    """the non-predictive controller of the same loop (DewhTheromstatController on the heaters, NoController elsewhere):
+    hysteresis rule with u(-1) = 0, simulation steps, grid bookkeeping"""
+    cname = "thermo"
+    N_h, steps = int(G["N_h"]), int(G["steps"])
+    params = [dict(zip(KEYS, row), T_h_max_sub_T_h_on=12, T_h_max_sub_T_h_off=4) for row in G["dewh_params"]]
+    P_nom = np.array([p["P_h_Nom"] for p in params])
+    dewh = P.OmegaProfiles(G["dewh_profiles"][:, :, None], 900.0)
+    pv, resd = P.OmegaProfiles(G["pv_profile"], 900.0), P.OmegaProfiles(G["resd_profile"], 900.0)
+    price = P.PriceProfile(G["price"], 900.0)
+    T, u_prev = G["x0"].astype(float).copy(), np.zeros(N_h)
+    for k in range(steps):
+        u = np.array([ol.dewh_thermostat(params[i], T[i], u_prev[i]) for i in range(N_h)], dtype=float)
+        assert np.array_equal(u, G[cname + "_u"][k]), k
+        w_act = dewh.omega_k_act(k)[:, 0]
+        T_next = np.array([ol.dewh_sim_step(params[i], T[i], u[i], w_act[i])[0] for i in range(N_h)])
+        np.testing.assert_allclose(T_next, G[cname + "_T_next"][k], rtol=1e-9)
+        powers = np.concatenate([P_nom * u, [float(G["pv_gain"]) * pv.omega_k_act(k)[0, 0]],
+                                 [float(G["resd_gain"]) * resd.omega_k_act(k)[0, 0]]])
+        np.testing.assert_allclose(powers, G[cname + "_grid_omega"][k], rtol=1e-12)
+        delta, z = ol.grid_aux_closed_form(powers.sum())
+        assert float(delta) == G[cname + "_grid_delta"][k] and abs(float(z) - G[cname + "_grid_z"][k]) <= 1e-6
+        assert abs(float(z) * price.price_tilde_k(k, 1)[0] - G[cname + "_cost"][k]) <= 1e-9
+        T, u_prev = T_next, u
+
+
 def test_reference_frame_shape():
     """the frame of the reference's loop: grid first, then the devices by (type, id), every controller's columns"""
     cols = [c.split("|") for c in G["frame_columns"]]
@@ -116,7 +145,8 @@ def test_result_frame_of_the_real_loop():
         blocks.append(("dewh", ids, cname, results.dewh_log_blocks(log, params, cname)))
         for dev, gain in (("pv", float(G["pv_gain"])), ("resd", float(G["resd_gain"]))):
             blocks.append((dev, [1], cname, results.source_log_blocks(col(dev, 1, cname, "omega"),
-                                                                      col(dev, 1, cname, "omega_hat"), gain)))
+                                                                      col(dev, 1, cname, "omega_hat"), gain,
+                                                                      is_mpc=cname != "thermo")))
         n_dev = N_h + 2
         grid = dict(y=col("grid", 1, cname, "y"), delta=col("grid", 1, cname, "delta"), z=col("grid", 1, cname, "z"),
                     omega=np.stack([col("grid", 1, cname, "omega", j) for j in range(n_dev)], axis=1),
@@ -125,7 +155,7 @@ def test_result_frame_of_the_real_loop():
                     z_hat=col("grid", 1, cname, "z_hat"),
                     omega_hat=np.stack([col("grid", 1, cname, "omega_hat", j) for j in range(n_dev)], axis=1),
                     price=G["price"][lag:lag + steps])
-        blocks.append(("grid", [1], cname, results.grid_log_blocks(grid)))
+        blocks.append(("grid", [1], cname, results.grid_log_blocks(grid, is_mpc=cname != "thermo")))
     df = results.grid_sim_dataframe(blocks, steps)
     got_cols = [tuple(str(x) for x in c) for c in df.columns.tolist()]
     assert got_cols == cols
