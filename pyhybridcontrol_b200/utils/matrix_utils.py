@@ -340,10 +340,111 @@ class ExprProgram(object):
         return "\n".join(lines)
 
 
+class _Tracer(object):
+    """A sympy expression that also answers numpy's object-dtype protocol: ``np.exp(x)`` on an object looks for
+    ``x.exp()``, ``np.sqrt(x)`` for ``x.sqrt()`` and so on, so matrix functions written with numpy ufuncs -- the way
+    the reference's users write them, since it calls them with floats -- can be traced as well.  Anything that needs
+    the VALUE (``if x > 0``, ``float(x)``, ``int(x)``) raises: such a function cannot run on the GPU."""
+    __array_priority__ = 1000.0
+    _UFUNCS = dict(exp="exp", log="log", sqrt="sqrt", sin="sin", cos="cos", tan="tan", arcsin="asin", arccos="acos",
+                   arctan="atan", sinh="sinh", cosh="cosh", tanh="tanh", fabs="Abs", absolute="Abs", sign="sign",
+                   floor="floor", ceil="ceiling", conjugate="conjugate", conj="conjugate")
+
+    _BINARY = dict(add=lambda sp, a, b: a + b, subtract=lambda sp, a, b: a - b, multiply=lambda sp, a, b: a * b,
+                   true_divide=lambda sp, a, b: a / b, divide=lambda sp, a, b: a / b, power=lambda sp, a, b: a ** b,
+                   float_power=lambda sp, a, b: a ** b, maximum=lambda sp, a, b: sp.Max(a, b),
+                   minimum=lambda sp, a, b: sp.Min(a, b), fmax=lambda sp, a, b: sp.Max(a, b),
+                   fmin=lambda sp, a, b: sp.Min(a, b), arctan2=lambda sp, a, b: sp.atan2(a, b))
+
+    def __init__(self, expr):
+        self.e = _sympy().sympify(expr)
+
+    @staticmethod
+    def _un(x):
+        return x.e if isinstance(x, _Tracer) else x
+
+    def __array_ufunc__(self, ufunc, method, *inputs, **kwargs):
+        """``np.exp(x)``, ``np.maximum(x, 0.0)``, ... called directly on a tracer"""
+        if method != "__call__" or kwargs:
+            return NotImplemented
+        if any(isinstance(i, np.ndarray) for i in inputs):
+            # tracer (op) array: let numpy's object loop apply the operator element by element
+            arrs = [np.asarray(i, dtype=object) if isinstance(i, np.ndarray) else i for i in inputs]
+            return getattr(ufunc, method)(*[np.array(a, dtype=object) if isinstance(a, _Tracer) else a for a in arrs])
+        sp = _sympy()
+        name = ufunc.__name__
+        args = [self._un(i) for i in inputs]
+        if len(args) == 1:
+            if name in _Tracer._UFUNCS:
+                return _Tracer(getattr(sp, _Tracer._UFUNCS[name])(args[0]))
+            if name == "negative":
+                return _Tracer(-args[0])
+            if name == "positive":
+                return _Tracer(args[0])
+            if name == "square":
+                return _Tracer(args[0] ** 2)
+            if name == "reciprocal":
+                return _Tracer(1 / args[0])
+        elif len(args) == 2 and name in _Tracer._BINARY:
+            return _Tracer(_Tracer._BINARY[name](sp, args[0], args[1]))
+        raise TypeError("numpy.%s has no GPU instruction" % name)
+
+    def __getattr__(self, name):
+        fname = _Tracer._UFUNCS.get(name)
+        if fname is None:
+            raise AttributeError(name)
+        sp = _sympy()
+        return lambda: _Tracer(getattr(sp, fname)(self.e))
+
+    def square(self):
+        return _Tracer(self.e ** 2)
+
+    def reciprocal(self):
+        return _Tracer(1 / self.e)
+
+    def __add__(self, o): return _Tracer(self.e + self._un(o))                     # noqa: E704
+    def __radd__(self, o): return _Tracer(self._un(o) + self.e)                    # noqa: E704
+    def __sub__(self, o): return _Tracer(self.e - self._un(o))                     # noqa: E704
+    def __rsub__(self, o): return _Tracer(self._un(o) - self.e)                    # noqa: E704
+    def __mul__(self, o): return _Tracer(self.e * self._un(o))                     # noqa: E704
+    def __rmul__(self, o): return _Tracer(self._un(o) * self.e)                    # noqa: E704
+    def __truediv__(self, o): return _Tracer(self.e / self._un(o))                 # noqa: E704
+    def __rtruediv__(self, o): return _Tracer(self._un(o) / self.e)                # noqa: E704
+    def __pow__(self, o): return _Tracer(self.e ** self._un(o))                    # noqa: E704
+    def __rpow__(self, o): return _Tracer(self._un(o) ** self.e)                   # noqa: E704
+    def __neg__(self): return _Tracer(-self.e)                                     # noqa: E704
+    def __pos__(self): return self                                                 # noqa: E704
+    def __abs__(self): return _Tracer(_sympy().Abs(self.e))                        # noqa: E704
+
+    def _needs_value(self, *a, **k):
+        raise TypeError("the function needs the VALUE of a parameter (a comparison, float() or int())")
+
+    __bool__ = __float__ = __int__ = __index__ = _needs_value
+    __lt__ = __le__ = __gt__ = __ge__ = _needs_value
+
+    def _sympy_(self):
+        return self.e
+
+
+def _unwrap_matrix(ret):
+    """whatever the function returned -> sympy Matrix (2-D; scalars (1,1), vectors columns)"""
+    sp = _sympy()
+    if isinstance(ret, _Tracer):
+        ret = ret.e
+    if is_symbolic(ret):
+        return sp.Matrix(ret) if isinstance(ret, sp.MatrixBase) else sp.Matrix([[ret]])
+    arr = np.asarray(atleast_2d_col(ret), dtype=object)
+    if arr.ndim != 2:
+        raise TypeError("expected a 2-D matrix, got %d dimensions" % arr.ndim)
+    return sp.Matrix(arr.shape[0], arr.shape[1],
+                     lambda i, j: arr[i, j].e if isinstance(arr[i, j], _Tracer) else sp.sympify(arr[i, j]))
+
+
 def _trace_function(func):
-    """Python matrix function -> sympy Matrix, by calling it with one Symbol per argument.  The reference calls such
-    functions with floats on the host (utils/matrix_utils.py:334-337, 441-470); on the GPU path the function has to be
-    expressible in sympy arithmetic, which holds for functions written with + - * / ** and sympy functions."""
+    """Python matrix function -> sympy Matrix, by calling it with one symbolic tracer per argument.  The reference
+    calls such functions with floats on the host (utils/matrix_utils.py:334-337, 441-470); on the GPU path the function
+    has to be expressible as arithmetic and elementary functions of its arguments -- written with Python operators,
+    numpy ufuncs or sympy functions -- and must not branch on their values."""
     sp = _sympy()
     spec = inspect.getfullargspec(func)
     if spec.varargs or spec.varkw:
@@ -351,17 +452,18 @@ def _trace_function(func):
     names = [n for n in list(spec.args) + list(spec.kwonlyargs) if n != "param_struct"]
     if inspect.ismethod(func):
         names = names[1:]
-    syms = {n: sp.Symbol(n) for n in names}
-    try:
-        ret = func(**syms)
-    except Exception as exc:  # numpy ufuncs on symbols, branches on values, ...
-        raise TypeError("matrix function %s() cannot be traced symbolically (%s: %s); write it with sympy "
-                        "arithmetic or pass the sympy matrix itself" % (func.__name__, type(exc).__name__, exc))
-    try:
-        mat = sp.Matrix(np.asarray(atleast_2d_col(ret), dtype=object).tolist()) if not is_symbolic(ret) \
-            else sp.Matrix(ret)
-    except Exception as exc:
-        raise TypeError("matrix function %s() did not return a matrix of constant shape: %s" % (func.__name__, exc))
+    last = None
+    for make in (lambda n: sp.Symbol(n), lambda n: _Tracer(sp.Symbol(n))):
+        try:
+            ret = func(**{n: make(n) for n in names})
+            mat = _unwrap_matrix(ret)
+            break
+        except Exception as exc:  # numpy ufuncs on plain symbols, branches on values, ragged returns, ...
+            last = exc
+    else:
+        raise TypeError("matrix function %s() cannot be traced symbolically (%s: %s); write it with arithmetic, numpy "
+                        "ufuncs or sympy functions of its arguments, or pass the sympy matrix itself"
+                        % (func.__name__, type(last).__name__, last))
     return mat, tuple(names)
 
 

@@ -165,6 +165,29 @@ def test_python_functions_are_traced():
 
     assert isinstance(CallableMatrix(lambda: np.eye(2)), CallableMatrixConstant)
 
+    def A_numpy(alpha, ts):                                # written the way users of the reference write them
+        a = np.exp(-alpha * ts)
+        row = np.array([a, np.sqrt(1 + alpha ** 2)])
+        return np.array([[a, np.sqrt(1 + alpha ** 2), np.maximum(alpha, 1.0)],
+                         [(a - 1) / (-alpha), np.tanh(ts) * np.abs(alpha - 2),
+                          np.arctan2(alpha, ts) + np.minimum(ts, alpha) ** 2],
+                         [np.power(alpha, 1.5), 2.0 * row[1] - row[0], np.sum(row * np.array([1.0, 2.0]))]])
+
+    cm = CallableMatrix(A_numpy, "A")
+    assert cm.shape == (3, 3) and cm.required_params == ["alpha", "ts"]
+    params = np.array([[0.3, 2.0], [1.5, 0.25], [2.5, 3.0]])
+    out = twin.run_program(cm.program, params)["A"]
+    for i, (al, ts) in enumerate(params):
+        np.testing.assert_allclose(out[i], A_numpy(al, ts), rtol=1e-14, atol=0)
+
+    def keyword_only(alpha, *, ts, param_struct=None):
+        return np.exp(-alpha * ts)                         # a scalar -> (1, 1)
+
+    cm = CallableMatrix(keyword_only)
+    assert cm.shape == (1, 1) and cm.required_params == ["alpha", "ts"] and cm.matrix_name == "keyword_only"
+    with pytest.raises(TypeError, match="heaviside has no GPU instruction"):
+        CallableMatrix(lambda x: [[np.heaviside(x, 0.5)]])
+
     def branches_on_value(x):
         return [[1.0 if x > 0 else 2.0]]
 
