@@ -8,6 +8,7 @@ certainty-equivalent and a perfect-forecast controller.  cvxpy's modelling layer
 
 Run in the build container only:   python tests/golden/make_golden_microgrid.py
 """
+import importlib
 import itertools
 import os
 import sys
@@ -66,10 +67,27 @@ def main():
     grid.add_device(resd)
     dewhs = [d for d in grid.devices if isinstance(d, ag.DewhAgentMpc)]
 
-    import importlib
     thermo_mod = importlib.import_module("examples.residential_mg_with_pv_and_dewhs.theromstat_control")
     no_ctrl = importlib.import_module("controllers.no_controller").NoController
-    controllers = dict(mpc_ce=False, mpc_pb=True, thermo=False)               # name -> is_deterministic
+    # name -> is_deterministic, in the order of the reference script (micro_grid_control_simulation.py:144-152, 266)
+    controllers = dict(mpc_pb=True, mpc_ce=False, mpc_sb_reduced=False, mpc_sb_full=False, mpc_minmax=False,
+                       thermo=False)
+    num_scenarios, N_sb_reduced = 5, 4
+    scen_days = rng.uniform(0, 0.02, (96, 30)) * (rng.random((96, 30)) < 0.35)
+    for dev in grid.devices:
+        if isinstance(dev, ag.DewhAgentMpc):
+            dev.set_omega_scenarios(omega_scenarios_profile=scen_days.flatten(order="f"))
+    min_day, max_day = scen_days.min(axis=1), scen_days.max(axis=1)
+    import ast
+    path = os.path.join(ref_shim.REFERENCE_ROOT, "examples", "residential_mg_with_pv_and_dewhs",
+                        "micro_grid_control_simulation.py")
+    fn = [n for n in ast.parse(open(path).read()).body
+          if isinstance(n, ast.FunctionDef) and n.name == "get_min_max_dhw_scenario"]
+    ns = dict(np=np, steps_per_day=96, atleast_2d_col=importlib.import_module("utils.matrix_utils").atleast_2d_col)
+    exec(compile(ast.Module(body=fn, type_ignores=[]), path, "exec"), ns)
+    get_min_max_dhw_scenario = ns["get_min_max_dhw_scenario"]
+    scen_log = {c: [] for c in controllers if c.startswith("mpc_sb")}
+    seed = 20261018
     for cname in controllers:
         for dev in itertools.chain([grid], grid.devices):
             if cname != "thermo":
@@ -92,6 +110,7 @@ def main():
     logs = {c: dict(obj=[], u=[], T=[], T_next=[], mu=[], grid_y=[], grid_z=[], grid_delta=[], cost=[], u_plan=[],
                     z_plan=[], grid_omega=[]) for c in controllers}
     grid.build_grid(k=0, deterministic_or_struct=controllers)
+    np.random.seed(seed)                                   # the scenario draws use numpy's global generator
     for k in range(steps):
         prices_tilde = grid.get_price_tilde_k(k=k)
         for cname in controllers:
@@ -102,6 +121,21 @@ def main():
                     max_cost = np.sum(prices_tilde[cname]) * R.params.dewh_param_struct.P_h_Nom
                     dev.set_device_objective_atoms(controller_name=cname,
                                                    q_mu=np.hstack([max_cost * soft_top, max_cost * soft_bot]).ravel(order="c"))
+                    ctrl = dev.controllers[cname]
+                    if cname.startswith("mpc_sb"):         # micro_grid_control_simulation.py:199-213
+                        sc = dev.get_omega_tilde_scenario(k, N_tilde=Nt, num_scenarios=num_scenarios)
+                        scen_log[cname].append(sc)
+                        if cname == "mpc_sb_reduced":
+                            ctrl.set_constraints(other_constraints=[
+                                ctrl.gen_evo_constraints(N_tilde=N_sb_reduced, omega_scenarios_k=sc)])
+                        else:
+                            ctrl.set_constraints(other_constraints=[ctrl.gen_evo_constraints(omega_scenarios_k=sc)])
+                    elif cname == "mpc_minmax":            # :215-227
+                        omega_min, omega_max = get_min_max_dhw_scenario(k=k, N_tilde=Nt, min_dhw_day=min_day,
+                                                                        max_dhw_day=max_day)
+                        ctrl.set_constraints(other_constraints=[
+                            ctrl.gen_evo_constraints(N_tilde=Nt, omega_tilde_k=omega_min),
+                            ctrl.gen_evo_constraints(N_tilde=Nt, omega_tilde_k=omega_max)])
                 elif isinstance(dev, ag.GridAgentMpc):
                     dev.controllers[cname].set_std_obj_atoms(q_z=prices_tilde[cname])
         grid.build_grid(k=k, deterministic_or_struct=controllers)
@@ -128,6 +162,10 @@ def main():
     for c, lg in logs.items():
         for key, val in lg.items():
             data["%s_%s" % (c, key)] = np.array(val, dtype=float)
+    for c, lst in scen_log.items():
+        data["scen_" + c] = np.array(lst).reshape(steps, N_h, Nt, num_scenarios)
+    data.update(scen_days=scen_days, num_scenarios=np.array(num_scenarios), N_sb_reduced=np.array(N_sb_reduced),
+                seed=np.array(seed))
     df = grid.grid_sim_dataframe
     data["frame_columns"] = np.array(["|".join(str(x) for x in col) for col in df.columns])
     data["frame_values"] = np.array(df.values, dtype=float)

@@ -1,7 +1,8 @@
 """CPU: the oracle's CENTRALISED micro-grid problem (oracle/coupled.py), device simulation steps and grid bookkeeping
 against the UNMODIFIED reference's own example loop on a small micro-grid -- GridAgentMpc.build_grid / solve_grid_mpc /
-sim_step_k with four water heaters, a PV plant and a residential demand, a certainty-equivalent and a perfect-forecast
-controller, three instants (tests/golden/microgrid_loop.npz, tests/golden/make_golden_microgrid.py; cvxpy's modelling
+sim_step_k with four water heaters, a PV plant and a residential demand, the six controllers of the reference's
+campaign side by side (perfect forecast, certainty equivalent, scenario-based reduced / full, min-max, thermostat),
+three instants (tests/golden/microgrid_loop.npz, tests/golden/make_golden_microgrid.py; cvxpy's modelling
 layer = oracle/mini_cvxpy.py, MILP backend = HiGHS).  The forecast / actual / price windows come from the product's
 input-side module (examples/.../profiles.py), so this also checks that module inside the loop."""
 import os
@@ -24,6 +25,32 @@ KEYS = ("C_w", "A_h", "U_h", "m_h", "T_w", "T_inf", "P_h_Nom", "T_h_min", "T_h_m
 MPC = [i for i, c in enumerate(G["controllers"]) if str(c).startswith("mpc")]
 
 
+def scenario_draws():
+    """(controller, k) -> [N_h, Nt, S]: the reference draws every heater's scenario set from numpy's GLOBAL generator,
+    inside its loops over instants, controllers and devices (micro_grid_control_simulation.py:184-201); the same seed
+    and the same call order through examples/.../profiles.py give the same sets."""
+    N_h, Nt, steps, S = int(G["N_h"]), int(G["N_p"]) + 1, int(G["steps"]), int(G["num_scenarios"])
+    sc = P.OmegaScenarios(G["scen_days"].flatten(order="F"), 900.0)
+    state = np.random.get_state()
+    try:
+        np.random.seed(int(G["seed"]))
+        out = {}
+        for k in range(steps):
+            for cname in (str(c) for c in G["controllers"]):
+                if cname.startswith("mpc_sb"):
+                    out[(cname, k)] = sc.fleet_scenarios(k, Nt, S, N_h)
+    finally:
+        np.random.set_state(state)
+    return out, sc
+
+
+def test_scenario_draws_of_the_loop_are_reproduced():
+    draws, _ = scenario_draws()
+    assert len(draws) == 2 * int(G["steps"])
+    for (cname, k), arr in draws.items():
+        assert np.array_equal(arr, G["scen_" + cname][k]), (cname, k)
+
+
 @pytest.mark.parametrize("ci", MPC)
 def test_centralised_loop_against_the_reference(ci):
     cname, det = str(G["controllers"][ci]), bool(G["deterministic"][ci])
@@ -42,15 +69,27 @@ def test_centralised_loop_against_the_reference(ci):
         full, dims, vt = omld.complete(ol.dewh_mld(p, const_heat=True), nu_l=1)
         models.append((oc.condense(full, dims, Nt), dims, vt))
     T = G["x0"].astype(float).copy()
+    draws, scen = scenario_draws()
+    lo_day, hi_day = scen.min_max_day()
     for k in range(steps):
         pk = price.price_tilde_k(k, Nt)
         w = dewh.omega_tilde_k_hat(k, Nt, deterministic=det)
+        # the constraint sets a controller variant adds to every heater (micro_grid_control_simulation.py:199-227)
+        if cname == "mpc_sb_reduced":
+            extra = [[dict(omega_scenarios=draws[(cname, k)][i], N_tilde=int(G["N_sb_reduced"]))] for i in range(N_h)]
+        elif cname == "mpc_sb_full":
+            extra = [[dict(omega_scenarios=draws[(cname, k)][i])] for i in range(N_h)]
+        elif cname == "mpc_minmax":
+            lo, hi = P.get_min_max_dhw_scenario(k, Nt, lo_day, hi_day)
+            extra = [[dict(omega_t=lo[:, 0]), dict(omega_t=hi[:, 0])]] * N_h
+        else:
+            extra = [[]] * N_h
         p_other = float(G["pv_gain"]) * pv.omega_tilde_k_hat(k, Nt, deterministic=det)[0] + \
             float(G["resd_gain"]) * resd.omega_tilde_k_hat(k, Nt, deterministic=det)[0]
         max_cost = pk.sum() * 3000.0                       # the script uses the base P_h_Nom for every heater (:196)
         q_mu = np.array([max_cost * G["soft"][0], max_cost * G["soft"][1]])
         np.testing.assert_allclose(T, G[cname + "_T"][k], rtol=1e-12)
-        agents = [oa.build_problem(evo, dims, vt, Nt, [T[i]], w[i], atoms=dict(q_mu=q_mu))
+        agents = [oa.build_problem(evo, dims, vt, Nt, [T[i]], w[i], atoms=dict(q_mu=q_mu), extra_constraints=extra[i])
                   for i, (evo, dims, vt) in enumerate(models)]
         prob, offs, n_agents = ocp.build_coupled_problem(agents, P_nom, p_other, pk, grid_params)
         status, obj, v = osv.solve_milp(prob, polish=True)
