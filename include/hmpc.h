@@ -244,7 +244,12 @@ enum { HMPC_EXPR_CONST = 0, HMPC_EXPR_PARAM = 1, HMPC_EXPR_OUT = 2,
        HMPC_EXPR_MAX, HMPC_EXPR_ATAN2 };
 int hmpc_param_eval_f64(int32_t B, int32_t n_params, int32_t n_regs, int32_t n_ins, const hmpc_expr_ins* program,
                         int32_t n_mats, const int32_t* mat_sizes, const double* params, double* out, void* stream);
-/* algorithmic bytes per agent of the call above: 8 (n_params + sum of sizes) -- the kernel is HBM-bound */
+/* EXPERIMENTAL variant, opt-in, NOT yet run on a B200 (pyhybridcontrol_b200: HMPC_PARAM_EVAL=v2): same contract, but
+ * registers 0 .. n_params-1 hold the parameters on entry (n_regs counts them; they must not be written), PARAM
+ * instructions are not allowed, and every thread evaluates two agents (one decode, two evaluations).            */
+int hmpc_param_eval_v2_f64(int32_t B, int32_t n_params, int32_t n_regs, int32_t n_ins, const hmpc_expr_ins* program,
+                           int32_t n_mats, const int32_t* mat_sizes, const double* params, double* out, void* stream);
+/* algorithmic bytes per agent of the calls above: 8 (n_params + sum of sizes) -- HBM-bound by design */
 int64_t hmpc_param_eval_bytes_per_agent(int32_t n_params, int32_t n_mats, const int32_t* mat_sizes);
 
 /* ---- K6 aggregate power: replaces GridAgentMpc.get_grid_device_powers_N_tilde + GridModel D4 = ones

@@ -22,7 +22,7 @@ EXPORTS = ("hmpc_version", "hmpc_last_cuda_error", "hmpc_device_info", "hmpc_con
            "hmpc_milp_default_opts", "hmpc_milp_workspace_bytes", "hmpc_milp_solve_f64", "hmpc_stage_dp_default_opts",
            "hmpc_stage_dp_supported", "hmpc_stage_dp_workspace_bytes", "hmpc_stage_dp_solve_f64", "hmpc_lsim_step_f64",
            "hmpc_dewh_sim_step_f64", "hmpc_dewh_control_model_f64", "hmpc_dewh_thermostat_f64",
-           "hmpc_param_eval_f64", "hmpc_param_eval_bytes_per_agent",
+           "hmpc_param_eval_f64", "hmpc_param_eval_v2_f64", "hmpc_param_eval_bytes_per_agent",
            "hmpc_aggregate_power_f64", "hmpc_coupling_price_cost_f64", "hmpc_coupling_sums_f64",
            "hmpc_coupling_dual_step_f64", "hmpc_coupling_keep_best_f64", "hmpc_coupling_response_cost_f64",
            "hmpc_coupling_merge_f64", "hmpc_coupling_accept_f64", "hmpc_coupling_restore_f64", "hmpc_step_plan_create", "hmpc_step_plan_destroy", "hmpc_mpc_step_host_f64", "hmpc_mpc_step_host_bytes",
@@ -101,6 +101,7 @@ _lib.hmpc_dewh_sim_step_f64.argtypes = [C.c_int32] + [_P] * 8
 _lib.hmpc_dewh_control_model_f64.argtypes = [C.c_int32, _P, _P, _P]
 _lib.hmpc_dewh_thermostat_f64.argtypes = [C.c_int32, _P, _P, C.c_int64, _P, _P, _P, _P]
 _lib.hmpc_param_eval_f64.argtypes = [C.c_int32] * 4 + [_P, C.c_int32, C.POINTER(C.c_int32), _P, _P, _P]
+_lib.hmpc_param_eval_v2_f64.argtypes = _lib.hmpc_param_eval_f64.argtypes
 _lib.hmpc_param_eval_bytes_per_agent.argtypes = [C.c_int32, C.c_int32, C.POINTER(C.c_int32)]
 _lib.hmpc_param_eval_bytes_per_agent.restype = C.c_int64
 _lib.hmpc_aggregate_power_f64.argtypes = [C.c_int32, C.c_int32, _P, C.c_int64, C.c_int32, _P, _P, _P, _P]
@@ -438,10 +439,11 @@ def dewh_control_model(params):
     return model
 
 
-def param_eval(program, n_regs, mat_sizes, params, out=None):
+def param_eval(program, n_regs, mat_sizes, params, out=None, version=1):
     """Symbolic / callable model front-end (hmpc.h: hmpc_param_eval_f64).  program: CUDA int32 tensor [n_ins, 4];
     params: CUDA float64 [B, P]; returns the flat output buffer, matrix m at [B*off_m, B*(off_m+size_m)) as
-    [B, size_m]."""
+    [B, size_m].  version=2: the experimental kernel (parameters preloaded as registers 0..P-1, two agents per
+    thread; hmpc_param_eval_v2_f64) -- the program must be in that form (ExprProgram.instructions_v2)."""
     global launch_count
     if program.dtype != torch.int32 or program.dim() != 2 or program.shape[1] != 4:
         raise ValueError("program must be an int32 tensor [n_ins, 4]")
@@ -454,8 +456,9 @@ def param_eval(program, n_regs, mat_sizes, params, out=None):
         out = torch.empty((B * n_out,), dtype=torch.float64, device=params.device)
     elif out.numel() != B * n_out or out.dtype != torch.float64:
         raise ValueError("out must hold B * sum(mat_sizes) doubles")
-    _check(_lib.hmpc_param_eval_f64(B, P, int(n_regs), program.shape[0], _ptr(program), len(mat_sizes), sizes,
-                                    _ptr(params) if P else None, _ptr(out), _stream()), "hmpc_param_eval_f64")
+    fn = _lib.hmpc_param_eval_f64 if int(version) == 1 else _lib.hmpc_param_eval_v2_f64
+    _check(fn(B, P, int(n_regs), program.shape[0], _ptr(program), len(mat_sizes), sizes,
+              _ptr(params) if P else None, _ptr(out), _stream()), "hmpc_param_eval_f64 (version %d)" % int(version))
     launch_count += 1
     return out
 

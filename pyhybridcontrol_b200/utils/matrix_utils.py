@@ -15,6 +15,7 @@ that + - * / round exactly as in the reference and only exp / log / pow / trig d
 Nothing here computes matrix values on the host: evaluation always goes through the CUDA library.
 """
 import inspect
+import os
 import struct
 
 import numpy as np
@@ -59,11 +60,12 @@ def _const_bits(value):
 class _Emitter(object):
     """Expression trees -> instructions over virtual registers, with structural sharing of sub-expressions."""
 
-    def __init__(self, param_index):
+    def __init__(self, param_index, preload_params=False):
         self.param_index = param_index
+        self.preload = bool(preload_params)   # parameters ARE virtual registers 0..P-1 (no PARAM instructions)
         self.ins = []              # [op, dst, a, b] over virtual registers
         self.memo = {}
-        self.n_vregs = 0
+        self.n_vregs = len(param_index) if self.preload else 0
 
     def _new(self, op, a=0, b=0):
         dst = self.n_vregs
@@ -98,6 +100,8 @@ class _Emitter(object):
             name = str(e)
             if name not in self.param_index:
                 raise KeyError("symbol %r is not a parameter of this program" % name)
+            if self.preload:
+                return self.param_index[name]
             return self._new(OP_PARAM, self.param_index[name])
         if e.is_number:
             if e is sp.nan:
@@ -186,8 +190,9 @@ class _Emitter(object):
         return self._new(OP_POW, self.emit(base), self.emit(ex))
 
 
-def _allocate_registers(ins):
-    """Dead values dropped, then a linear scan virtual -> physical registers: a register is free after the last read
+def _allocate_registers(ins, n_pinned=0):
+    """``n_pinned`` leading virtual registers (preloaded parameters) keep their numbers and are never reused.
+    Dead values dropped, then a linear scan virtual -> physical registers: a register is free after the last read
     of its value, and the destination of an instruction may reuse a source that dies there (the kernel reads both
     operands before it writes)."""
     live, kept = set(), []
@@ -201,13 +206,13 @@ def _allocate_registers(ins):
     for i, (op, dst, a, b) in enumerate(kept):
         for r in _reads(op, dst, a, b):
             last_use[r] = i
-    free, phys, n_phys, out = [], {}, 0, []
+    free, phys, n_phys, out = [], {r: r for r in range(n_pinned)}, n_pinned, []
     for i, (op, dst, a, b) in enumerate(kept):
         reads = set(_reads(op, dst, a, b))
         pa = phys[a] if a in reads else a
         pb = phys[b] if (op >= OP_ADD and b in reads) else b
         for r in reads:
-            if last_use[r] == i:
+            if last_use[r] == i and r >= n_pinned:
                 free.append(phys.pop(r))
         if op == OP_OUT:
             out.append((op, dst, pa, 0))
@@ -258,28 +263,43 @@ class ExprProgram(object):
         self.mat_shapes = tuple(tuple(int(s) for s in m.shape) for _, m in mats)
         self.mat_sizes = tuple(r * c for r, c in self.mat_shapes)
         self.n_out = int(sum(self.mat_sizes))
-        em = _Emitter({n: i for i, n in enumerate(self.param_names)})
+        self._mats = mats
+        ins, self.n_regs = self._compile(preload_params=False)
+        if not ins:
+            raise ValueError("all matrices of the program are empty")
+        self.instructions = np.array(ins, dtype=np.int32).reshape(-1, 4)
+        self.n_ins = int(self.instructions.shape[0])
+        self._v2 = None
+        self._dev = {}
+
+    def _compile(self, preload_params):
+        em = _Emitter({n: i for i, n in enumerate(self.param_names)}, preload_params=preload_params)
         slot = 0
-        for _, m in mats:
+        for _, m in self._mats:
             rows, cols = m.shape
             for i in range(rows):
                 for j in range(cols):
                     reg = em.emit(m[i, j])
                     em.ins.append([OP_OUT, slot, reg, 0])
                     slot += 1
-        if not em.ins:
-            raise ValueError("all matrices of the program are empty")
-        ins, self.n_regs = _allocate_registers(em.ins)
-        self.instructions = np.array(ins, dtype=np.int32).reshape(-1, 4)
-        self.n_ins = int(self.instructions.shape[0])
-        self._dev = {}
+        return _allocate_registers(em.ins, n_pinned=len(self.param_names) if preload_params else 0)
+
+    @property
+    def instructions_v2(self):
+        """(instructions, n_regs) for the experimental kernel hmpc_param_eval_v2_f64: registers 0..P-1 are the
+        parameters (preloaded, never written), no PARAM instructions; same operations in the same order otherwise."""
+        if self._v2 is None:
+            ins, n_regs = self._compile(preload_params=True)
+            self._v2 = (np.array(ins, dtype=np.int32).reshape(-1, 4), max(n_regs, len(self.param_names) + 1))
+        return self._v2
 
     # ---- device side -----------------------------------------------------------------------------------------
-    def _program_on(self, device):
+    def _program_on(self, device, version=1):
         import torch
-        key = str(device)
+        key = (str(device), int(version))
         if key not in self._dev:
-            self._dev[key] = torch.from_numpy(self.instructions.copy()).to(device)
+            ins = self.instructions if version == 1 else self.instructions_v2[0]
+            self._dev[key] = torch.from_numpy(ins.copy()).to(device)
         return self._dev[key]
 
     def param_table(self, param_struct, overrides=None, B=None, device="cuda"):
@@ -305,12 +325,19 @@ class ExprProgram(object):
                     tab[:, j] = 0.0
         return torch.from_numpy(tab).to(device)
 
-    def evaluate(self, params):
-        """params: CUDA float64 tensor [B, P] -> dict name -> CUDA tensor [B, rows, cols] (views of one buffer)."""
+    def evaluate(self, params, version=None):
+        """params: CUDA float64 tensor [B, P] -> dict name -> CUDA tensor [B, rows, cols] (views of one buffer).
+        version: 1 = hmpc_param_eval_f64 (default); 2 = the experimental kernel (also HMPC_PARAM_EVAL=v2)."""
         from .. import cabi
         if params.dim() != 2 or params.shape[1] != len(self.param_names):
             raise ValueError("params must be [B, %d]" % len(self.param_names))
-        flat = cabi.param_eval(self._program_on(params.device), self.n_regs, self.mat_sizes, params)
+        if version is None:
+            version = 2 if os.environ.get("HMPC_PARAM_EVAL", "v1").lower() in ("v2", "2") else 1
+        if int(version) == 1:
+            flat = cabi.param_eval(self._program_on(params.device), self.n_regs, self.mat_sizes, params)
+        else:
+            flat = cabi.param_eval(self._program_on(params.device, 2), self.instructions_v2[1], self.mat_sizes, params,
+                                   version=2)
         B = params.shape[0]
         out, off = {}, 0
         for name, (r, c), sz in zip(self.mat_names, self.mat_shapes, self.mat_sizes):

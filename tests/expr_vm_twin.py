@@ -27,18 +27,21 @@ def _powi(x, n):
     return 1.0 / r if n < 0 else r
 
 
-def valid(instructions, n_regs, n_params, n_out):
+def valid(instructions, n_regs, n_params, n_out, preload=False):
+    """the checks the kernels make while loading a program; preload = the experimental kernel's form (parameters are
+    registers 0..P-1, never written, no PARAM instruction)"""
+    lo = n_params if preload else 0
     for op, dst, a, b in np.asarray(instructions).tolist():
         if op == mu.OP_OUT:
             ok = 0 <= dst < n_out and 0 <= a < n_regs
         elif op == mu.OP_CONST:
-            ok = 0 <= dst < n_regs
+            ok = lo <= dst < n_regs
         elif op == mu.OP_PARAM:
-            ok = 0 <= dst < n_regs and 0 <= a < n_params
+            ok = (not preload) and 0 <= dst < n_regs and 0 <= a < n_params
         elif op in _UNARY or op == mu.OP_POWI:
-            ok = 0 <= dst < n_regs and 0 <= a < n_regs
+            ok = lo <= dst < n_regs and 0 <= a < n_regs
         elif op in _BINARY:
-            ok = 0 <= dst < n_regs and 0 <= a < n_regs and 0 <= b < n_regs
+            ok = lo <= dst < n_regs and 0 <= a < n_regs and 0 <= b < n_regs
         else:
             ok = False
         if not ok:
@@ -51,7 +54,7 @@ LIBRARY_OPS = frozenset((mu.OP_EXP, mu.OP_LOG, mu.OP_SIN, mu.OP_COS, mu.OP_TAN, 
                          mu.OP_SINH, mu.OP_COSH, mu.OP_TANH, mu.OP_POW, mu.OP_ATAN2))
 
 
-def run(instructions, n_regs, mat_sizes, params, noise=None, noise_ulps=2):
+def run(instructions, n_regs, mat_sizes, params, noise=None, noise_ulps=2, preload=False):
     """params [B, P] -> flat buffer laid out like hmpc_param_eval_f64's out (matrix m = [B, size_m] block).
 
     ``noise``: a numpy Generator -- every library-function result is moved by a random integer number of ulps in
@@ -61,8 +64,10 @@ def run(instructions, n_regs, mat_sizes, params, noise=None, noise_ulps=2):
     B, P = params.shape
     n_out = int(sum(mat_sizes))
     slots = np.full((n_out, B), np.nan)
-    if valid(instructions, n_regs, P, n_out):
+    if valid(instructions, n_regs, P, n_out, preload=preload):
         regs = np.zeros((n_regs, B))
+        if preload:
+            regs[:P] = params.T
         with np.errstate(all="ignore"):
             for op, dst, a, b in np.asarray(instructions).tolist():
                 if op == mu.OP_OUT:

@@ -273,3 +273,33 @@ def test_c_abi_argument_validation_without_gpu():
     assert f(4, 0, 1, 2, prog, 2, sizes, None, None, None) == -1              # outputs expected, no buffer
     assert f(0, 0, 1, 2, prog, 2, sizes, None, None, None) == 0               # empty batch: nothing to do
     assert cabi.param_eval_bytes_per_agent(13, [1, 1, 1, 1, 2]) == 8 * 19
+
+
+@pytest.mark.parametrize("fixture", FIXTURES)
+def test_register_preloaded_program_form_is_equivalent(fixture):
+    """the program form of the experimental kernel (hmpc_param_eval_v2_f64: parameters preloaded as registers 0..P-1,
+    no PARAM instructions) performs the same operations in the same order: identical results to the last bit"""
+    z, names, mats, pnames = load_fixture(fixture)
+    prog = ExprProgram(mats, param_names=pnames)
+    ins2, R2 = prog.instructions_v2
+    P = len(pnames)
+    assert twin.valid(ins2, R2, P, prog.n_out, preload=True)
+    assert not np.any(ins2[:, 0] == mu.OP_PARAM) and ins2.shape[0] < prog.n_ins
+    writes = ins2[ins2[:, 0] != mu.OP_OUT][:, 1]
+    assert writes.size == 0 or writes.min() >= P                       # parameters are never overwritten
+    a = twin.run(prog.instructions, prog.n_regs, prog.mat_sizes, z["params"])
+    b = twin.run(ins2, R2, prog.mat_sizes, z["params"], preload=True)
+    assert np.array_equal(a, b, equal_nan=True)
+    # the v1 form is not a valid v2 program and vice versa where parameters exist
+    if P:
+        assert not twin.valid(prog.instructions, prog.n_regs, P, prog.n_out, preload=True)
+
+
+def test_c_abi_v2_argument_validation_without_gpu():
+    from pyhybridcontrol_b200 import cabi
+    f = cabi.lib().hmpc_param_eval_v2_f64
+    sizes = (ctypes.c_int32 * 1)(1)
+    prog = (ctypes.c_int32 * 8)()
+    assert f(4, 2, 2, 2, prog, 1, sizes, None, None, None) == -1               # n_regs must exceed n_params
+    assert f(4, 0, 1, 2, None, 1, sizes, None, None, None) == -1               # no program
+    assert f(0, 2, 3, 2, prog, 1, sizes, prog, None, None) == 0                # empty batch

@@ -284,3 +284,30 @@ def test_controller_on_a_symbolic_model_and_batch_from_front_end(cuda_device):
     # a parameter change re-evaluates the model and asks for a rebuild (controller_base.py:503-505)
     sym_ctrl.control_model.update_param_struct(T_h_max=p0["T_h_max"] + 5.0)
     assert sym_ctrl.build_required
+
+
+@pytest.mark.skipif(__import__("os").environ.get("HMPC_EXPERIMENTAL", "0") != "1",
+                    reason="experimental kernel hmpc_param_eval_v2_f64: opt-in (HMPC_EXPERIMENTAL=1), not yet run on a B200")
+def test_experimental_kernel_v2_matches_v1(cuda_device):
+    """parameters preloaded as registers + two agents per thread: bit-identical to the first kernel (same operations,
+    same order, same math functions), on the golden fixtures, ragged tiles and the fuzz programs"""
+    import torch
+    from pyhybridcontrol_b200.utils.matrix_utils import ExprProgram
+    cases = []
+    for fixture in FIXTURES:
+        z, names, mats, pnames = load_fixture(fixture)
+        cases.append((ExprProgram(mats, param_names=pnames), z["params"]))
+    z, names, mats, pnames = load_fixture("callable_dewh_sim.npz")
+    prog = ExprProgram(mats, param_names=pnames)
+    rng = np.random.default_rng(5)
+    for B in (1, 63, 64, 65, 257, 9473, 80001):
+        params = np.tile(z["params"][0], (B, 1)) * (1.0 + 0.05 * rng.uniform(-1, 1, size=(B, len(pnames))))
+        params[:, pnames.index("T_h")] = rng.uniform(20, 85, B)
+        cases.append((prog, params))
+    cases += [(p, x) for _, p, x in fuzz_cases()]
+    for prog, params in cases:
+        t = torch.as_tensor(np.ascontiguousarray(params), dtype=torch.float64).to(cuda_device)
+        a = {k: v.cpu().numpy() for k, v in prog.evaluate(t, version=1).items()}
+        b = {k: v.cpu().numpy() for k, v in prog.evaluate(t, version=2).items()}
+        for k in a:
+            assert np.array_equal(a[k], b[k], equal_nan=True), k
