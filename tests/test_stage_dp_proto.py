@@ -58,3 +58,39 @@ def test_bound_pruned_search_is_exact(N_p, cells):
         assert st == osv.OPTIMAL and abs(obj + prob.c0 - oref) <= 1e-6 * max(1.0, abs(oref)), (b, obj, oref, nodes)
         assert np.array_equal(u, np.round(vref[prob.is_bin]))
         assert nodes < 200000
+
+
+# ---- the round-2 candidate: nodal piecewise-linear bound (tools/stage_dp_pwl_proto.py) --------------------------
+from stage_dp_pwl_proto import StageDpPwl  # noqa: E402
+
+
+@pytest.mark.parametrize("cells", [64, 512])
+@pytest.mark.parametrize("x0_shift", [0.0, -12.0, 14.0])     # nominal / cold start / above the upper limit
+def test_piecewise_linear_table_is_a_lower_bound(cells, x0_shift):
+    """the chord-deficiency construction is valid where it matters most: with slack penalties active"""
+    wl = syn.dewh_batch(3, 9, seed=17)
+    wl["x0"] = wl["x0"] + x0_shift
+    rng = np.random.default_rng(cells)
+    for b in range(3):
+        mats, prob = _problem(wl, b)
+        dp = StageDpPwl(*from_dewh_problem(mats, prob, wl["Nt"]), cells=cells)
+        for k in range(1, wl["Nt"]):
+            reach = {0.0}
+            for j in range(k):
+                reach |= {s + dp.shift[j] for s in reach}
+            states = list(reach)[:64] + list(dp.S0 + rng.uniform(0, 1, size=16) * dp.G * dp.w)
+            for s in states:
+                lb, true = dp.bound(k, s), dp.cost_to_go_exact(k, s)
+                assert lb <= true + 1e-9 * max(1.0, abs(true)), (b, k, s, lb, true)
+
+
+@pytest.mark.parametrize("N_p,cells", [(24, 4096), (48, 2048)])
+def test_search_with_the_piecewise_linear_bound_is_exact(N_p, cells):
+    wl = syn.dewh_batch(4, N_p, seed=23)
+    for b in range(4):
+        mats, prob = _problem(wl, b)
+        dp = StageDpPwl(*from_dewh_problem(mats, prob, wl["Nt"]), cells=cells)
+        obj, u, nodes = dp.solve()
+        st, oref, vref = osv.solve_milp(prob, polish=True)
+        assert st == osv.OPTIMAL and abs(obj + prob.c0 - oref) <= 1e-6 * max(1.0, abs(oref)), (b, obj, oref, nodes)
+        assert np.array_equal(u, np.round(vref[prob.is_bin]))
