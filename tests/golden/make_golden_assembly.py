@@ -149,6 +149,42 @@ def closed_loop_case(name, N_p, steps, seed):
     print(name, "u =", data["u"], "x_end =", data["x"][-1])
 
 
+def update_sequence_case(dewh, rng):
+    """MpcController.update_std_obj_atoms (controllers/mpc_controller.py:47-58, objective_atoms.py:498-521): weights
+    merged into existing atoms -- terminal weight next to a horizon weight, N_p weight over it, an all-zero weight
+    deleting the atom -- and the cost vector after every call"""
+    N_p, Nt = 6, 7
+    q_u = rng.uniform(1, 2, Nt)
+    steps = [("set", dict(q_u=q_u, q_mu=np.array([5.0, 1.0]))),
+             ("update", dict(q_u_f=np.array([9.0]), q_mu=np.array([7.0, 2.0]))),
+             ("update", dict(q_u_N_p=np.array([0.5]))),
+             ("update", dict(q_mu=np.zeros(2))),
+             ("update", dict(q_x=np.array([0.25]), q_u=2.0 * q_u)),
+             ("set", dict(q_mu=np.array([3.0, 4.0])))]
+    ctrl = R.MpcController(model=R.MldSystemModel(mld_numeric=dewh), N_p=N_p)
+    ctrl.x_k = 55.0
+    ctrl.omega_tilde_k = rng.uniform(0, 0.01, (Nt, 1))
+    data = dict(N_p=np.array(N_p), n_steps=np.array(len(steps)), x_k=np.array([55.0]),
+                omega_tilde=np.asarray(ctrl.omega_tilde_k.value if hasattr(ctrl.omega_tilde_k, "value")
+                                       else ctrl.omega_tilde_k, dtype=float).reshape(-1))
+    for k in MAT_NAMES:
+        data["in_" + k] = np.asarray(dewh[k], dtype=float)
+    for i, (how, kw) in enumerate(steps):
+        getattr(ctrl, "set_std_obj_atoms" if how == "set" else "update_std_obj_atoms")(**kw)
+        ctrl.build()
+        cf = ctrl.problem.canonical_form()
+        c = cf["c"]                                        # reference order: U (Nt) then Mu (2 Nt, step-major)
+        c_v = np.zeros(3 * Nt)
+        c_v[0::3], c_v[1::3], c_v[2::3] = c[:Nt], c[Nt:].reshape(Nt, 2)[:, 0], c[Nt:].reshape(Nt, 2)[:, 1]
+        data["how_%d" % i] = np.array(how)
+        data["keys_%d" % i] = np.array(list(kw))
+        for j, val in enumerate(kw.values()):
+            data["val_%d_%d" % (i, j)] = np.asarray(val, dtype=float)
+        data["c_v_%d" % i], data["c0_%d" % i] = c_v, np.array(cf["c0"])
+    np.savez_compressed(os.path.join(HERE, "assembly_update_sequence.npz"), **data)
+    print("update_sequence", len(steps), "calls")
+
+
 def random_mld(rng):
     """2 states, a continuous and a binary input, one delta, one z, 2 disturbances, 2 outputs, 5 rows, 3 slacks"""
     nx, nu, nd, nz, nw, ny, nc, nmu = 2, 2, 1, 1, 2, 2, 5, 3
@@ -210,6 +246,7 @@ def main():
              k_neg1=dict(z=[0.7]), seed=9, solve=False)
 
     closed_loop_case("dewh_closed_loop", N_p=10, steps=14, seed=21)
+    update_sequence_case(dewh, rng)
 
 
 if __name__ == "__main__":

@@ -97,3 +97,37 @@ def test_atoms_outside_the_stage_dp_class_are_refused():
             refused.append((atom.atom_type, atom.var_name, atom.is_rate_atom))
     assert ("L1", "u", True) in refused and any(a[0] == "Linf" for a in refused)
     assert not any(a[0] == "Linear" for a in refused)
+
+
+def test_update_std_obj_atoms_sequence():
+    """set / update calls one after the other (a terminal weight merged next to a horizon weight, an N_p weight over
+    it, an all-zero weight deleting the atom, an atom on x added later, a final set that replaces everything): the
+    cost vector and constant after every call equal the reference's"""
+    import os
+    from oracle import condense as oc, mld as omld
+    from test_oracle_assembly_pinned import GOLDEN
+    z = np.load(os.path.join(GOLDEN, "assembly_update_sequence.npz"))
+    N_p = int(z["N_p"])
+    Nt = N_p + 1
+    mats = {k: z["in_" + k] for k in MAT_NAMES if z["in_" + k].size}
+    mld = MldModel(nu_l=1, **mats)
+    full, dims, vt = omld.complete(mats, nu_l=1)
+    maps = oa.affine_maps(oc.condense(full, dims, Nt), dims, Nt, z["x_k"], z["omega_tilde"])
+    batch = BatchMpc({k: np.array(v) for k, v in mld.items() if v.size}, N_p, Nt, nu_l=1, B=1, device="cpu")
+    atoms = None
+    for i in range(int(z["n_steps"])):
+        kw = {str(k): z["val_%d_%d" % (i, j)] for j, k in enumerate(z["keys_%d" % i])}
+        if str(z["how_%d" % i]) == "set":
+            if atoms is None:
+                atoms = ObjectiveAtoms(mld.mld_info, N_p, Nt, None, **kw)
+            else:
+                atoms.set(None, **kw)
+        else:
+            atoms.update_atoms(None, **kw)
+        ctrl = types.SimpleNamespace(mld_info_k=mld.mld_info, N_tilde=Nt, _mld_evo_matrices=types.SimpleNamespace(batch=batch),
+                                     _sense="minimize", _with_std_objective=True, _std_obj_atoms=atoms,
+                                     variables_k_neg1={}, _omega_tilde_k=z["omega_tilde"].reshape(-1, 1))
+        c, c0 = _affine_cost(MpcController._cost_terms(ctrl, 0), maps)
+        np.testing.assert_allclose(c, z["c_v_%d" % i], rtol=0, atol=1e-12 * max(1.0, np.abs(z["c_v_%d" % i]).max()),
+                                   err_msg="call %d" % i)
+        assert abs(c0 - float(z["c0_%d" % i])) <= 1e-10 * max(1.0, abs(float(z["c0_%d" % i]))), i

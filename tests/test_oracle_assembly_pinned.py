@@ -22,7 +22,7 @@ from oracle import solve as osv
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CASES = sorted(os.path.basename(p)[len("assembly_"):-4] for p in glob.glob(os.path.join(GOLDEN, "assembly_*.npz"))
-               if "closed_loop" not in p)
+               if "closed_loop" not in p and "update_sequence" not in p)
 MAT_NAMES = ("A", "B1", "B2", "B3", "B4", "b5", "C", "D1", "D2", "D3", "D4", "d5",
              "E", "F1", "F2", "F3", "F4", "f5", "G", "Psi")
 REF_VAR_NAMES = dict(U_var_N_tilde="u", Delta_var_N_tilde="delta", Z_var_N_tilde="z", Mu_var_N_tilde="mu")
