@@ -148,7 +148,9 @@ int  hmpc_milp_solve_f64(int32_t B, int32_t n, int32_t m,
  *  rhs [B, nc*Nt] (from hmpc_constraint_rhs_f64; several constraint sets over the same rows fold into their
  *  row-wise minimum), cost_v [B|1, nv*Nt], lb_v/ub_v/is_bin_v [nv*Nt] shared by the batch, v(k) = [u; delta; mu].
  *  status[b] = HMPC_SOLVE_UNSUPPORTED marks an agent outside the class (use hmpc_milp_solve_f64 for it).
- *  stats [B,8] = {search nodes, 0, 0, cells, max open nodes, incumbent updates, 0, kilo-FMAs}.               */
+ *  stats [B,8] = {search nodes, set-up time, sweep time, cells, search time (device time of the agent's CTA / warp, in
+ *  units of 0.1 us), incumbent updates, certified relative gap of an unfinished search in units of 1e-9 (0 when
+ *  proven), thousands of FP64-pipe instructions executed}.                                                    */
 typedef struct {
     double  mip_rel_gap;   /* 0 = prove optimality                                     */
     double  feas_tol;      /* tolerance of hard (slack-free) rows, default 1e-9        */
@@ -158,8 +160,15 @@ typedef struct {
                               tariffs) are pruned at mip_rel_gap = 0;  0: FP32 table rounded down -- half the
                               workspace and shared memory, ~5-10 % faster, but ties are explored unless
                               mip_rel_gap >= 4e-6                                                               */
+    int32_t bound;         /* HMPC_DP_BOUND_CONSTANT (default): one value per cell;  HMPC_DP_BOUND_LINEAR: a line per
+                              cell (16 bytes), exact where slack penalties make the cost-to-go steep (full-horizon
+                              robust constraint sets); DEWH shape only, other agents get constant lines; the cell
+                              count must fit shared memory (hmpc_stage_dp_max_cells)                             */
+    int32_t fuse_search;   /* -1 (default): the table kernel's tail searches the agent itself when B <= 296;
+                              0 / 1: never / always                                                             */
     int32_t reserved;
 } hmpc_stage_dp_opts;
+enum { HMPC_DP_BOUND_CONSTANT = 0, HMPC_DP_BOUND_LINEAR = 1 };
 /* Optional convex cost terms of the stage-DP solve -- the reference's Quadratic / L22 / L1 atoms on the state, the
  * outputs and the slacks (controllers/components/objective_atoms.py:320-363), which make the problem an MIQP:
  *     cost += sum_k sum_t  wq[k,t] tau_k,t^2 + w1[k,t] |tau_k,t|  +  sum_k sum_i qmu[k,i] mu_k,i^2 ,
@@ -179,6 +188,8 @@ typedef struct {
 void hmpc_stage_dp_default_opts(hmpc_stage_dp_opts* opts);
 int  hmpc_stage_dp_supported(const hmpc_dims* dims);     /* 1 when the dimensions fit the class */
 int  hmpc_stage_dp_workspace_bytes(const hmpc_dims* dims, const hmpc_stage_dp_opts* opts, size_t* bytes);
+/* largest cell count (multiple of 256) whose stage buffers fit shared memory for these dimensions and this format */
+int  hmpc_stage_dp_max_cells(const hmpc_dims* dims, const hmpc_stage_dp_opts* opts, int32_t* cells);
 int  hmpc_stage_dp_solve_f64(const hmpc_dims* dims, const double* const mats[HMPC_NUM_MATS],
                              const int64_t mat_stride_b[HMPC_NUM_MATS], const double* rhs,
                              const double* cost_v, int64_t cost_v_stride_b, const double* lb_v, const double* ub_v,

@@ -23,12 +23,14 @@ def _dev_tensor(a, device, dtype=torch.float64):
 
 class BatchMpc(object):
     def __init__(self, mats, N_p, N_tilde=None, nu_l=0, nmu_l=0, B=None, device="cuda", opts=None, solver="auto",
-                 dp_opts=None):
+                 dp_opts=None, dp_bound="constant"):
         """mats: name -> array [B|1, r, c] (or [r, c]); missing blocks are zero, C defaults to I (nx == ny).
 
         solver: "auto" -- the exact stage-DP kernels (csrc/stage_dp.cu) when the MLD is in their class (scalar
         state, binary inputs, one slack per row: every DEWH of the reference example), else the general
-        branch-and-cut kernel (csrc/milp_bnc.cu); "bnc" / "stage_dp" force one of them."""
+        branch-and-cut kernel (csrc/milp_bnc.cu); "bnc" / "stage_dp" force one of them.
+        dp_bound: "constant" (one value per table cell) or "linear" (a line per cell: the bound to use when slack
+        penalties are active along the whole trajectory -- full-horizon robust constraint sets)."""
         self.device = torch.device(device)
         self.N_p = int(N_p)
         self.Nt = int(N_tilde) if N_tilde is not None else self.N_p + 1
@@ -87,8 +89,15 @@ class BatchMpc(object):
         # table resolution: 8192 cells per stage keep the search at its minimum (the first dive is optimal) when the
         # batch is small and the step time is the slowest agent's latency; with many agents per SM the sweep is what
         # costs, and 4096 cells give the same optimum with ~6 % more search expansions at half the sweep
-        self.dp_opts = dp_opts if dp_opts is not None else \
-            cabi.stage_dp_default_opts(cells=8192 if self.B <= 2 * 148 else 4096)
+        if dp_bound not in ("constant", "linear"):
+            raise ValueError("dp_bound must be 'constant' or 'linear'")
+        if dp_opts is None:
+            dp_opts = cabi.stage_dp_default_opts(cells=8192 if self.B <= 2 * 148 else 4096)
+            if dp_bound == "linear":
+                dp_opts.bound = cabi.DP_BOUND_LINEAR
+            if cabi.stage_dp_supported(d):       # the two stage buffers must fit shared memory in this format
+                dp_opts.cells = min(dp_opts.cells, cabi.stage_dp_max_cells(d, dp_opts))
+        self.dp_opts = dp_opts
         self.stage_dp_ok = self._stage_dp_class()
         if solver == "stage_dp" and not self.stage_dp_ok:
             raise ValueError("this MLD is outside the stage-DP class (needs nx == 1, nz == 0, binary inputs, "

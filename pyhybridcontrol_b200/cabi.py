@@ -20,7 +20,7 @@ EVO_NAMES = ("Phi_x", "Gamma_v", "Gamma_omega", "Gamma_5", "L_x", "L_v", "L_omeg
 EXPORTS = ("hmpc_version", "hmpc_last_cuda_error", "hmpc_device_info", "hmpc_condense_f64",
            "hmpc_condense_bytes_per_agent", "hmpc_constraint_rhs_f64", "hmpc_predict_f64", "hmpc_linear_cost_f64",
            "hmpc_milp_default_opts", "hmpc_milp_workspace_bytes", "hmpc_milp_solve_f64", "hmpc_stage_dp_default_opts",
-           "hmpc_stage_dp_supported", "hmpc_stage_dp_workspace_bytes", "hmpc_stage_dp_solve_f64", "hmpc_lsim_step_f64",
+           "hmpc_stage_dp_supported", "hmpc_stage_dp_workspace_bytes", "hmpc_stage_dp_max_cells", "hmpc_stage_dp_solve_f64", "hmpc_lsim_step_f64",
            "hmpc_dewh_sim_step_f64", "hmpc_dewh_control_model_f64", "hmpc_dewh_thermostat_f64",
            "hmpc_param_eval_f64", "hmpc_param_eval_v2_f64", "hmpc_param_eval_bytes_per_agent",
            "hmpc_aggregate_power_f64", "hmpc_coupling_price_cost_f64", "hmpc_coupling_sums_f64",
@@ -55,7 +55,7 @@ class MilpOpts(C.Structure):
 
 class StageDpOpts(C.Structure):
     _fields_ = [("mip_rel_gap", C.c_double), ("feas_tol", C.c_double), ("cells", C.c_int32), ("max_nodes", C.c_int32),
-                ("table_fp64", C.c_int32), ("reserved", C.c_int32)]
+                ("table_fp64", C.c_int32), ("bound", C.c_int32), ("fuse_search", C.c_int32), ("reserved", C.c_int32)]
 
 
 class StageTerms(C.Structure):
@@ -93,6 +93,7 @@ _lib.hmpc_stage_dp_default_opts.argtypes = [C.POINTER(StageDpOpts)]
 _lib.hmpc_stage_dp_default_opts.restype = None
 _lib.hmpc_stage_dp_supported.argtypes = [C.POINTER(Dims)]
 _lib.hmpc_stage_dp_workspace_bytes.argtypes = [C.POINTER(Dims), C.POINTER(StageDpOpts), C.POINTER(C.c_size_t)]
+_lib.hmpc_stage_dp_max_cells.argtypes = [C.POINTER(Dims), C.POINTER(StageDpOpts), C.POINTER(C.c_int32)]
 _lib.hmpc_stage_dp_solve_f64.argtypes = [C.POINTER(Dims), _MatArr, _StrideArr, _P, _P, C.c_int64, _P, _P, _P,
                                          C.POINTER(StageTerms), C.POINTER(StageDpOpts), _P, C.c_size_t, _P, _P, _P,
                                          _P, _P]
@@ -298,6 +299,17 @@ def stage_dp_default_opts(**kw):
     for k, v in kw.items():
         setattr(o, k, v)
     return o
+
+
+DP_BOUND_CONSTANT, DP_BOUND_LINEAR = 0, 1
+
+
+def stage_dp_max_cells(d, opts=None):
+    """Largest cell count whose two stage buffers fit shared memory for these dimensions / this cell format."""
+    o = opts if opts is not None else stage_dp_default_opts()
+    n = C.c_int32()
+    _check(_lib.hmpc_stage_dp_max_cells(C.byref(d), C.byref(o), C.byref(n)), "hmpc_stage_dp_max_cells")
+    return int(n.value)
 
 
 def stage_dp_supported(d):

@@ -12,31 +12,37 @@
 // This is exactly  min c'v  s.t.  H_v v <= rhs  of the condensed form (mld_evolution_matrices.py:237-240), whose
 // continuous part has the closed form  mu_k,i = max(0, e_i p_k + f_i' alpha_k - rhs_k,i) / d_i.
 //
-// Algorithm
+// Algorithm (round 2)
 //   * scaled state s_k = p_k / a^k turns the recursion into a pure translation s_k+1 = s_k + beta_k(alpha),
-//     beta_k = g' alpha / a^(k+1): the "no input" action maps every cell of a uniform s-grid onto itself.
-//   * kernel 1 (stage_dp_table_kernel, one CTA per agent): backward sweep over the stages of a LOWER BOUND
-//     LB_k[cell] of the cost-to-go that is valid for every state in the cell (stage penalties are bounded from
-//     below over the cell, a translated cell overlaps two cells of the next stage and takes their min).  The
-//     stage in flight lives in shared memory between guard cells (no bound checks in the hot loop); every stage is
-//     streamed to HBM by a TMA bulk copy -- as FP64 (default: sequences that tie with the incumbent are then pruned
-//     at gap 0) or as FP32 rounded DOWN (half the workspace; still a valid bound).  States outside the grid
-//     window get the trivial bound (sum of negative costs), so the window only affects speed, never correctness.
-//   * kernel 2 (stage_dp_search_kernel, one warp per agent): exact search over the binary sequence in time
-//     order; states and costs are exact FP64, a node is pruned when cost so far + LB >= incumbent.  The unit of
-//     work is the depth-5 subtree under an open node (32 lanes = 32 action sequences, one table read each).  A
-//     greedy dive gives the incumbent (it is optimal on > 99 % of the DEWH instances); the depth-first pass that
-//     follows is the optimality proof.
+//     beta_k = g' alpha / a^(k+1).  All stages share ONE lattice of cells of width w (absolute cell a holds the
+//     states [a w, (a+1) w)), so the "no input" action maps a cell onto a cell exactly.
+//   * MOVING WINDOW: stage k tabulates the G absolute cells [off_k, off_k + G), off_k following the violation-free
+//     band of the stage (the band drifts with the free response; one global window over a long horizon wastes most of
+//     its cells).  Everything below / above the window is one SEMI-INFINITE cell each, whose bound is valid for all
+//     of its states (penalty at its favourable edge, minimum over every next-stage cell its image can touch), so a
+//     state that leaves the window never falls back to the trivial bound.
+//   * kernel 1 (stage_dp_table_kernel, one CTA per agent): backward sweep of a LOWER BOUND of the cost-to-go per
+//     cell.  Two cell formats: a constant per cell (default), or a LINE per cell (value at the left and right edge,
+//     cells need not agree at their common edge) built from the lower convex hull of the translated pieces -- exact
+//     where slack penalties make the cost-to-go steep (full-horizon robust constraint sets), and never below the
+//     constant-cell bound.  Two stage buffers live in shared memory between guard cells that hold the semi-infinite
+//     bounds; only the stages the search can read (k = D, 2D, ...: the depth of one search expansion) leave the SM,
+//     each through one TMA bulk copy.
+//   * search (one warp per agent; the tail of kernel 1 when the batch is small, else / for the hard agents kernel 2):
+//     exact depth-first search over the binary sequence in time order -- states and costs are exact FP64 -- pruned by
+//     cost so far + table bound >= min(incumbent, T), where the threshold T starts just above the root bound and
+//     grows geometrically whenever the tree below it is exhausted without a solution (iterative deepening on the
+//     bound: a poor first dive can no longer trap the search in a bad subtree).  The unit of work is the depth-D
+//     subtree under an open node (32 lanes = 32 action sequences, one table read each).
 // Optional convex stage terms (quadratic / L1 atoms on the state, outputs and slacks) make the problem an MIQP; they
 // run through the general loops of both kernels.
-// Work: Nt * G cell updates (~45 instructions each) + ~15 subtree expansions per agent -- against ~10^3..10^5
-// dense simplex pivots of the general branch-and-cut kernel (milp_bnc.cu) on the same problems.
+#include <limits.h>
 #include <string.h>
 #include "common.cuh"
 
 namespace hmpc {
 
-constexpr int kDpThreads = 256;
+constexpr int kTableThreads = 512;
 constexpr int kDpMaxNb = 4;
 constexpr int kDpMaxAct = 1 << kDpMaxNb;
 constexpr int kDpMaxNc = 8;
@@ -44,8 +50,12 @@ constexpr int kDpMaxNt = 128;
 constexpr int kDpMaxT = 4;           // extra state terms per stage
 constexpr int kSearchWarps = 4;
 constexpr int kStackCap = 512;        // open nodes per agent
+constexpr int kTailBudget = 64;       // expansions the fused tail search may spend before deferring to kernel 2
+constexpr int kPending = -1;          // status of an agent that kernel 2 still has to search
 constexpr double kEdgeEps = 1e-9;     // cell-boundary guard (fraction of a cell)
-__host__ __device__ constexpr int G_PAD(int G) { return G / 4; }   // guard cells on each side of a stage buffer
+constexpr double kLinSlop = 4e-15;    // relative floating-point slop subtracted per stage from a linear cell
+
+enum { FMT_F32 = 0, FMT_F64 = 1, FMT_LIN = 2 };
 
 struct DpArgs {
     hmpc_dims d;
@@ -58,20 +68,23 @@ struct DpArgs {
     hmpc_stage_dp_opts o;
     hmpc_stage_terms t;                // optional convex state / slack terms (T == 0 and qmu == NULL: none)
     int G, nb, nact, nv, T;
-    float* table;                      // [B, Nt, G]   (stage 0 unused)
+    int D, nstore, fmt, fuse;          // search depth per expansion, stored stages (k = D, 2D, ...), cell format
+    void* table;                       // [B, nstore, G] cells
     double* pblk;                      // [B, plan doubles]: the agent's stage data, handed from kernel 1 to kernel 2
     double* v; double* obj; int32_t* status; int32_t* stats;
 };
 
-// per-agent stage data in shared memory (all doubles; amask is stored as doubles too so that the block can be
-// handed to the search kernel with one coalesced copy)
+__host__ __device__ inline int fmt_bytes(int fmt) { return fmt == FMT_LIN ? 16 : (fmt == FMT_F64 ? 8 : 4); }
+
+// per-agent stage data in shared memory (all doubles; small integers are stored as doubles or packed ints so that
+// the block can be handed to the search kernel with one coalesced copy)
 struct DpPlan {
-    int ak, iak, cu, qs, rhs, tailmin, amask, e, dscale, galpha, falpha, misc, nd;   // persistent part
+    int ak, iak, cu, qs, rhs, tailmin, amask, e, dscale, galpha, falpha, misc, off, loinf, hiinf, nd;   // persistent
     int x_eak, x_foff, x_hq, x_ca, x_shift;
     int t_h, t_ga, t_r, t_wq, t_w1, qq;
     int scr;                                                                      // load-time scratch [6*Nt]
     int mst;                                                                      // staged MLD blocks [11][64]
-    int sc_ca, sc_base, sc_slope, sc_i0, sc_span, sc_flags;                       // per-stage sweep constants
+    int sc_ca, sc_base, sc_slope, sc_fr, sc_i0, sc_span, sc_flags, sc_z, sc_semi, sc_semd;   // per-stage sweep constants
     int total;
 };
 
@@ -82,10 +95,11 @@ __host__ __device__ inline DpPlan make_dp_plan(int Nt, int nb, int nc, int T = k
     const int nact = 1 << nb;
     int o = 0;
     auto take = [&](int n) { int r = o; o += n; return r; };
-    p.misc = take(8);
+    p.misc = take(16);
     p.ak = take(Nt + 2); p.iak = take(Nt + 2); p.cu = take(Nt * nb); p.qs = take(Nt * nc); p.rhs = take(Nt * nc);
     p.tailmin = take(Nt + 1); p.amask = take(Nt);
     p.e = take(nc); p.dscale = take(nc); p.galpha = take(nact); p.falpha = take(nc * nact);
+    p.off = take((Nt + 3) / 2); p.loinf = take(Nt + 1); p.hiinf = take(Nt + 1);
     // per-stage constants of the forward search: viol_i = x_eak[k][i] * s + x_foff[k][i][al], penalty weight / 2,
     // action cost, translation of s
     p.x_eak = take(Nt * nc); p.x_foff = take(Nt * nc * nact); p.x_hq = take(Nt * nc); p.x_ca = take(Nt * nact);
@@ -98,18 +112,21 @@ __host__ __device__ inline DpPlan make_dp_plan(int Nt, int nb, int nc, int T = k
     p.scr = take(6 * Nt);
     p.mst = take(kMstMats * kMstElems);
     const int nc_ = nc > 0 ? nc : 1;
-    p.sc_ca = take(Nt * nact); p.sc_base = take(Nt * nc_ * nact); p.sc_slope = take(Nt * nc_);
+    p.sc_ca = take(Nt * nact); p.sc_base = take(Nt * nc_ * nact); p.sc_slope = take(Nt * nc_); p.sc_fr = take(Nt * nact);
     p.sc_i0 = take((Nt * nact + 1) / 2); p.sc_span = take((Nt * nact + 1) / 2); p.sc_flags = take((Nt + 1) / 2);
+    p.sc_z = take(Nt + 1); p.sc_semi = take(4 * Nt); p.sc_semd = take(4 * Nt);
     p.total = (o + 1) & ~1;
     return p;
 }
 
-enum { MISC_S0 = 0, MISC_W, MISC_A, MISC_FLAG, MISC_INVW, MISC_SIMPLE, MISC_TERMS };
+enum { MISC_W = 0, MISC_INVW, MISC_A, MISC_FLAG, MISC_SIMPLE, MISC_TERMS, MISC_LINOK, MISC_INC_OBJ, MISC_INC_P0,
+       MISC_INC_P1, MISC_NODES0, MISC_IMPR0, MISC_KINS, MISC_T_SETUP, MISC_T_SWEEP };
 
 struct DpCtx {
     int Nt, nb, nc, nact, nmu, nv, G;
     double *ak, *iak, *cu, *qs, *rhs, *tailmin, *amask, *e, *dscale, *galpha, *falpha, *misc, *scr, *mst;
-    double *sc_ca, *sc_base, *sc_slope; int *sc_i0, *sc_span, *sc_flags;
+    double *loinf, *hiinf; int* off;
+    double *sc_ca, *sc_base, *sc_slope, *sc_fr, *sc_semd; int *sc_i0, *sc_span, *sc_flags, *sc_z, *sc_semi;
     double *x_eak, *x_foff, *x_hq, *x_ca, *x_shift;
     double *t_h, *t_ga, *t_r, *t_wq, *t_w1, *qq;
     int T;
@@ -125,13 +142,21 @@ __device__ inline DpCtx bind_ctx(const DpArgs& A, unsigned char* smem) {
     c.ak = sd + p.ak; c.iak = sd + p.iak; c.cu = sd + p.cu; c.qs = sd + p.qs; c.rhs = sd + p.rhs;
     c.tailmin = sd + p.tailmin; c.amask = sd + p.amask; c.e = sd + p.e; c.dscale = sd + p.dscale;
     c.galpha = sd + p.galpha; c.falpha = sd + p.falpha; c.misc = sd + p.misc; c.scr = sd + p.scr; c.mst = sd + p.mst;
-    c.sc_ca = sd + p.sc_ca; c.sc_base = sd + p.sc_base; c.sc_slope = sd + p.sc_slope;
+    c.off = reinterpret_cast<int*>(sd + p.off); c.loinf = sd + p.loinf; c.hiinf = sd + p.hiinf;
+    c.sc_ca = sd + p.sc_ca; c.sc_base = sd + p.sc_base; c.sc_slope = sd + p.sc_slope; c.sc_fr = sd + p.sc_fr;
     c.sc_i0 = reinterpret_cast<int*>(sd + p.sc_i0); c.sc_span = reinterpret_cast<int*>(sd + p.sc_span);
-    c.sc_flags = reinterpret_cast<int*>(sd + p.sc_flags);
+    c.sc_flags = reinterpret_cast<int*>(sd + p.sc_flags); c.sc_z = reinterpret_cast<int*>(sd + p.sc_z);
+    c.sc_semi = reinterpret_cast<int*>(sd + p.sc_semi); c.sc_semd = sd + p.sc_semd;
     c.x_eak = sd + p.x_eak; c.x_foff = sd + p.x_foff; c.x_hq = sd + p.x_hq; c.x_ca = sd + p.x_ca; c.x_shift = sd + p.x_shift;
     c.t_h = sd + p.t_h; c.t_ga = sd + p.t_ga; c.t_r = sd + p.t_r; c.t_wq = sd + p.t_wq; c.t_w1 = sd + p.t_w1; c.qq = sd + p.qq;
     c.feas_tol = A.o.feas_tol;
     return c;
+}
+
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
 }
 
 __device__ __forceinline__ const double* mat_of(const DpArgs& A, int which, int b) {
@@ -154,15 +179,22 @@ __device__ inline void dp_load(const DpArgs& A, int b, DpCtx& c) {
         }
     }
     __syncthreads();
+    // a^k (the reference's A_pow_tilde, mld_evolution_matrices.py:266-272) by binary powers, one stage per thread
+    for (int k = tid; k <= Nt + 1; k += nthr) {
+        double r = 1.0, pw = c.mst[0];
+        for (int e = k; e > 0; e >>= 1) { if (e & 1) r *= pw; pw *= pw; }
+        c.ak[k] = r; c.iak[k] = 1.0 / r;
+    }
     if (tid == 0) {
         int flag = 0;
         const double* Am = c.mst;
         const double a = Am[0];
         c.misc[MISC_A] = a;
-        // a^k by running products, like the reference's A_pow_tilde (mld_evolution_matrices.py:266-272)
-        double ap = 1.0;
-        for (int k = 0; k <= Nt + 1; ++k) { c.ak[k] = ap; ap *= a; }
-        if (!(a > 0.0) || !(c.ak[Nt] > 1e-3) || !(c.ak[Nt] < 1e3)) flag = 1;
+        {   // a^Nt must stay within three decades (same product, computed here so that thread 0 need not wait)
+            double r = 1.0, pw = a;
+            for (int e = Nt; e > 0; e >>= 1) { if (e & 1) r *= pw; pw *= pw; }
+            if (!(a > 0.0) || !(r > 1e-3) || !(r < 1e3)) flag = 1;
+        }
         const double* B1 = c.mst + 1 * kMstElems; const double* B2 = c.mst + 2 * kMstElems;
         const double* Cm = c.mst + 3 * kMstElems;
         const double* D1 = c.mst + 4 * kMstElems; const double* D2 = c.mst + 5 * kMstElems;
@@ -171,21 +203,21 @@ __device__ inline void dp_load(const DpArgs& A, int b, DpCtx& c) {
         const double* Gm = c.mst + 9 * kMstElems; const double* Psi = c.mst + 10 * kMstElems;
         const int ny = A.d.ny, nd = A.d.ndelta;
         double g[kDpMaxNb], f[kDpMaxNc][kDpMaxNb];
-        for (int j = 0; j < nb; ++j) g[j] = j < nu ? (B1 ? B1[j] : 0.0) : (B2 ? B2[j - nu] : 0.0);
+        for (int j = 0; j < nb; ++j) g[j] = j < nu ? B1[j] : B2[j - nu];
         for (int i = 0; i < nc; ++i) {
-            double ei = E ? E[i] : 0.0;                       // E is [nc, nx = 1]
-            for (int j = 0; j < nb; ++j) f[i][j] = j < nu ? (F1 ? F1[i * nu + j] : 0.0) : (F2 ? F2[i * nd + (j - nu)] : 0.0);
-            if (Gm) for (int r = 0; r < ny; ++r) {            // y = C x + D1 u + D2 delta (+ terms already in rhs)
+            double ei = E[i];                                 // E is [nc, nx = 1]
+            for (int j = 0; j < nb; ++j) f[i][j] = j < nu ? F1[i * nu + j] : F2[i * nd + (j - nu)];
+            for (int r = 0; r < ny; ++r) {                    // y = C x + D1 u + D2 delta (+ terms already in rhs)
                 const double gir = Gm[i * ny + r];
                 if (gir == 0.0) continue;
-                ei += gir * (Cm ? Cm[r] : 0.0);
-                for (int j = 0; j < nb; ++j) f[i][j] += gir * (j < nu ? (D1 ? D1[r * nu + j] : 0.0) : (D2 ? D2[r * nd + (j - nu)] : 0.0));
+                ei += gir * Cm[r];
+                for (int j = 0; j < nb; ++j) f[i][j] += gir * (j < nu ? D1[r * nu + j] : D2[r * nd + (j - nu)]);
             }
             c.e[i] = ei;
             double di = 0.0;
             if (nmu) {
                 for (int j = 0; j < nmu; ++j) {
-                    const double pij = Psi ? Psi[i * nmu + j] : 0.0;
+                    const double pij = Psi[i * nmu + j];
                     if (j == i) di = -pij; else if (pij != 0.0) flag = 1;   // every row owns at most its own slack
                 }
                 if (di < 0.0) flag = 1;
@@ -212,6 +244,8 @@ __device__ inline void dp_load(const DpArgs& A, int b, DpCtx& c) {
         }
         c.misc[MISC_FLAG] = (double)flag;
         c.misc[MISC_TERMS] = (c.T > 0 || A.t.qmu) ? 1.0 : 0.0;
+        c.misc[MISC_INC_OBJ] = INFINITY; c.misc[MISC_INC_P0] = 0.0; c.misc[MISC_INC_P1] = 0.0;
+        c.misc[MISC_NODES0] = 0.0; c.misc[MISC_IMPR0] = 0.0;
     }
     __syncthreads();
     // ---- per-stage data, one stage per thread
@@ -220,7 +254,6 @@ __device__ inline void dp_load(const DpArgs& A, int b, DpCtx& c) {
     double* s_lo = c.scr; double* s_hi = c.scr + Nt; double* s_smin = c.scr + 2 * Nt; double* s_smax = c.scr + 3 * Nt;
     double* s_cmin = c.scr + 4 * Nt; double* s_marg = c.scr + 5 * Nt;
     int bad = 0;
-    for (int k = tid; k <= Nt + 1; k += nthr) c.iak[k] = 1.0 / c.ak[k];
     for (int k = tid; k < Nt; k += nthr) {
         int mask = 0;
         for (int al = 0; al < nact; ++al) {
@@ -288,31 +321,77 @@ __device__ inline void dp_load(const DpArgs& A, int b, DpCtx& c) {
     }
     if (bad) c.misc[MISC_FLAG] = 1.0;   // benign race: every writer stores the same value
     __syncthreads();
-    if (tid == 0) {
-        // trivial bound on the cost-to-go from ANY state: the negative action costs that are still ahead
-        c.tailmin[Nt] = 0.0;
-        for (int k = Nt - 1; k >= 0; --k) c.tailmin[k] = c.tailmin[k + 1] + fmin(s_cmin[k], 0.0);
-        // grid window: hull over the stages of the violation-free band (clamped to what is reachable at that
-        // stage), one max shift of margin, intersected with what is reachable at all
-        double rlo = 0.0, rhi = 0.0, blo = INFINITY, bhi = -INFINITY, margin = 0.0;
-        for (int k = 0; k < Nt; ++k) {
+    // ---- grid window and trivial bound: prefix sums / minima over the stages, done by warp 0 (lane l owns the stages
+    // [l*per, (l+1)*per); scans across lanes by shuffles).
+    //   tailmin_k  = sum_{i>=k} min(cmin_i, 0): trivial bound on the cost-to-go from ANY state
+    //   moving window: stage k covers [band_k - 2 shifts, band_k + 1 shift], the band clamped to what is reachable at
+    //   that stage and slew-limited -- the state climbs by at most the largest shift per stage and falls by at most
+    //   the most negative one, so after a jump of the band the window follows the states that are catching up, not the
+    //   band itself:  env_lo_k = min(lo_k, env_lo_k-1 + smax_k-1) = P_k + min_{j<=k} (lo_j - P_j),  P = prefix sum of
+    //   smax (likewise env_hi with the most negative shifts).  Every stage has the same width (the widest of them, at
+    //   least 5.4 shifts so that a translation plus the drift of the window between two stages stays within the guard
+    //   cells of the stage buffers).
+    if (tid < 32) {
+        const int per = (Nt + 31) / 32, k0 = tid * per, k1 = min(k0 + per, Nt);
+        auto scan_add = [&](double v) {      // exclusive prefix sum across lanes; returns (exclusive, total)
+            double inc = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const double t = __shfl_up_sync(0xffffffffu, inc, o); if (tid >= o) inc += t; }
+            return make_double2(inc - v, __shfl_sync(0xffffffffu, inc, 31));
+        };
+        double a_neg = 0.0, a_min = 0.0, a_max = 0.0, a_pp = 0.0, a_pm = 0.0, margin = 0.0;
+        for (int k = k0; k < k1; ++k) {
+            a_neg += fmin(s_cmin[k], 0.0); a_min += s_smin[k]; a_max += s_smax[k];
+            a_pp += fmax(s_smax[k], 0.0); a_pm += fmin(s_smin[k], 0.0); margin = fmax(margin, s_marg[k]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) margin = fmax(margin, __shfl_xor_sync(0xffffffffu, margin, o));
+        const double2 x_neg = scan_add(a_neg), x_min = scan_add(a_min), x_max = scan_add(a_max), x_pp = scan_add(a_pp), x_pm = scan_add(a_pm);
+        // pass 1: clamped band edges relative to the slew prefix; lane-local running minima / maxima
+        double rlo = x_min.x, rhi = x_max.x, pp = x_pp.x, pm = x_pm.x, tail = x_neg.y - x_neg.x;
+        double lmin = INFINITY, lmax = -INFINITY;
+        for (int k = k0; k < k1; ++k) {
+            c.tailmin[k] = tail; tail -= fmin(s_cmin[k], 0.0);
             const double lo_c = fmin(fmax(s_lo[k], rlo), rhi), hi_c = fmax(fmin(s_hi[k], rhi), rlo);
-            blo = fmin(blo, fmin(lo_c, hi_c)); bhi = fmax(bhi, fmax(lo_c, hi_c));
-            margin = fmax(margin, s_marg[k]);
-            rlo += s_smin[k]; rhi += s_smax[k];
+            lmin = fmin(lmin, lo_c - pp); lmax = fmax(lmax, hi_c - pm);
+            s_lo[k] = lmin; s_hi[k] = lmax;                      // running extrema within the lane's block
+            s_cmin[k] = rlo; s_marg[k] = rhi;                    // (scratch reuse: reachable range of the stage)
+            rlo += s_smin[k]; rhi += s_smax[k]; pp += fmax(s_smax[k], 0.0); pm += fmin(s_smin[k], 0.0);
         }
-        double S0 = fmax(rlo, blo - margin), S1 = fmin(rhi, bhi + margin);
-        if (!(S1 > S0)) { S0 = rlo; S1 = rhi; }
-        // keep every translation within the guard cells of the stage buffers (G / 4 on each side), so that the whole
-        // sweep runs through the hot loop: a window narrower than four shifts is widened around its centre (the
-        // extra cells are unreachable or dead; they cost nothing but their share of the sweep)
-        {
-            const double minw = 4.0 * margin * (1.0 + 16.0 / (double)c.G);
-            if (S1 - S0 < minw) { const double mid = 0.5 * (S0 + S1); S0 = mid - 0.5 * minw; S1 = mid + 0.5 * minw; }
+        if (tid == 0) c.tailmin[Nt] = 0.0;
+        // exclusive prefix min / max of the lanes' block extrema
+        double imin = lmin, imax = lmax;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double t1 = __shfl_up_sync(0xffffffffu, imin, o), t2 = __shfl_up_sync(0xffffffffu, imax, o);
+            if (tid >= o) { imin = fmin(imin, t1); imax = fmax(imax, t2); }
         }
-        double w = (S1 - S0) / (double)c.G;
-        if (!(w > 0.0) || !isfinite(w)) w = 1.0;
-        c.misc[MISC_S0] = S0; c.misc[MISC_W] = w; c.misc[MISC_INVW] = 1.0 / w; c.misc[MISC_SIMPLE] = 1.0;
+        double emin = __shfl_up_sync(0xffffffffu, imin, 1), emax = __shfl_up_sync(0xffffffffu, imax, 1);
+        if (tid == 0) { emin = INFINITY; emax = -INFINITY; }
+        // pass 2: envelopes -> window start of every stage, widest window
+        pp = x_pp.x; pm = x_pm.x;
+        double Wmax = 0.0;
+        for (int k = k0; k < k1; ++k) {
+            const double env_lo = pp + fmin(emin, s_lo[k]), env_hi = pm + fmax(emax, s_hi[k]);
+            const double rlo_k = s_cmin[k], rhi_k = s_marg[k];
+            const double a0 = fmax(fmin(env_lo, env_hi) - 2.0 * margin, rlo_k - 0.01 * margin);
+            double b0 = fmin(fmax(env_lo, env_hi) + margin, rhi_k + 0.01 * margin);
+            if (!(b0 > a0)) b0 = a0;
+            s_lo[k] = a0; Wmax = fmax(Wmax, b0 - a0);
+            pp += fmax(s_smax[k], 0.0); pm += fmin(s_smin[k], 0.0);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) Wmax = fmax(Wmax, __shfl_xor_sync(0xffffffffu, Wmax, o));
+        double W = fmax(Wmax, 5.4 * margin * (1.0 + 16.0 / (double)c.G));
+        if (!(W > 0.0) || !isfinite(W)) W = 1.0;
+        const double w = W / (double)c.G, invw = 1.0 / w;
+        for (int k = k0; k < k1; ++k) c.off[k] = (int)fmax(fmin(floor(s_lo[k] * invw), 1.0e9), -1.0e9);
+        __syncwarp();
+        if (tid == 0) {
+            c.off[Nt] = c.off[Nt - 1]; c.off[Nt + 1] = c.off[Nt - 1];
+            c.misc[MISC_W] = w; c.misc[MISC_INVW] = invw; c.misc[MISC_SIMPLE] = 1.0;
+            c.loinf[Nt] = 0.0; c.hiinf[Nt] = 0.0;
+        }
     }
     __syncthreads();
 }
@@ -357,17 +436,33 @@ __device__ __forceinline__ double terms_lower_bound(const DpCtx& c, int k, int a
     return st;
 }
 
-// Table storage: FP32 rounded DOWN (default: half the HBM stream and shared memory) or FP64 (exact: sequences that
-// tie with the incumbent are then pruned instead of explored, see DESIGN.md section 4.2 "known limits").
-template <typename TT> __device__ __forceinline__ TT to_table(double v);
-template <> __device__ __forceinline__ float to_table<float>(double v) { return __double2float_rd(v); }
-template <> __device__ __forceinline__ double to_table<double>(double v) { return v; }
-template <typename TT> __device__ __forceinline__ TT table_min(TT a, TT b);
-template <> __device__ __forceinline__ float table_min<float>(float a, float b) { return fminf(a, b); }
-template <> __device__ __forceinline__ double table_min<double>(double a, double b) { return a < b ? a : b; }
+// ---- cell formats.  F32: constant, rounded DOWN (half the shared memory; still a valid bound).  F64: constant
+// (default: sequences that tie with the incumbent are pruned at gap 0).  LIN: a line (x = value at the left edge,
+// y = value at the right edge).
+template <int FMT> struct Cell;
+template <> struct Cell<FMT_F32> {
+    typedef float T;
+    static __device__ __forceinline__ T pack(double v) { return __double2float_rd(v); }
+    static __device__ __forceinline__ double lo(T a) { return (double)a; }
+};
+template <> struct Cell<FMT_F64> {
+    typedef double T;
+    static __device__ __forceinline__ T pack(double v) { return v; }
+    static __device__ __forceinline__ double lo(T a) { return a; }
+};
+template <> struct Cell<FMT_LIN> {
+    typedef double2 T;
+    static __device__ __forceinline__ T pack(double v) { return make_double2(v, v); }
+    static __device__ __forceinline__ double lo(T a) { return a.x < a.y ? a.x : a.y; }
+};
+__device__ __forceinline__ float cmin2(float a, float b) { return fminf(a, b); }
+__device__ __forceinline__ double cmin2(double a, double b) { return a < b ? a : b; }
+__device__ __forceinline__ double dmin(double a, double b) { return a < b ? a : b; }      // (no NaN handling: two instructions less than fmin)
+__device__ __forceinline__ void put_cell(float* p, double v) { *p = __double2float_rd(v); }   // rounded DOWN: still a bound
+__device__ __forceinline__ void put_cell(double* p, double v) { *p = v; }
 
 // TMA bulk copy (cp.async.bulk, shared -> global) of one finished stage of the table: one elected thread issues it,
-// the copy engine streams the 4 G bytes to HBM while the CTA already sweeps the next stage.
+// the copy engine streams the stage to HBM / L2 while the CTA already sweeps the next stage.
 __device__ __forceinline__ void bulk_store_stage(void* gdst, const void* ssrc, unsigned bytes) {
     const unsigned saddr = (unsigned)__cvta_generic_to_shared(ssrc);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the async proxy
@@ -377,30 +472,75 @@ __device__ __forceinline__ void bulk_store_stage(void* gdst, const void* ssrc, u
 __device__ __forceinline__ void bulk_wait_source_free() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
-// Hot loop of the backward sweep over the cells [lo, hi) whose translated neighbours are all inside the table:
-// no bound checks, every per-stage constant in registers.  q max(v, 0) is evaluated as (q/2) (v + |v|) -- exact,
-// and |v| is a free operand modifier of the FP64 add.
+// ---- hot loops of the backward sweep.  A thread owns the cells n * 512 + tid; a warp's 32 cells of block n are
+// INTERIOR when every cell they read lies inside the next stage's window (no bound checks) and PENALTY-FREE when none
+// of them violates a row at its favourable edge; both sets are ranges of n (per warp, per stage), so the sweep is a
+// few straight loops with every per-stage constant in registers.  q max(v, 0) is evaluated as (q/2) (v + |v|) --
+// exact, and |v| is a free operand modifier of the FP64 add.
+struct Semi { double lo, hi; };      // bounds of the two semi-infinite cells of the next stage
+
+// (a) the DEWH shape: two actions, action 0 = no input (a cell maps onto the cell `d0` away in the next stage's
+//     window), action 1 = a translation over two cells; row violations do not depend on the action.
+template <int NC, bool PEN, bool CHECKED, typename TT>
+__device__ __forceinline__ void sweep_same2(const TT* __restrict__ cur, TT* __restrict__ nxt, int G, int n0, int n1,
+                                            int d0, int i1, const double (&slope)[NC], const double (&hq)[NC],
+                                            const double (&base)[NC], double c0, double c1, Semi out) {
+    if (n0 >= n1) return;
+    int cell = n0 * kTableThreads + threadIdx.x;
+    const TT* ps = cur + cell + d0;
+    const TT* pm = ps + i1;
+    TT* po = nxt + cell;
+    double cd = (double)cell;
+#pragma unroll 4
+    for (int n = n0; n < n1; ++n, cell += kTableThreads, cd += (double)kTableThreads, ps += kTableThreads,
+                             pm += kTableThreads, po += kTableThreads) {
+        double st, m0, m1;
+        if (CHECKED) {
+            if (cell >= G) break;
+            const int js = cell + d0, jm = js + i1;
+            st = js < 0 ? out.lo : (js >= G ? out.hi : (double)ps[0]);
+            m0 = jm < 0 ? out.lo : (jm >= G ? out.hi : (double)pm[0]);
+            m1 = jm + 1 < 0 ? out.lo : (jm + 1 >= G ? out.hi : (double)pm[1]);
+        } else {
+            st = (double)ps[0]; m0 = (double)pm[0]; m1 = (double)pm[1];
+        }
+        st += c0;
+        const double mv = (m0 < m1 ? m0 : m1) + c1;
+        double best = st < mv ? st : mv;
+        if (PEN) {
+            double pen = 0.0;
+#pragma unroll
+            for (int i = 0; i < NC; ++i) {
+                const double v = fma(cd, slope[i], base[i]);
+                pen = fma(hq[i], v + fabs(v), pen);
+            }
+            best += pen;
+        }
+        put_cell(po, best);
+    }
+}
+
+// (b) any action count, violations may depend on the action; interior blocks only
 template <int NC, int NACT, bool SAME, typename TT>
-__device__ __forceinline__ void sweep_interior(const TT* __restrict__ cur, TT* __restrict__ nxt,
-                                               int lo, int hi, int nthr,
+__device__ __forceinline__ void sweep_interior(const TT* __restrict__ cur, TT* __restrict__ nxt, int n0, int n1, int d0,
                                                const double* __restrict__ s_slope, const double* __restrict__ s_q,
                                                const double* __restrict__ s_base, const double* __restrict__ s_ca,
                                                const int* __restrict__ s_i0, const int* __restrict__ s_span) {
+    if (n0 >= n1) return;
     double slope[NC], hq[NC], base[NC * NACT], ca[NACT];
     int i0[NACT]; bool two[NACT];
 #pragma unroll
     for (int i = 0; i < NC; ++i) { slope[i] = s_slope[i]; hq[i] = 0.5 * s_q[i]; }
 #pragma unroll
     for (int al = 0; al < NACT; ++al) {
-        ca[al] = s_ca[al]; i0[al] = s_i0[al]; two[al] = (s_span[al] & 1) != 0;
+        ca[al] = s_ca[al]; i0[al] = s_i0[al] + d0; two[al] = (s_span[al] & 1) != 0;
 #pragma unroll
         for (int i = 0; i < NC; ++i) base[i * NACT + al] = s_base[i * NACT + al];
     }
-    int cell = lo + threadIdx.x;
+    int cell = n0 * kTableThreads + threadIdx.x;
     double cd = (double)cell;
-    const double dstep = (double)nthr;
-#pragma unroll 4
-    for (; cell < hi; cell += nthr, cd += dstep) {
+#pragma unroll 2
+    for (int n = n0; n < n1; ++n, cell += kTableThreads, cd += (double)kTableThreads) {
         double pen = 0.0;
         if (SAME) {
 #pragma unroll
@@ -422,77 +562,221 @@ __device__ __forceinline__ void sweep_interior(const TT* __restrict__ cur, TT* _
             }
             const TT* src = cur + (cell + i0[al]);
             TT nx = src[0];
-            if (two[al]) nx = table_min<TT>(nx, src[1]);
+            if (two[al]) nx = cmin2(nx, src[1]);
             st += (double)nx;
             best = (al == 0 || st < best) ? st : best;
         }
-        nxt[cell] = to_table<TT>(best + pen);   // FP32: rounded DOWN, so the stored table stays a lower bound
+        put_cell(nxt + cell, best + pen);
     }
 }
+
+// ---- linear cells.  One backward step for a cell with the two actions of the DEWH shape:
+//     g(s) = min( stay: line of the cell d0 away,  move: line of cell m on [lo, t) and of cell m+1 on [t, hi) ) + costs
+//     out  = tightest supporting line of the lower convex hull of g at the hull's lowest vertex
+//            + the stage penalty of every row that the WHOLE cell violates (a cell that straddles a kink gets zero)
+// -- never below the constant-cell bound min g.
+__device__ __forceinline__ double2 hull_line(double y_lo, double y_t, double y_hi, double th, double ith, double i1th) {
+    const double chord = fma(th, y_hi - y_lo, y_lo);
+    if (!(y_t < chord)) return make_double2(y_lo, y_hi);         // no kink below the chord of the end points
+    if (y_t <= fmin(y_lo, y_hi)) return make_double2(y_t, y_t);
+    if (y_lo > y_hi) { const double s2 = (y_hi - y_t) * i1th; return make_double2(y_hi - s2, y_hi); }
+    const double s1 = (y_t - y_lo) * ith;
+    return make_double2(y_lo, y_lo + s1);
+}
+
+struct LinStage {
+    int mask, d0, i1, span1; double fr, c0, c1;
+};
+
+template <int NC, bool CHECKED>
+__device__ __forceinline__ double2 lin_cell(const double2* __restrict__ cur, int cell, int G, double2 lo_out, double2 hi_out,
+                                            const LinStage& L, const double* slope, const double* q, const double* lbase,
+                                            double cd, double feas_tol) {
+    auto at = [&](int i) -> double2 {
+        if (CHECKED) { if (i < 0) return lo_out; if (i >= G) return hi_out; }
+        return cur[i];
+    };
+    const double BIG = INFINITY;
+    double y_lo = BIG, y_hi = BIG, y_t = BIG;
+    const double th = 1.0 - L.fr;
+    if (L.mask & 2) {
+        const int m = cell + L.d0 + L.i1;
+        if (L.span1 == 0) {                       // zero translation: the move is a second "stay"
+            const double2 s = at(m);
+            y_lo = s.x + L.c1; y_hi = s.y + L.c1;
+        } else if (L.span1 == 1) {
+            const double2 a = at(m), bq = at(m + 1);
+            y_lo = fma(L.fr, a.y - a.x, a.x) + L.c1;
+            y_hi = fma(L.fr, bq.y - bq.x, bq.x) + L.c1;
+            y_t = fmin(a.y, bq.x) + L.c1;
+        } else {                                  // the translation lands on a cell boundary: constant over all it can touch
+            const int j0 = (L.span1 & 2) ? m - 1 : m, j1 = (L.span1 & 4) ? m + 2 : m + 1;
+            double mv = BIG;
+            for (int j = j0; j <= j1; ++j) { const double2 a = at(j); mv = fmin(mv, fmin(a.x, a.y)); }
+            y_lo = y_hi = mv + L.c1;
+        }
+    }
+    if (L.mask & 1) {
+        const double2 s = at(cell + L.d0);
+        y_lo = fmin(y_lo, s.x + L.c0); y_hi = fmin(y_hi, s.y + L.c0);
+    }
+    double2 o = hull_line(y_lo, y_t, y_hi, th, 1.0 / th, 1.0 / fmax(L.fr, 1e-300));
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+        const double vL = fma(cd, slope[i], lbase[i]), vR = vL + slope[i];
+        if (fmin(vL, vR) >= 0.0) { o.x = fma(q[i], vL, o.x); o.y = fma(q[i], vR, o.y); }
+    }
+    (void)feas_tol;
+    o.x -= kLinSlop * fabs(o.x); o.y -= kLinSlop * fabs(o.y);
+    return o;
+}
+
+
+// monotone map double -> unsigned 64 (smaller value <=> smaller key), and back
+__device__ __forceinline__ unsigned long long order_key(double x) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(x);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double key_value(unsigned long long k) {
+    if (k == ~0ull) return INFINITY;                                  // untouched slot
+    const unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+    return __longlong_as_double((long long)b);
+}
+// minimum over the warp of a key / of the key of a value: two 32-bit redux.sync
+__device__ __forceinline__ unsigned long long warp_min_key_u(unsigned long long key) {
+    const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+    const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
+    const unsigned mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xffffffffu);
+    return ((unsigned long long)mhi << 32) | mlo;
+}
+__device__ __forceinline__ unsigned long long warp_min_key(double v) { return warp_min_key_u(order_key(v)); }
 
 // NC / NACT > 0: compile-time row and action counts (the DEWH shape is <2, 2>); 0: run-time loops.
 // Per-stage sweep constants (computed for all stages at once, one thread per stage, before the sweep):
 //   ca[k][al]      action cost
-//   base[k][i][al] violation of row i under action al at the favourable edge of cell 0,
+//   base[k][i][al] violation of row i under action al at the favourable edge of local cell 0,
 //   slope[k][i]    ... and its increment per cell:  viol(cell) = slope * cell + base
 //   i0[k][al]      translation of a cell in whole cells; span bit0: also i0+1, bit1: also i0-1, bit2: also i0+2
-//                  (span 0 = identity: the "no input" action maps a cell onto itself exactly)
-//   flags[k]       bit0 fast (every action allowed, no hard row, no boundary-case translation),
-//                  bit1 samepen (row violations do not depend on the action: F = 0, G D = 0)
-template <int NC, int NACT, typename TT>
-__global__ void __launch_bounds__(512) stage_dp_table_kernel(const DpArgs A) {
+//                  (span 0 = identity: the "no input" action maps a cell onto itself exactly);  fr[k][al] its fraction
+//   flags[k]       bit0 fast (every action allowed, no hard row, no boundary-case translation, every read inside the
+//                  guard cells), bit1 samepen (row violations do not depend on the action: F = 0, G D = 0)
+//   z[k]           cells [z0, z1) of a samepen stage violate no row
+template <int NC, int NACT, int FMT>
+__global__ void __launch_bounds__(kTableThreads) stage_dp_table_kernel(const DpArgs A);
+
+struct Node { double s, cost, bound; unsigned long long p0, p1; int k, pad; };
+
+__device__ bool dp_search(const DpArgs& A, const DpCtx& c, int b, Node* stack, double* ptraj, int lane, int budget);
+
+template <int NC, int NACT, int FMT>
+__global__ void __launch_bounds__(kTableThreads) stage_dp_table_kernel(const DpArgs A) {
+    typedef typename Cell<FMT>::T TT;
     extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ unsigned long long s_part[2][kTableThreads / 32][4];
+    __shared__ int s_tail;
     const int b = blockIdx.x;
-    const int nthr = blockDim.x;
+    const int nthr = kTableThreads;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     DpCtx c = bind_ctx(A, smem);
     const DpPlan plan = make_dp_plan(c.Nt, c.nb, c.nc, c.T);
-    // two stage buffers (k+1 / k), each with `pad` guard cells on both sides that hold the out-of-window bound, so
-    // that the hot loop needs no bound checks
-    const int pad = G_PAD(A.G);
     TT* buf0 = reinterpret_cast<TT*>(smem + (size_t)plan.total * 8);
+    const unsigned long long t_start = global_ns();
     dp_load(A, b, c);
     const int G = c.G, Nt = c.Nt;
     const int nc = NC > 0 ? NC : c.nc, nact = NACT > 0 ? NACT : c.nact;
-    const double S0 = c.misc[MISC_S0], w = c.misc[MISC_W];
-    TT* tab = reinterpret_cast<TT*>(A.table) + (int64_t)b * Nt * G;
-    TT* cur = buf0 + pad;                  // stage k+1
-    TT* nxt = buf0 + (G + 2 * pad) + pad;  // stage k (being written)
-    for (int cell = threadIdx.x - pad; cell < G + pad; cell += nthr) cur[cell] = (TT)0;      // LB of the terminal stage
-    __shared__ int s_maxshift;
-    if (threadIdx.x == 0) s_maxshift = 0;
-    __syncthreads();
-    for (int k = threadIdx.x; k < Nt; k += nthr) {
+    const double w = c.misc[MISC_W];
+    TT* tab = reinterpret_cast<TT*>(A.table) + (int64_t)b * A.nstore * G;
+    TT* cur = buf0;                        // stage k+1
+    TT* nxt = buf0 + G;                    // stage k (being written)
+    for (int cell = tid; cell < G; cell += nthr) cur[cell] = Cell<FMT>::pack(0.0);   // terminal stage
+    // ---- per-stage constants, one stage per thread
+    for (int k = tid; k < Nt; k += nthr) {
         const double akk = c.ak[k];
         const int mask = (int)c.amask[k];
-        int fast = mask == (1 << nact) - 1 && c.misc[MISC_TERMS] == 0.0, same = 1;
+        const int offk = c.off[k], d0 = offk - c.off[k + 1];
+        int fast = mask == (1 << nact) - 1 && c.misc[MISC_TERMS] == 0.0, same = 1, hard = 0;
         for (int i = 0; i < nc; ++i) {
             c.sc_slope[k * nc + i] = c.e[i] * akk * w;
-            if (isinf(c.qs[k * nc + i])) fast = 0;
+            if (isinf(c.qs[k * nc + i])) { fast = 0; hard = 1; }
         }
+        int rd_lo = 0, rd_hi = 0;
         for (int al = 0; al < nact; ++al) {
             c.sc_ca[k * nact + al] = action_cost(c, k, al);
             const double ga = c.galpha[al];
             int i0 = 0, span = 0;
+            double fr = 0.0;
             if (ga != 0.0) {
                 const double r = ga * c.iak[k + 1] * c.misc[MISC_INVW];   // translation of a cell, in cells
-                const double fl = floor(r), fr = r - fl;
+                const double fl = floor(r);
+                fr = r - fl;
                 i0 = (int)fmax(fmin(fl, 1.0e9), -1.0e9);
                 span = 1 | (fr < kEdgeEps ? 2 : 0) | (fr > 1.0 - kEdgeEps ? 4 : 0);
             }
-            c.sc_i0[k * nact + al] = i0; c.sc_span[k * nact + al] = span;
+            c.sc_i0[k * nact + al] = i0; c.sc_span[k * nact + al] = span; c.sc_fr[k * nact + al] = fr;
             if (span & 6) fast = 0;
-            atomicMax(&s_maxshift, (i0 < 0 ? -i0 : i0) + 2);
+            rd_lo = min(rd_lo, i0); rd_hi = max(rd_hi, i0 + (span & 1));
             // the cell is widened by a hair (kEdgeEps of its width on both sides) so that the bound also holds for
-            // states that floating-point rounding assigns to it from just outside
+            // states that floating-point rounding assigns to it from just outside; linear cells use the exact left
+            // edge (their look-up takes the neighbour's edge value when a state sits on a boundary)
             for (int i = 0; i < nc; ++i) {
                 const double ei = c.e[i];
-                const double edge = akk * (ei >= 0.0 ? fma(-kEdgeEps, w, S0) : fma(1.0 + kEdgeEps, w, S0));
-                const double bs = fma(ei, edge, c.falpha[i * nact + al] - c.rhs[k * nc + i]);
+                const double pos = FMT == FMT_LIN ? (double)offk : ((double)offk + (ei >= 0.0 ? -kEdgeEps : 1.0 + kEdgeEps));
+                const double bs = fma(ei, akk * (pos * w), c.falpha[i * nact + al] - c.rhs[k * nc + i]);
                 c.sc_base[(k * nc + i) * nact + al] = bs;
-                if (bs != c.sc_base[(k * nc + i) * nact]) same = 0;
+                if (c.falpha[i * nact + al] != c.falpha[i * nact]) same = 0;
             }
         }
-        c.sc_flags[k] = fast | (same << 1);
+        c.sc_flags[k] = fast | (same << 1) | (hard << 2);
+        // cells [z0, z1) of the stage violate no row at their favourable edge (exact test with the sweep's own formula)
+        {
+            int z0 = 0, z1 = same && !hard ? G : 0;
+            auto clean = [&](int cell) {
+                for (int i = 0; i < nc; ++i) if (fma((double)cell, c.sc_slope[k * nc + i], c.sc_base[(k * nc + i) * nact]) > 0.0) return false;
+                return true;
+            };
+            for (int i = 0; i < nc && z1 > z0; ++i) {
+                const double sl = c.sc_slope[k * nc + i], bs = c.sc_base[(k * nc + i) * nact];
+                if (sl > 0.0) { const double t = floor(-bs / sl); z1 = (int)fmin((double)z1, fmax(t + 1.0, 0.0)); }
+                else if (sl < 0.0) { const double t = ceil(-bs / sl); z0 = (int)fmax((double)z0, fmin(t, (double)G)); }
+                else if (bs > 0.0) z1 = z0;
+            }
+            int guard = 0;
+            while (z0 < z1 && !clean(z0) && guard++ < 64) ++z0;
+            while (z1 > z0 && !clean(z1 - 1) && guard++ < 128) --z1;
+            if (z1 <= z0 || !clean(z0) || !clean(z1 - 1)) { z0 = 0; z1 = 0; }
+            c.sc_z[2 * k] = z0; c.sc_z[2 * k + 1] = z1;
+        }
+        // the two semi-infinite cells of the stage: which next-stage cells their images can touch (below the window
+        // under the identity action: <= jl0, under any other action: <= jl1; above: >= jh0 / >= jh1), the cheapest
+        // action cost of either kind, and the stage penalty at the favourable edge of each of them
+        {
+            int jl0 = INT_MIN, jl1 = INT_MIN, jh0 = INT_MAX, jh1 = INT_MAX;
+            double c_id = INFINITY, c_rest = INFINITY;
+            for (int al = 0; al < nact; ++al) {
+                if (!(mask >> al & 1)) continue;
+                const int sp = c.sc_span[k * nact + al], i0 = c.sc_i0[k * nact + al];
+                if (al == 0 && sp == 0) { jl0 = d0 - 1; jh0 = d0 + G; c_id = c.sc_ca[k * nact]; continue; }
+                jl1 = max(jl1, d0 - 1 + i0 + (sp ? 2 : 0));
+                jh1 = min(jh1, d0 + G + i0 - (sp ? 1 : 0));
+                c_rest = fmin(c_rest, c.sc_ca[k * nact + al]);
+            }
+            double plo = 0.0, phi = 0.0;
+            for (int i = 0; i < nc; ++i) {
+                const double ei = c.e[i], q = c.qs[k * nc + i];
+                if (ei == 0.0) continue;
+                double fm = INFINITY;
+                for (int al = 0; al < nact; ++al) if (mask >> al & 1) fm = fmin(fm, c.falpha[i * nact + al]);
+                const double pos = ei < 0.0 ? ((double)offk + kEdgeEps) : ((double)offk + (double)G - kEdgeEps);
+                const double viol = fma(ei, akk * (pos * w), fm - c.rhs[k * nc + i]);
+                double add = 0.0;
+                if (isinf(q)) { if (viol > c.feas_tol) add = INFINITY; }
+                else if (viol > 0.0) add = q * viol;
+                if (ei < 0.0) plo += add; else phi += add;
+            }
+            c.sc_semi[8 * k] = jl0; c.sc_semi[8 * k + 1] = jl1; c.sc_semi[8 * k + 2] = jh0; c.sc_semi[8 * k + 3] = jh1;
+            c.sc_semi[8 * k + 4] = rd_lo; c.sc_semi[8 * k + 5] = rd_hi;
+            c.sc_semd[4 * k] = c_id; c.sc_semd[4 * k + 1] = c_rest; c.sc_semd[4 * k + 2] = plo; c.sc_semd[4 * k + 3] = phi;
+        }
         // forward-search constants
         for (int i = 0; i < nc; ++i) {
             c.x_eak[k * nc + i] = c.e[i] * akk;
@@ -507,40 +791,187 @@ __global__ void __launch_bounds__(512) stage_dp_table_kernel(const DpArgs A) {
         for (int i = 0; i < nc; ++i) if (isinf(c.qs[k * nc + i])) c.misc[MISC_SIMPLE] = 0.0;
     }
     __syncthreads();
-    {   // hand the stage data to the search kernel
-        const double* src = reinterpret_cast<const double*>(smem);
-        double* dst = A.pblk + (int64_t)b * plan.nd;
-        for (int i = threadIdx.x; i < plan.nd; i += nthr) dst[i] = src[i];
+    // linear cells proper need the DEWH shape on every stage (else the agent's cells carry constant lines)
+    bool lin_ok = false;
+    if (FMT == FMT_LIN && NACT == 2) {
+        lin_ok = c.misc[MISC_TERMS] == 0.0 && c.galpha[0] == 0.0;
+        for (int k = 1; k < Nt && lin_ok; ++k) {
+            const int fl = c.sc_flags[k], mask = (int)c.amask[k];
+            if (!(fl & 2) || (fl & 4) || mask == 0) lin_ok = false;
+        }
     }
-    if (c.misc[MISC_FLAG] != 0.0) return;
+    {   // executed FP64-pipe instructions of the sweep (for the roofline): per cell 4 (two compares, two adds) without
+        // and 5 + 3 NC with penalty arithmetic on the hand-tuned path; the other paths at their mix per action
+        double kins = 0.0;
+        for (int k = 1 + tid; k < Nt; k += nthr) {
+            const int zc = c.sc_z[2 * k + 1] - c.sc_z[2 * k];
+            const int fl = c.sc_flags[k];
+            if (FMT == FMT_LIN) kins += (double)G * (22.0 + 4.0 * nc);
+            else if ((fl & 1) && (fl & 2) && nact == 2) kins += 4.0 * zc + (5.0 + 3.0 * nc) * (G - zc);
+            else kins += (double)G * nact * (3.0 + 3.0 * nc);
+        }
+        if (warp < (Nt + 31) / 32) { kins = warp_sum(kins); if (lane == 0) s_part[0][warp][0] = (unsigned long long)__double_as_longlong(kins); }
+        __syncthreads();
+        if (tid == 0) {
+            double tot = 0.0;
+            for (int wv = 0; wv < (Nt + 31) / 32; ++wv) tot += __longlong_as_double((long long)s_part[0][wv][0]);
+            c.misc[MISC_KINS] = tot;
+            c.misc[MISC_LINOK] = lin_ok ? 1.0 : 0.0;
+        }
+        __syncthreads();
+    }
+    const bool bad_agent = c.misc[MISC_FLAG] != 0.0;
+    if (bad_agent) {
+        double* vout = A.v + (int64_t)b * Nt * c.nv;
+        for (int j = tid; j < Nt * c.nv; j += nthr) vout[j] = nan("");
+        if (tid == 0) {
+            A.status[b] = HMPC_SOLVE_UNSUPPORTED; A.obj[b] = INFINITY;
+            for (int i = 0; i < 8; ++i) A.stats[(int64_t)b * 8 + i] = 0;
+        }
+        return;
+    }
+    const unsigned long long t_setup = global_ns();
+    // bounds of the two semi-infinite cells: S_k = f(minima of stage k+1 over the cells their images can touch, S_k+1).
+    // Iteration k (a) finishes S_k+1 from the per-warp minima that iteration k+1 left in shared memory, (b) leaves the
+    // minima for S_k (over `cur` = stage k+1), (c) sweeps the cells of stage k -- one barrier per stage.
+    Semi S_next; S_next.lo = 0.0; S_next.hi = 0.0;        // S_k+1 (the terminal stage costs nothing)
+    auto finish_semi = [&](int kk, Semi above) -> Semi {  // S_kk from the minima of parity kk & 1 and S_kk+1 = above
+        const int jl0 = c.sc_semi[8 * kk], jl1 = c.sc_semi[8 * kk + 1], jh0 = c.sc_semi[8 * kk + 2], jh1 = c.sc_semi[8 * kk + 3];
+        const unsigned long long* part = &s_part[kk & 1][0][0];
+        const int pl = lane < kTableThreads / 32 ? lane : 0;
+        double m0 = INFINITY, m1 = INFINITY, m2 = INFINITY, m3 = INFINITY;
+        if (jl0 >= 0) m0 = key_value(warp_min_key_u(part[pl * 4 + 0]));
+        if (jl1 >= 0) m1 = key_value(warp_min_key_u(part[pl * 4 + 1]));
+        if (jh0 < G) m2 = key_value(warp_min_key_u(part[pl * 4 + 2]));
+        if (jh1 < G) m3 = key_value(warp_min_key_u(part[pl * 4 + 3]));
+        // images that reach beyond the next window on either side
+        if (jl0 != INT_MIN) { m0 = dmin(m0, above.lo); if (jl0 >= G) m0 = dmin(m0, above.hi); m2 = dmin(m2, above.hi); if (jh0 < 0) m2 = dmin(m2, above.lo); }
+        if (jl1 != INT_MIN) { m1 = dmin(m1, above.lo); if (jl1 >= G) m1 = dmin(m1, above.hi); m3 = dmin(m3, above.hi); if (jh1 < 0) m3 = dmin(m3, above.lo); }
+        const double c_id = c.sc_semd[4 * kk], c_rest = c.sc_semd[4 * kk + 1];
+        Semi r;
+        r.lo = dmin(c_id + m0, c_rest + m1) + c.sc_semd[4 * kk + 2];
+        r.hi = dmin(c_id + m2, c_rest + m3) + c.sc_semd[4 * kk + 3];
+        if (tid == 0) { c.loinf[kk] = r.lo; c.hiinf[kk] = r.hi; }
+        return r;
+    };
+    const int wbase = warp * 32;
+    const int nblocks = (G + kTableThreads - 1) / kTableThreads;
     for (int k = Nt - 1; k >= 1; --k) {
-        const TT out_next = to_table<TT>(c.tailmin[k + 1]);
-        TT* tabk = tab + (int64_t)k * G;
+        if (k < Nt - 1) S_next = finish_semi(k + 1, S_next);
         const int flags = c.sc_flags[k];
+        const int mask = (int)c.amask[k];
+        const int offk = c.off[k], d0 = offk - c.off[k + 1];
         const double* s_ca = c.sc_ca + k * nact; const double* s_base = c.sc_base + k * nc * nact;
         const double* s_slope = c.sc_slope + k * nc; const double* s_q = c.qs + k * nc;
         const int* s_i0 = c.sc_i0 + k * nact; const int* s_span = c.sc_span + k * nact;
-        // every translated neighbour lands inside the guard cells: the whole stage goes through the hot loop
-        const bool fast = (flags & 1) && NC > 0 && s_maxshift <= pad;
-        const int lo = 0, hi = G;
-        if (fast) {
-            if (flags & 2) sweep_interior<(NC > 0 ? NC : 1), (NACT > 0 ? NACT : 1), true, TT>(cur, nxt, lo, hi, nthr, s_slope, s_q, s_base, s_ca, s_i0, s_span);
-            else sweep_interior<(NC > 0 ? NC : 1), (NACT > 0 ? NACT : 1), false, TT>(cur, nxt, lo, hi, nthr, s_slope, s_q, s_base, s_ca, s_i0, s_span);
-        }
+        // ---- (b) minima of stage k+1 over the cells the images of this stage's semi-infinite cells can touch
         {
-            // ---- general loop: restricted action sets, hard rows, translations that land on a cell boundary or
-            //      beyond the guard cells
-            const int mask = (int)c.amask[k];
-            const int nedge = fast ? lo + (G - hi) : G;
-            for (int e = threadIdx.x; e < nedge; e += nthr) {
-                const int cell = fast ? (e < lo ? e : hi + (e - lo)) : e;
+            const int jl0 = c.sc_semi[8 * k], jl1 = c.sc_semi[8 * k + 1], jh0 = c.sc_semi[8 * k + 2], jh1 = c.sc_semi[8 * k + 3];
+            unsigned long long* part = &s_part[k & 1][warp][0];
+            const int jl = min(max(jl0, jl1), G - 1), jh = min(jh0, jh1);
+            if (jl >= 0) {
+                double m0 = INFINITY, m1 = INFINITY;
+                for (int j = tid; j <= jl; j += nthr) {
+                    const double v = Cell<FMT>::lo(cur[j]);
+                    if (j <= jl0) m0 = dmin(m0, v);
+                    if (j <= jl1) m1 = dmin(m1, v);
+                }
+                if (jl0 >= 0) { const unsigned long long kk = warp_min_key(m0); if (lane == 0) part[0] = kk; }
+                if (jl1 >= 0) { const unsigned long long kk = warp_min_key(m1); if (lane == 0) part[1] = kk; }
+            }
+            if (jh < G) {
+                double m2 = INFINITY, m3 = INFINITY;
+                for (int j = max(jh, 0) + tid; j < G; j += nthr) {
+                    const double v = Cell<FMT>::lo(cur[j]);
+                    if (j >= jh0) m2 = dmin(m2, v);
+                    if (j >= jh1) m3 = dmin(m3, v);
+                }
+                if (jh0 < G) { const unsigned long long kk = warp_min_key(m2); if (lane == 0) part[2] = kk; }
+                if (jh1 < G) { const unsigned long long kk = warp_min_key(m3); if (lane == 0) part[3] = kk; }
+            }
+        }
+        // ---- (c) the cells of the window.  Blocks [na, nb) of this warp are interior: every cell they read is inside
+        // the next stage's window.
+        const bool fast = (flags & 1) && NC > 0;
+        int na = 0, nb_ = 0;
+        if (fast) {
+            const int rd_lo = c.sc_semi[8 * k + 4], rd_hi = c.sc_semi[8 * k + 5];
+            const int lo_need = -(wbase + d0 + rd_lo);                    // n * 512 >= lo_need
+            const int hi_room = G - 1 - wbase - 31 - d0 - max(rd_hi, -d0);  // n * 512 <= hi_room (and the cells exist)
+            na = max((lo_need + kTableThreads - 1) >> 9, 0);
+            nb_ = hi_room >= 0 ? (hi_room >> 9) + 1 : 0;
+            if (nb_ < na) nb_ = na;
+        }
+        Semi out = S_next;
+        if (FMT == FMT_LIN && lin_ok) {
+            LinStage L;
+            L.mask = mask; L.d0 = d0; L.i1 = s_i0[1]; L.span1 = s_span[1]; L.fr = c.sc_fr[k * nact + 1];
+            L.c0 = s_ca[0]; L.c1 = s_ca[1];
+            double slope[NC > 0 ? NC : 1], q[NC > 0 ? NC : 1], lbase[NC > 0 ? NC : 1];
+#pragma unroll
+            for (int i = 0; i < (NC > 0 ? NC : 1); ++i) { slope[i] = s_slope[i]; q[i] = s_q[i]; lbase[i] = s_base[i * nact]; }
+            const double2* cur2 = reinterpret_cast<const double2*>(cur);
+            double2* nxt2 = reinterpret_cast<double2*>(nxt);
+            const double2 lo2 = make_double2(out.lo, out.lo), hi2 = make_double2(out.hi, out.hi);
+            if (!(fast && L.span1 == 1)) { na = 0; nb_ = 0; }
+            for (int n = 0; n < na; ++n) {
+                const int cell = n * kTableThreads + tid;
+                if (cell < G) nxt2[cell] = lin_cell<(NC > 0 ? NC : 1), true>(cur2, cell, G, lo2, hi2, L, slope, q, lbase, (double)cell, c.feas_tol);
+            }
+#pragma unroll 2
+            for (int n = na; n < nb_; ++n) {
+                const int cell = n * kTableThreads + tid;
+                nxt2[cell] = lin_cell<(NC > 0 ? NC : 1), false>(cur2, cell, G, lo2, hi2, L, slope, q, lbase, (double)cell, c.feas_tol);
+            }
+            for (int n = nb_; n < nblocks; ++n) {
+                const int cell = n * kTableThreads + tid;
+                if (cell < G) nxt2[cell] = lin_cell<(NC > 0 ? NC : 1), true>(cur2, cell, G, lo2, hi2, L, slope, q, lbase, (double)cell, c.feas_tol);
+            }
+        } else if (fast && FMT != FMT_LIN && NACT == 2 && (flags & 2) && s_span[0] == 0 && s_span[1] == 1) {
+            typedef typename Cell<FMT == FMT_LIN ? FMT_F64 : FMT>::T ST;     // (scalar formats only)
+            const ST* curs = reinterpret_cast<const ST*>(cur);
+            ST* nxts = reinterpret_cast<ST*>(nxt);
+            constexpr int NCc = NC > 0 ? NC : 1;
+            double slope[NCc], hq[NCc], base[NCc];
+#pragma unroll
+            for (int i = 0; i < NCc; ++i) { slope[i] = s_slope[i]; hq[i] = 0.5 * s_q[i]; base[i] = s_base[i * 2]; }
+            const double c0 = s_ca[0], c1 = s_ca[1];
+            const int i1 = s_i0[1];
+            // penalty-free blocks of this warp: all 32 cells inside [z0, z1)
+            const int z0 = c.sc_z[2 * k], z1 = c.sc_z[2 * k + 1];
+            int za = max((z0 - wbase + kTableThreads - 1) >> 9, 0), zb = ((z1 - 32 - wbase) >> 9) + 1;
+            za = min(max(za, na), nb_); zb = min(max(zb, za), nb_);
+            sweep_same2<NCc, true, true, ST>(curs, nxts, G, 0, na, d0, i1, slope, hq, base, c0, c1, out);
+            sweep_same2<NCc, true, false, ST>(curs, nxts, G, na, za, d0, i1, slope, hq, base, c0, c1, out);
+            sweep_same2<NCc, false, false, ST>(curs, nxts, G, za, zb, d0, i1, slope, hq, base, c0, c1, out);
+            sweep_same2<NCc, true, false, ST>(curs, nxts, G, zb, nb_, d0, i1, slope, hq, base, c0, c1, out);
+            sweep_same2<NCc, true, true, ST>(curs, nxts, G, nb_, nblocks, d0, i1, slope, hq, base, c0, c1, out);
+        } else {
+            if (fast && FMT != FMT_LIN) {
+                typedef typename Cell<FMT == FMT_LIN ? FMT_F64 : FMT>::T ST;
+                const ST* curs = reinterpret_cast<const ST*>(cur);
+                ST* nxts = reinterpret_cast<ST*>(nxt);
+                if (flags & 2)
+                    sweep_interior<(NC > 0 ? NC : 1), (NACT > 0 ? NACT : 1), true, ST>(curs, nxts, na, nb_, d0, s_slope, s_q, s_base, s_ca, s_i0, s_span);
+                else
+                    sweep_interior<(NC > 0 ? NC : 1), (NACT > 0 ? NACT : 1), false, ST>(curs, nxts, na, nb_, d0, s_slope, s_q, s_base, s_ca, s_i0, s_span);
+            } else { na = 0; nb_ = 0; }
+            // ---- general loop (the blocks outside [na, nb)): restricted action sets, hard rows, convex terms,
+            //      translations that land on a cell boundary, reads beyond the window (constant bound per cell in
+            //      every format)
+            for (int n = 0; n < nblocks; ++n) {
+                if (n == na) { n = nb_; if (n >= nblocks) break; }
+                const int cell = n * kTableThreads + tid;
+                if (cell >= G) break;
                 const double cd = (double)cell;
                 double best = INFINITY;
                 for (int al = 0; al < nact; ++al) {
                     if (!(mask >> al & 1)) continue;
                     double st = s_ca[al];
                     for (int i = 0; i < nc; ++i) {
-                        const double viol = fma(cd, s_slope[i], s_base[i * nact + al]);
+                        double viol = fma(cd, s_slope[i], s_base[i * nact + al]);
+                        if (FMT == FMT_LIN)        // base is the exact left edge here: move to the favourable, widened edge
+                            viol += s_slope[i] * (s_slope[i] >= 0.0 ? -kEdgeEps : 1.0 + kEdgeEps);
                         const double q = s_q[i];
                         if (isinf(q)) { if (viol > c.feas_tol) st = INFINITY; }
                         else {
@@ -550,41 +981,60 @@ __global__ void __launch_bounds__(512) stage_dp_table_kernel(const DpArgs A) {
                         }
                     }
                     if (c.T > 0) {
-                        const double plo = c.ak[k] * fma(cd - kEdgeEps, w, S0);
-                        const double phi = c.ak[k] * fma(cd + 1.0 + kEdgeEps, w, S0);
-                        st += terms_lower_bound(c, k, al, plo, phi);
+                        const double plo_ = c.ak[k] * (((double)offk + cd - kEdgeEps) * w);
+                        const double phi_ = c.ak[k] * (((double)offk + cd + 1.0 + kEdgeEps) * w);
+                        st += terms_lower_bound(c, k, al, plo_, phi_);
                     }
                     const int span = s_span[al];
-                    const long long c0 = (long long)cell + s_i0[al];
-                    auto at = [&](long long i) -> TT { return (i < 0 || i >= G) ? out_next : cur[i]; };
-                    TT nx = at(c0);
-                    if (span & 1) nx = table_min<TT>(nx, at(c0 + 1));
-                    if (span & 2) nx = table_min<TT>(nx, at(c0 - 1));
-                    if (span & 4) nx = table_min<TT>(nx, at(c0 + 2));
-                    st += (double)nx;
+                    const long long c0 = (long long)cell + d0 + s_i0[al];
+                    auto at = [&](long long i) -> double { return i < 0 ? out.lo : (i >= G ? out.hi : Cell<FMT>::lo(cur[i])); };
+                    double nx = at(c0);
+                    if (span & 1) nx = dmin(nx, at(c0 + 1));
+                    if (span & 2) nx = dmin(nx, at(c0 - 1));
+                    if (span & 4) nx = dmin(nx, at(c0 + 2));
+                    st += nx;
                     best = st < best ? st : best;
                 }
-                nxt[cell] = to_table<TT>(best);
+                nxt[cell] = Cell<FMT>::pack(best);
             }
         }
-        // guard cells of the stage just written: the bound of states outside the window at stage k
-        {
-            const TT out_k = to_table<TT>(c.tailmin[k]);
-            for (int i = threadIdx.x; i < pad; i += nthr) { nxt[-1 - i] = out_k; nxt[G + i] = out_k; }
-        }
-        // the buffer the NEXT stage overwrites is the source of the bulk copy issued one stage ago: it must have
+        // the buffer the NEXT stage overwrites is the source of the bulk copy issued at most D stages ago: it must have
         // been read completely before anybody passes the barrier
-        if (threadIdx.x == 0) bulk_wait_source_free();
+        if (tid == 0) bulk_wait_source_free();
         __syncthreads();
-        if (threadIdx.x == 0) bulk_store_stage(tabk, nxt, (unsigned)G * sizeof(TT));   // stage k -> HBM, asynchronously
+        if (tid == 0 && k % A.D == 0 && k / A.D <= A.nstore)
+            bulk_store_stage(tab + (int64_t)(k / A.D - 1) * G, nxt, (unsigned)G * sizeof(TT));   // stage k -> L2 / HBM, asynchronously
         TT* t = cur; cur = nxt; nxt = t;
     }
-    if (threadIdx.x == 0) bulk_wait_all();
+    if (Nt > 1) S_next = finish_semi(1, S_next);      // (stage 1 is read by the search when D == 1)
+    if (tid == 0) {
+        bulk_wait_all(); asm volatile("fence.proxy.async;" ::: "memory");
+        c.misc[MISC_T_SETUP] = (double)(t_setup - t_start); c.misc[MISC_T_SWEEP] = (double)(global_ns() - t_setup);
+    }
+    __syncthreads();
+    const DpPlan plan2 = plan;
+    if (A.fuse) {
+        // ---- tail: warp 0 searches this agent right away (stage data still in shared memory, table in L2)
+        if (tid == 0) s_tail = 0;
+        Node* stack = reinterpret_cast<Node*>(buf0);
+        double* ptraj = reinterpret_cast<double*>(stack + kStackCap);
+        __syncthreads();
+        if (warp == 0) {
+            const bool done = dp_search(A, c, b, stack, ptraj, lane, kTailBudget);
+            if (lane == 0) s_tail = done ? 0 : 1;
+        }
+        __syncthreads();
+        if (s_tail == 0) return;
+    }
+    {   // hand the stage data to the search kernel
+        const double* src = reinterpret_cast<const double*>(smem);
+        double* dst = A.pblk + (int64_t)b * plan2.nd;
+        for (int i = tid; i < plan2.nd; i += nthr) dst[i] = src[i];
+        if (tid == 0) A.status[b] = kPending;
+    }
 }
 
-// ------------------------------------------------------------------------------------------------ kernel 2
-struct Node { double s, cost, bound; unsigned long long p0, p1; int k, pad; };
-
+// ------------------------------------------------------------------------------------------------ search
 __device__ __forceinline__ void path_set(unsigned long long& p0, unsigned long long& p1, int k, int nb, int al) {
     const int pos = k * nb;
     const unsigned long long a = (unsigned long long)al;
@@ -605,15 +1055,9 @@ __device__ __forceinline__ void path_set_bits(unsigned long long& p0, unsigned l
     else p1 |= val << (pos - 64);
 }
 
-// monotone map double -> unsigned 64 (smaller value <=> smaller key)
-__device__ __forceinline__ unsigned long long order_key(double x) {
-    const unsigned long long b = (unsigned long long)__double_as_longlong(x);
-    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
-}
-
 // lane holding the smallest `val` among the lanes with `flag` (lowest lane on exact ties), -1 if none:
 // two 32-bit redux.sync + one ballot instead of a 5-step shuffle butterfly
-__device__ __forceinline__ int warp_argmin(bool flag, double val, int lane) {
+__device__ __forceinline__ int warp_argmin(bool flag, double val) {
     const unsigned fm = __ballot_sync(0xffffffffu, flag);
     if (fm == 0) return -1;
     const unsigned long long key = flag ? order_key(val) : ~0ull;
@@ -622,20 +1066,38 @@ __device__ __forceinline__ int warp_argmin(bool flag, double val, int lane) {
     const bool cand = flag && hi == mhi;
     const unsigned mlo = __reduce_min_sync(0xffffffffu, cand ? lo : 0xffffffffu);
     const unsigned wm = __ballot_sync(0xffffffffu, cand && lo == mlo);
-    (void)lane;
     return wm ? __ffs(wm) - 1 : __ffs(fm) - 1;
+}
+
+// Table bound of the cost-to-go from the exact state s at a stored stage k (a multiple of D).  The table may have been
+// written by this very kernel (fused tail): read through L2 (ld.global.cg), never through the non-coherent path.
+struct TabRef { const void* tab; int fmt, G, D; double invw; const int* off; const double* loinf; const double* hiinf; bool linok; };
+
+__device__ __forceinline__ double table_bound(const TabRef& t, int k, double s) {
+    const double x = fma(s, t.invw, -(double)t.off[k]);
+    const double fl = floor(x);
+    if (!(fl >= 0.0)) return t.loinf[k];
+    if (!(fl < (double)t.G)) return t.hiinf[k];
+    const int64_t idx = (int64_t)(k / t.D - 1) * t.G + (int)fl;
+    if (t.fmt == FMT_F64) return __ldcg(reinterpret_cast<const double*>(t.tab) + idx);
+    if (t.fmt == FMT_F32) return (double)__ldcg(reinterpret_cast<const float*>(t.tab) + idx);
+    const double2* tp = reinterpret_cast<const double2*>(t.tab) + idx;
+    const double2 e = __ldcg(tp);
+    if (!t.linok) return fmin(e.x, e.y);
+    const double fr = x - fl;
+    double v = fma(fr, e.y - e.x, e.x);
+    // a state on a cell boundary (within rounding) may belong to the neighbour: take the lower of the two edge values
+    if (fr < kEdgeEps) v = fmin(v, fl >= 1.0 ? __ldcg(tp - 1).y : t.loinf[k]);
+    if (fr > 1.0 - kEdgeEps) v = fmin(v, fl + 1.0 < (double)t.G ? __ldcg(tp + 1).x : t.hiinf[k]);
+    return v;
 }
 
 // Branch-free evaluation of lane's action sequence (depth D, NB binaries per stage, NC soft rows, every action
 // allowed): the D states are a short FMA chain, the table read of the final state is issued before the D
 // independent stage costs are computed, so its latency is hidden behind them.
-__device__ __forceinline__ double table_read(const void* tab, bool fp64, int64_t idx) {
-    return fp64 ? __ldg(reinterpret_cast<const double*>(tab) + idx) : (double)__ldg(reinterpret_cast<const float*>(tab) + idx);
-}
-
 template <int NC, int NB, int D>
-__device__ __forceinline__ bool expand_simple(const DpCtx& c, const void* __restrict__ tab, bool fp64, int k0, int lane, double S0,
-                                              double invw, double& s, double& cost, unsigned long long& q0,
+__device__ __forceinline__ bool expand_simple(const DpCtx& c, const TabRef& tr, int k0, int lane,
+                                              double& s, double& cost, unsigned long long& q0,
                                               unsigned long long& q1, double cut, double& bd, bool& leaf) {
     constexpr int NACT = 1 << NB;
     const int Nt = c.Nt;
@@ -652,12 +1114,7 @@ __device__ __forceinline__ bool expand_simple(const DpCtx& c, const void* __rest
         st[t + 1] = st[t] + (t < De ? c.x_shift[k * NACT + al[t]] : 0.0);
     }
     double lbf = 0.0;
-    bool inwin = false;
-    if (!leaf) {
-        const double fl = floor((st[D] - S0) * invw);
-        inwin = fl >= 0.0 && fl < (double)c.G;
-        if (ok && inwin) lbf = table_read(tab, fp64, (int64_t)(k0 + D) * c.G + (int)fl);
-    }
+    if (!leaf && ok) lbf = table_bound(tr, k0 + D, st[D]);
 #pragma unroll
     for (int t = 0; t < D; ++t) {
         if (t < De) {
@@ -673,93 +1130,67 @@ __device__ __forceinline__ bool expand_simple(const DpCtx& c, const void* __rest
     }
     path_set_bits(q0, q1, k0 * NB, NB * De, (unsigned long long)(lane & ((1 << (NB * De)) - 1)));
     s = st[D];
+    bd = leaf ? cost : cost + lbf;
+    if (!ok) bd = INFINITY;
     ok = ok && cost + c.tailmin[k0 + De] < cut;      // (the costs still ahead may be negative: tailmin <= 0)
-    bd = cost;
-    if (!leaf) {
-        bd = cost + (inwin ? lbf : c.tailmin[k0 + D]);
-        ok = ok && bd < cut;
-    }
+    ok = ok && bd < cut;
     return ok;
 }
 
 // One warp per agent.  The unit of work is the depth-D subtree below one open node, D = the largest depth with
 // nact^D <= 32: lane l evaluates the action sequence whose base-nact digits are l -- exact stage costs, exact
 // states -- and closes it with the table bound of the state it reaches (one table read per lane per iteration).
-//   search : depth-first from the root; a sequence survives when cost + bound < incumbent, the best survivor goes
-//            on top of the stack; whole runs of dominated nodes are discarded in one step.  The first descent has no
-//            incumbent yet, so it is a greedy dive that also leaves every sibling (with its exact bound) on the stack;
-//   dive   : on long horizons those siblings would not fit, so a separate greedy dive (best lane of every subtree,
-//            nothing pushed) produces the incumbent first and the search then starts from the root with it.
-__global__ void __launch_bounds__(kSearchWarps * 32) stage_dp_search_kernel(const DpArgs A) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.x * kSearchWarps + warp;
-    if (b >= A.d.B) return;
-    const DpPlan plan = make_dp_plan(A.d.Nt, A.nb, A.d.nc, A.T);
-    const size_t per_warp = (size_t)plan.nd * 8 + sizeof(Node) * kStackCap + 8 * (kDpMaxNt + 1);
-    unsigned char* base = smem + per_warp * warp;
-    DpCtx c = bind_ctx(A, base);
-    Node* stack = reinterpret_cast<Node*>(base + (size_t)plan.nd * 8);
-    double* ptraj = reinterpret_cast<double*>(stack + kStackCap);
-    {
-        const double* src = A.pblk + (int64_t)b * plan.nd;
-        double* dst = reinterpret_cast<double*>(base);
-        for (int i = lane; i < plan.nd; i += 32) dst[i] = src[i];
-    }
-    __syncwarp();
+//   search : depth-first from the root; a sequence survives when cost + bound < min(incumbent, T), the best survivor
+//            goes on top of the stack; whole runs of dominated nodes are discarded in one step;
+//   T      : threshold of the pass.  The first pass sets it a hair above the best bound of the root's children; a pass
+//            that exhausts the tree below T without a solution is repeated with four times the distance;
+//   dive   : on long horizons the siblings of a first descent would not fit the stack, so a separate greedy dive (best
+//            lane of every subtree, nothing pushed) produces an incumbent first.
+// Returns false when `budget` expansions were not enough (fused tail): the incumbent goes to misc[] for kernel 2.
+__device__ bool dp_search(const DpArgs& A, const DpCtx& c, int b, Node* stack, double* ptraj, int lane, int budget) {
     const int Nt = c.Nt, nb = c.nb, nc = c.nc, nv = c.nv, nact = c.nact;
     double* vout = A.v + (int64_t)b * Nt * nv;
     int32_t* st_out = A.stats + (int64_t)b * 8;
-    if (c.misc[MISC_FLAG] != 0.0) {
-        for (int j = lane; j < Nt * nv; j += 32) vout[j] = nan("");
-        if (lane == 0) { A.status[b] = HMPC_SOLVE_UNSUPPORTED; A.obj[b] = INFINITY; for (int i = 0; i < 8; ++i) st_out[i] = 0; }
-        return;
-    }
-    const double S0 = c.misc[MISC_S0], invw = c.misc[MISC_INVW], a = c.misc[MISC_A];
-    const bool fp64 = A.o.table_fp64 != 0;
-    const void* tab = fp64 ? (const void*)(reinterpret_cast<const double*>(A.table) + (int64_t)b * Nt * c.G)
-                           : (const void*)(A.table + (int64_t)b * Nt * c.G);
-    const int D = nb == 1 ? 5 : (nb == 2 ? 2 : 1);      // nact^D <= 32
+    const double a = c.misc[MISC_A];
+    const unsigned long long t_search = global_ns();
+    TabRef tr;
+    tr.fmt = A.fmt; tr.G = c.G; tr.D = A.D; tr.invw = c.misc[MISC_INVW]; tr.off = c.off; tr.loinf = c.loinf; tr.hiinf = c.hiinf;
+    tr.linok = c.misc[MISC_LINOK] != 0.0;
+    tr.tab = reinterpret_cast<const unsigned char*>(A.table) + (int64_t)b * A.nstore * c.G * fmt_bytes(A.fmt);
+    const int D = A.D;
 
-    double best = INFINITY;
-    unsigned long long bp0 = 0, bp1 = 0;
-    int nodes = 0, improvements = 0, max_sp = 0;
-    bool limit = false;
+    double best = c.misc[MISC_INC_OBJ];
+    unsigned long long bp0 = (unsigned long long)__double_as_longlong(c.misc[MISC_INC_P0]);
+    unsigned long long bp1 = (unsigned long long)__double_as_longlong(c.misc[MISC_INC_P1]);
+    int nodes = (int)c.misc[MISC_NODES0], improvements = (int)c.misc[MISC_IMPR0], max_sp = 0;
+    const int nodes_in = nodes;
+    bool limit = false, defer = false;
 
-    const bool simple21 = c.misc[MISC_SIMPLE] != 0.0 && nb == 1 && nc == 2;
+    const bool simple21 = c.misc[MISC_SIMPLE] != 0.0 && nb == 1 && nc == 2 && D == 5;
     // evaluate lane's action sequence below node (k0, s, cost, path); returns ok, and (k1, s, cost, path, bd)
     auto expand = [&](int k0, double& s, double& cost, unsigned long long& q0, unsigned long long& q1, double cut,
                       double& bd, bool& leaf) -> bool {
-        if (simple21) return expand_simple<2, 1, 5>(c, tab, fp64, k0, lane, S0, invw, s, cost, q0, q1, cut, bd, leaf);
+        if (simple21) return expand_simple<2, 1, 5>(c, tr, k0, lane, s, cost, q0, q1, cut, bd, leaf);
         const int De = (Nt - k0) < D ? (Nt - k0) : D;
         bool ok = lane < (1 << (nb * De));
         for (int t = 0; t < De; ++t) {
             if (!ok) break;
             const int k = k0 + t, al = (lane >> (t * nb)) & (nact - 1);
-            if (!(((int)c.amask[k] >> al) & 1)) { ok = false; break; }
+            if (!(((int)c.amask[k] >> al) & 1)) { ok = false; cost = INFINITY; break; }
             cost += stage_cost(c, k, al, c.ak[k] * s);
             s = fma(c.galpha[al], c.iak[k + 1], s);
             path_set(q0, q1, k, nb, al);
             if (!(cost + c.tailmin[k + 1] < cut)) ok = false;   // partial cost + the most negative costs still ahead
         }
         leaf = (k0 + De == Nt);
-        bd = cost;
+        bd = lane < (1 << (nb * De)) ? cost : INFINITY;
         if (ok && !leaf) {
-            const int k1 = k0 + De;
-            const double fl = floor((s - S0) * invw);
-            const double lbv = (fl >= 0.0 && fl < (double)c.G) ? table_read(tab, fp64, (int64_t)k1 * c.G + (int)fl)
-                                                               : c.tailmin[k1];
-            bd = cost + lbv;
+            bd = cost + table_bound(tr, k0 + De, s);
             ok = bd < cut;
         }
         return ok;
     };
-    auto argmin_lane = [&](bool flag, double val) -> int { return warp_argmin(flag, val, lane); };
 
-    // ---- phase A: greedy dive.  Only when the stack could not hold every sibling of a first dive that runs inside
-    // phase B itself (long horizons): otherwise phase B starts without an incumbent, its first descent IS the dive,
-    // the siblings it pushes carry their exact bounds and are discarded 32 at a time once the incumbent exists --
-    // cheaper than walking the optimal path a second time.
     const bool two_phase = ((Nt + D - 1) / D) * ((1 << (nb * D)) - 1) + 64 > kStackCap;
     auto greedy_dive = [&]() {
         int k0 = 0; double s0 = 0.0, cost0 = 0.0; unsigned long long r0 = 0, r1 = 0;
@@ -767,59 +1198,95 @@ __global__ void __launch_bounds__(kSearchWarps * 32) stage_dp_search_kernel(cons
             double s = s0, cost = cost0, bd; unsigned long long q0 = r0, q1 = r1; bool leaf;
             const bool ok = expand(k0, s, cost, q0, q1, INFINITY, bd, leaf);
             ++nodes;
-            const int win = argmin_lane(ok, bd);
-            if (win < 0) break;                                   // dead end (hard rows): phase B searches properly
+            const int win = warp_argmin(ok, bd);
+            if (win < 0) break;                                   // dead end (hard rows): the search proper takes over
             s0 = __shfl_sync(0xffffffffu, s, win); cost0 = __shfl_sync(0xffffffffu, cost, win);
             r0 = __shfl_sync(0xffffffffu, q0, win); r1 = __shfl_sync(0xffffffffu, q1, win);
             k0 += (Nt - k0) < D ? (Nt - k0) : D;
             if (k0 >= Nt && cost0 < best) { best = cost0; bp0 = r0; bp1 = r1; ++improvements; }
         }
     };
-    if (two_phase) greedy_dive();
-    // ---- phase B: exact search
-    int sp = 1;
-    if (lane == 0) { Node r; r.s = 0.0; r.cost = 0.0; r.bound = -INFINITY; r.p0 = r.p1 = 0; r.k = 0; r.pad = 0; stack[0] = r; }
-    __syncwarp();
-    while (sp > 0) {
-        if (nodes >= A.o.max_nodes) { limit = true; break; }
-        const double tol = isfinite(best) ? fmax(1e-11 * fmax(1.0, fabs(best)), A.o.mip_rel_gap * fabs(best)) : 0.0;
-        const double cut = best - tol;
-        // discard the run of dominated nodes on top of the stack, pop the first live one
-        const bool live = lane < sp && stack[sp - 1 - lane].bound < cut;
-        const unsigned lm = __ballot_sync(0xffffffffu, live);
-        if (lm == 0) { sp -= sp < 32 ? sp : 32; continue; }
-        const int first = __ffs(lm) - 1;
-        const Node nd = stack[sp - 1 - first];
-        sp -= first + 1;
+    if (two_phase && !isfinite(best)) greedy_dive();
+    // ---- exact search, pass by pass
+    double T = INFINITY, root_lb = INFINITY, delta = 0.0, open_lb = INFINITY;
+    for (int pass = 0; pass < 200 && !limit && !defer; ++pass) {
+        bool cut_by_T = false;
+        int sp = 1;
+        if (lane == 0) { Node r; r.s = 0.0; r.cost = 0.0; r.bound = -INFINITY; r.p0 = r.p1 = 0; r.k = 0; r.pad = 0; stack[0] = r; }
         __syncwarp();
-        double s = nd.s, cost = nd.cost, bd; unsigned long long q0 = nd.p0, q1 = nd.p1; bool leaf;
-        const bool ok = expand(nd.k, s, cost, q0, q1, cut, bd, leaf);
-        ++nodes;
-        if (leaf) {
-            const int win = argmin_lane(ok, cost);
-            if (win >= 0) {
-                best = __shfl_sync(0xffffffffu, cost, win);
-                bp0 = __shfl_sync(0xffffffffu, q0, win); bp1 = __shfl_sync(0xffffffffu, q1, win);
-                ++improvements;
+        while (sp > 0) {
+            if (nodes >= A.o.max_nodes) { limit = true; break; }
+            if (nodes - nodes_in >= budget) { defer = true; break; }
+            const double tol = isfinite(best) ? fmax(1e-11 * fmax(1.0, fabs(best)), A.o.mip_rel_gap * fabs(best)) : 0.0;
+            const double bcut = best - tol;
+            const double cut = fmin(bcut, T);
+            // discard the run of dominated nodes on top of the stack, pop the first live one
+            const bool live = lane < sp && stack[sp - 1 - lane].bound < cut;
+            const unsigned lm = __ballot_sync(0xffffffffu, live);
+            if (lm == 0) { sp -= sp < 32 ? sp : 32; continue; }
+            const int first = __ffs(lm) - 1;
+            const Node nd = stack[sp - 1 - first];
+            sp -= first + 1;
+            __syncwarp();
+            double s = nd.s, cost = nd.cost, bd; unsigned long long q0 = nd.p0, q1 = nd.p1; bool leaf;
+            bool ok = expand(nd.k, s, cost, q0, q1, cut, bd, leaf);
+            ++nodes;
+            if (nd.k == 0 && pass == 0) {
+                // the root's children fix the first threshold: a hair above the best of their bounds
+                root_lb = warp_min(bd);
+                delta = fmax(1e-3 * fmax(1.0, fabs(root_lb)), 1e-9);
+                T = root_lb + delta;
+                ok = ok && bd < T;
             }
-            continue;
+            if (__any_sync(0xffffffffu, !ok && bd < bcut)) cut_by_T = true;
+            if (leaf) {
+                const int win = warp_argmin(ok, cost);
+                if (win >= 0) {
+                    best = __shfl_sync(0xffffffffu, cost, win);
+                    bp0 = __shfl_sync(0xffffffffu, q0, win); bp1 = __shfl_sync(0xffffffffu, q1, win);
+                    ++improvements;
+                }
+                continue;
+            }
+            const unsigned pm = __ballot_sync(0xffffffffu, ok);
+            const int npush = __popc(pm);
+            if (npush == 0) continue;
+            if (sp + npush > kStackCap) { limit = true; open_lb = fmin(open_lb, warp_min(ok ? bd : INFINITY)); break; }
+            // best survivor on top, the others below it in lane order
+            const int win = npush > 1 ? warp_argmin(ok, bd) : __ffs(pm) - 1;
+            if (ok) {
+                int pos = __popc(pm & ((1u << lane) - 1u));           // rank among the survivors
+                if (lane == win) pos = npush - 1;
+                else if (lane > win) pos -= 1;
+                Node ch; ch.s = s; ch.cost = cost; ch.bound = bd; ch.k = nd.k + D; ch.pad = 0; ch.p0 = q0; ch.p1 = q1;
+                stack[sp + pos] = ch;
+            }
+            sp += npush;
+            max_sp = sp > max_sp ? sp : max_sp;
+            __syncwarp();
         }
-        const unsigned pm = __ballot_sync(0xffffffffu, ok);
-        const int npush = __popc(pm);
-        if (npush == 0) continue;
-        if (sp + npush > kStackCap) { limit = true; break; }
-        // best survivor on top, the others below it in lane order
-        const int win = npush > 1 ? argmin_lane(ok, bd) : __ffs(pm) - 1;
-        if (ok) {
-            int pos = __popc(pm & ((1u << lane) - 1u));           // rank among the survivors
-            if (lane == win) pos = npush - 1;
-            else if (lane > win) pos -= 1;
-            Node ch; ch.s = s; ch.cost = cost; ch.bound = bd; ch.k = nd.k + D; ch.pad = 0; ch.p0 = q0; ch.p1 = q1;
-            stack[sp + pos] = ch;
+        if (limit || defer) {
+            // what is still open bounds the optimum from below (certified gap of an unfinished search)
+            double m = INFINITY;
+            for (int i = lane; i < sp; i += 32) m = fmin(m, stack[i].bound);
+            open_lb = fmin(open_lb, warp_min(m));
+            if (cut_by_T) open_lb = fmin(open_lb, T);
+            break;
         }
-        sp += npush;
-        max_sp = sp > max_sp ? sp : max_sp;
+        if (!cut_by_T || (isfinite(best) && best <= T)) break;       // nothing was held back by the threshold: done
+        delta *= 4.0;
+        T = root_lb + delta;
+        if (!isfinite(T)) T = INFINITY;
+    }
+    if (defer) {
+        if (lane == 0) {
+            double* misc = c.misc;
+            misc[MISC_INC_OBJ] = best;
+            misc[MISC_INC_P0] = __longlong_as_double((long long)bp0); misc[MISC_INC_P1] = __longlong_as_double((long long)bp1);
+            misc[MISC_NODES0] = (double)nodes; misc[MISC_IMPR0] = (double)improvements;
+        }
         __syncwarp();
+        return false;
     }
     if (limit && !isfinite(best)) greedy_dive();     // budget gone before the first descent finished: best effort
     // ---- write the solution: binaries from the path, mu in closed form along the exact trajectory
@@ -846,19 +1313,57 @@ __global__ void __launch_bounds__(kSearchWarps * 32) stage_dp_search_kernel(cons
     if (lane == 0) {
         A.obj[b] = have ? best : INFINITY;
         A.status[b] = limit ? HMPC_SOLVE_NODE_LIMIT : (have ? HMPC_SOLVE_OPTIMAL : HMPC_SOLVE_INFEASIBLE);
-        st_out[0] = nodes; st_out[1] = 0; st_out[2] = 0; st_out[3] = c.G; st_out[4] = max_sp; st_out[5] = improvements;
-        st_out[6] = 0;
-        st_out[7] = (int32_t)fmin(((double)(Nt - 1) * c.G * nact * (4.0 + 3.0 * nc) + (double)nodes * 32.0 * D * (4.0 + 3.0 * nc)) / 1024.0, 2.0e9);
+        // certified relative gap of an unfinished search, in units of 1e-9 (0 when proven)
+        int gap9 = 0;
+        if (limit) {
+            const double lbv = fmin(open_lb, best);
+            const double g = have ? (best - lbv) / fmax(fabs(best), 1e-300) : INFINITY;
+            gap9 = (int)fmin(fmax(g, 0.0) * 1e9, 2.0e9);
+        }
+        // executed FP64-pipe instructions (sweep + search), in thousands (stats[7])
+        const double kins = c.misc[MISC_KINS] + (double)nodes * 32.0 * D * (2.0 + 3.0 * nc);
+        // device time of this agent's phases in units of 0.1 us: [1] load + set-up, [2] sweep, [4] this search
+        st_out[0] = nodes; st_out[1] = (int32_t)fmin(c.misc[MISC_T_SETUP] * 0.01, 2.0e9);
+        st_out[2] = (int32_t)fmin(c.misc[MISC_T_SWEEP] * 0.01, 2.0e9); st_out[3] = c.G;
+        st_out[4] = (int32_t)fmin((double)(global_ns() - t_search) * 0.01, 2.0e9); st_out[5] = improvements;
+        st_out[6] = gap9;
+        st_out[7] = (int32_t)fmin(kins / 1000.0, 2.0e9);
     }
+    __syncwarp();
+    return true;
 }
 
-static size_t table_bytes(int B, int Nt, int G, bool fp64) { return (size_t)B * Nt * G * (fp64 ? sizeof(double) : sizeof(float)); }
+// kernel 2: the agents kernel 1 left pending (all of them when the tail search is off), four warps per CTA
+__global__ void __launch_bounds__(kSearchWarps * 32) stage_dp_search_kernel(const DpArgs A) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * kSearchWarps + warp;
+    if (b >= A.d.B) return;
+    if (A.status[b] != kPending) return;
+    const DpPlan plan = make_dp_plan(A.d.Nt, A.nb, A.d.nc, A.T);
+    const size_t per_warp = (size_t)plan.nd * 8 + sizeof(Node) * kStackCap + 8 * (kDpMaxNt + 1);
+    unsigned char* base = smem + per_warp * warp;
+    DpCtx c = bind_ctx(A, base);
+    Node* stack = reinterpret_cast<Node*>(base + (size_t)plan.nd * 8);
+    double* ptraj = reinterpret_cast<double*>(stack + kStackCap);
+    {
+        const double* src = A.pblk + (int64_t)b * plan.nd;
+        double* dst = reinterpret_cast<double*>(base);
+        for (int i = lane; i < plan.nd; i += 32) dst[i] = src[i];
+    }
+    __syncwarp();
+    dp_search(A, c, b, stack, ptraj, lane, INT_MAX);
+}
+
+static size_t table_bytes(int B, int nstore, int G, int fmt) { return (size_t)B * nstore * G * fmt_bytes(fmt); }
+static int search_depth(int nb) { return nb == 1 ? 5 : (nb == 2 ? 2 : 1); }      // nact^D <= 32
 
 }  // namespace hmpc
 
 extern "C" void hmpc_stage_dp_default_opts(hmpc_stage_dp_opts* o) {
     if (!o) return;
-    o->mip_rel_gap = 0.0; o->feas_tol = 1e-9; o->cells = 8192; o->max_nodes = 4000000; o->table_fp64 = 1; o->reserved = 0;
+    o->mip_rel_gap = 0.0; o->feas_tol = 1e-9; o->cells = 8192; o->max_nodes = 4000000; o->table_fp64 = 1;
+    o->bound = HMPC_DP_BOUND_CONSTANT; o->fuse_search = -1; o->reserved = 0;
 }
 
 extern "C" int hmpc_stage_dp_supported(const hmpc_dims* d) {
@@ -871,14 +1376,23 @@ extern "C" int hmpc_stage_dp_supported(const hmpc_dims* d) {
     return 1;
 }
 
+static int dp_format(const hmpc_stage_dp_opts& o) {
+    using namespace hmpc;
+    return o.bound == HMPC_DP_BOUND_LINEAR ? FMT_LIN : (o.table_fp64 ? FMT_F64 : FMT_F32);
+}
+
 extern "C" int hmpc_stage_dp_workspace_bytes(const hmpc_dims* d, const hmpc_stage_dp_opts* opts, size_t* bytes) {
     using namespace hmpc;
     if (!d || !bytes || d->B < 0) return HMPC_ERR_ARG;
     hmpc_stage_dp_opts o;
     if (opts) o = *opts; else hmpc_stage_dp_default_opts(&o);
     if (o.cells < 64) return HMPC_ERR_ARG;
-    const DpPlan plan = make_dp_plan(d->Nt, d->nu + d->ndelta, d->nc);
-    *bytes = ((table_bytes(d->B, d->Nt, o.cells, o.table_fp64 != 0) + 255) & ~(size_t)255) + (size_t)d->B * plan.nd * sizeof(double) + 256;
+    const int nb = d->nu + d->ndelta;
+    const DpPlan plan = make_dp_plan(d->Nt, nb, d->nc);
+    const int D = search_depth(nb), nstore = (d->Nt - 1) / D;
+    // sized for the widest format the options can end up with (an FP64 table that does not fit shared memory falls
+    // back to FP32, which is smaller)
+    *bytes = ((table_bytes(d->B, nstore > 0 ? nstore : 1, o.cells, dp_format(o)) + 255) & ~(size_t)255) + (size_t)d->B * plan.nd * sizeof(double) + 256;
     return HMPC_OK;
 }
 
@@ -908,34 +1422,67 @@ extern "C" int hmpc_stage_dp_solve_f64(const hmpc_dims* dims, const double* cons
     }
     a.T = a.t.T;
     a.rhs = rhs; a.cost = cost_v; a.sc = cost_v_stride_b; a.lb = lb_v; a.ub = ub_v; a.is_bin = is_bin_v;
+    a.D = search_depth(a.nb); a.nstore = (dims->Nt - 1) / a.D;
     size_t need = 0;
     hmpc_stage_dp_workspace_bytes(dims, &a.o, &need);
     if (!workspace || workspace_bytes < need) return HMPC_ERR_WORKSPACE;
-    a.table = reinterpret_cast<float*>(workspace);
-    a.pblk = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(workspace) + ((table_bytes(dims->B, dims->Nt, a.G, a.o.table_fp64 != 0) + 255) & ~(size_t)255));
-    a.v = v; a.obj = obj; a.status = status; a.stats = stats;
     const DpPlan plan = make_dp_plan(dims->Nt, a.nb, dims->nc, a.T);
     int dev = 0, smem_optin = 0;
     HMPC_CUDA_TRY(cudaGetDevice(&dev));
     HMPC_CUDA_TRY(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    auto smem_table = [&](bool f64) { return (size_t)plan.total * 8 + 2 * (size_t)(a.G + 2 * G_PAD(a.G)) * (f64 ? sizeof(double) : sizeof(float)); };
-    // an FP64 table that does not fit the two stage buffers into shared memory (cells > ~9000) falls back to FP32
-    if (a.o.table_fp64 && smem_table(true) > (size_t)smem_optin) a.o.table_fp64 = 0;
-    const bool fp64 = a.o.table_fp64 != 0;
-    const size_t smem1 = smem_table(fp64);
-    const size_t smem2 = ((size_t)plan.nd * 8 + sizeof(Node) * kStackCap + 8 * (kDpMaxNt + 1)) * kSearchWarps;
-    if (smem1 > (size_t)smem_optin || smem2 > (size_t)smem_optin) return HMPC_ERR_ARG;
+    const size_t tail_bytes = sizeof(Node) * kStackCap + 8 * (kDpMaxNt + 1);
+    auto smem_table = [&](int fmt) {
+        size_t bufs = 2 * (size_t)a.G * fmt_bytes(fmt);
+        if (bufs < tail_bytes) bufs = tail_bytes;
+        return (size_t)plan.total * 8 + bufs + 1024;    // + the kernel's static shared memory
+    };
+    // a format that does not fit the two stage buffers into shared memory falls back to the next smaller one
+    a.fmt = dp_format(a.o);
+    if (a.fmt == FMT_LIN && smem_table(FMT_LIN) > (size_t)smem_optin) return HMPC_ERR_ARG;     // (the caller picks the cell count)
+    if (a.fmt == FMT_F64 && smem_table(FMT_F64) > (size_t)smem_optin) a.fmt = FMT_F32;
+    a.table = workspace;
+    a.pblk = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(workspace) + ((table_bytes(dims->B, a.nstore > 0 ? a.nstore : 1, a.G, dp_format(a.o)) + 255) & ~(size_t)255));
+    a.v = v; a.obj = obj; a.status = status; a.stats = stats;
+    // the tail search keeps an agent's CTA (and its shared memory) for the length of one warp's search: worth it while
+    // the batch is at most two CTAs per SM, else kernel 2 searches many agents per SM concurrently
+    a.fuse = a.o.fuse_search < 0 ? (dims->B <= 2 * kNumSM ? 1 : 0) : (a.o.fuse_search != 0);
+    const size_t smem1 = smem_table(a.fmt) - 1024;
+    const size_t smem2 = ((size_t)plan.nd * 8 + tail_bytes) * kSearchWarps;
+    if (smem1 + 1024 > (size_t)smem_optin || smem2 > (size_t)smem_optin) return HMPC_ERR_ARG;
     const bool dewh_shape = dims->nc == 2 && a.nact == 2;
-    auto table_kernel = fp64 ? (dewh_shape ? stage_dp_table_kernel<2, 2, double> : stage_dp_table_kernel<0, 0, double>)
-                             : (dewh_shape ? stage_dp_table_kernel<2, 2, float> : stage_dp_table_kernel<0, 0, float>);
+    void (*table_kernel)(const DpArgs) = nullptr;
+    if (a.fmt == FMT_LIN) table_kernel = dewh_shape ? stage_dp_table_kernel<2, 2, FMT_LIN> : stage_dp_table_kernel<0, 0, FMT_LIN>;
+    else if (a.fmt == FMT_F64) table_kernel = dewh_shape ? stage_dp_table_kernel<2, 2, FMT_F64> : stage_dp_table_kernel<0, 0, FMT_F64>;
+    else table_kernel = dewh_shape ? stage_dp_table_kernel<2, 2, FMT_F32> : stage_dp_table_kernel<0, 0, FMT_F32>;
     HMPC_CUDA_TRY(cudaFuncSetAttribute(table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
     HMPC_CUDA_TRY(cudaFuncSetAttribute(stage_dp_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
     cudaStream_t s = (cudaStream_t)stream;
     // one fat CTA per SM: measured, two 256-thread CTAs per SM sweep 40 % fewer agents per second than one 512-thread CTA
-    const int table_threads = 512;
-    table_kernel<<<dims->B, table_threads, smem1, s>>>(a);
+    table_kernel<<<dims->B, kTableThreads, smem1, s>>>(a);
     HMPC_LAUNCH_CHECK("stage_dp_table_kernel");
     stage_dp_search_kernel<<<ceil_div(dims->B, kSearchWarps), kSearchWarps * 32, smem2, s>>>(a);
     HMPC_LAUNCH_CHECK("stage_dp_search_kernel");
     return HMPC_OK;
+}
+
+extern "C" int hmpc_stage_dp_max_cells(const hmpc_dims* dims, const hmpc_stage_dp_opts* opts, int32_t* cells) {
+    using namespace hmpc;
+    if (!dims || !cells || !hmpc_stage_dp_supported(dims)) return HMPC_ERR_ARG;
+    hmpc_stage_dp_opts o;
+    if (opts) o = *opts; else hmpc_stage_dp_default_opts(&o);
+    int dev = 0, smem_optin = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) {
+        (void)cudaGetLastError();
+        smem_optin = 232448;                      // sm_100: 227 KB per CTA (no device here: a host-side sizing query)
+    }
+    const DpPlan plan = make_dp_plan(dims->Nt, dims->nu + dims->ndelta, dims->nc);
+    const int fmt = dp_format(o);
+    int best = 0;
+    for (int G = 256; G <= 32768; G += 256) {
+        const size_t need = (size_t)plan.total * 8 + 2 * (size_t)G * fmt_bytes(fmt) + 1024;
+        if (need <= (size_t)smem_optin) best = G;
+    }
+    *cells = best;
+    return best > 0 ? HMPC_OK : HMPC_ERR_ARG;
 }
