@@ -16,6 +16,10 @@ _GROUPS = (("state_input", ("Phi_x", "Gamma_v", "Gamma_omega", "Gamma_5"), "nx")
            ("constraint", ("H_x", "H_v", "H_omega", "H_5"), "n_constraints"))
 
 
+def controller_model(controller):
+    return controller.mld_numeric_k if controller is not None else None
+
+
 class MldEvoMatrices(StructDict):
     matrix_types = StructDict(state_input="state_input", output="output", constraint="constraint")
 
@@ -31,6 +35,10 @@ class MldEvoMatrices(StructDict):
             mld_numeric_k = controller.mld_numeric_k if mld_numeric_k is None else mld_numeric_k
         self._N_p = int(N_p)
         self._N_tilde = int(N_tilde) if N_tilde is not None else self._N_p + 1
+        # a controller's model object can be REPLACED (MldSystemModel.update_param_struct / update_mld build a new
+        # numeric model), so the component keeps the controller and re-reads its model on every update, like the
+        # reference's process_base_args / has_updated_version (mld_evolution_matrices.py:73-87)
+        self._controller = controller if mld_numeric_k is controller_model(controller) else None
         self._mld = mld_numeric_k
         self._device = device
         self._version = None
@@ -52,11 +60,20 @@ class MldEvoMatrices(StructDict):
     def batch(self):
         return self._batch
 
+    def _current_mld(self):
+        if self._controller is not None:
+            mld = self._controller.mld_numeric_k
+            if mld is not None:
+                return mld
+        return self._mld
+
     def update(self, reset=False):
-        """Recondense only when the model changed (reference :73-87)."""
-        if not reset and self._version == self._mld.version:
+        """Recondense only when the model changed -- a new version of the same object or a new object (reference :73-87)."""
+        mld = self._current_mld()
+        key = (id(mld), mld.version)
+        if not reset and self._version == key:
             return
-        mld = self._mld
+        self._mld = mld
         info = mld.mld_info
         mats = {k: mld[k] for k in cabi.MAT_NAMES if mld[k].size}
         self._batch = BatchMpc(mats, self._N_p, self._N_tilde, nu_l=info.nu_l, nmu_l=info.nmu_l, B=1,
@@ -73,7 +90,7 @@ class MldEvoMatrices(StructDict):
                 g[nm + "_N_tilde"] = full
                 g[nm + "_N_p"] = full[:self._N_p * rows_per_step, :]
             self[grp] = g
-        self._version = mld.version
+        self._version = key
 
     def get_evo_matrices_N_tilde(self, N_tilde=None):
         if N_tilde is None or N_tilde == self._N_tilde:

@@ -42,7 +42,9 @@
 
 namespace hmpc {
 
-constexpr int kTableThreads = 512;
+constexpr int kTableThreads = 512;     // sweep threads of the table kernel (a thread owns the cells n * 512 + tid)
+constexpr int kTableShift = 9;        // log2(kTableThreads)
+constexpr int kTableBlock = kTableThreads + 32;   // + one helper warp (semi-infinite cells, off the sweep's critical path)
 constexpr int kDpMaxNb = 4;
 constexpr int kDpMaxAct = 1 << kDpMaxNb;
 constexpr int kDpMaxNc = 8;
@@ -82,7 +84,7 @@ struct DpPlan {
     int ak, iak, cu, qs, rhs, tailmin, amask, e, dscale, galpha, falpha, misc, off, loinf, hiinf, nd;   // persistent
     int x_eak, x_foff, x_hq, x_ca, x_shift;
     int t_h, t_ga, t_r, t_wq, t_w1, qq;
-    int scr;                                                                      // load-time scratch [6*Nt]
+    int scr;                                                                      // load-time scratch [9*Nt]
     int mst;                                                                      // staged MLD blocks [11][64]
     int sc_ca, sc_base, sc_slope, sc_fr, sc_i0, sc_span, sc_flags, sc_z, sc_semi, sc_semd;   // per-stage sweep constants
     int total;
@@ -109,7 +111,7 @@ __host__ __device__ inline DpPlan make_dp_plan(int Nt, int nb, int nc, int T = k
     p.qq = take(Nt * nc);
     p.nd = (o + 1) & ~1;
     o = p.nd;
-    p.scr = take(6 * Nt);
+    p.scr = take(9 * Nt);
     p.mst = take(kMstMats * kMstElems);
     const int nc_ = nc > 0 ? nc : 1;
     p.sc_ca = take(Nt * nact); p.sc_base = take(Nt * nc_ * nact); p.sc_slope = take(Nt * nc_); p.sc_fr = take(Nt * nact);
@@ -321,78 +323,65 @@ __device__ inline void dp_load(const DpArgs& A, int b, DpCtx& c) {
     }
     if (bad) c.misc[MISC_FLAG] = 1.0;   // benign race: every writer stores the same value
     __syncthreads();
-    // ---- grid window and trivial bound: prefix sums / minima over the stages, done by warp 0 (lane l owns the stages
-    // [l*per, (l+1)*per); scans across lanes by shuffles).
+    // ---- grid window and trivial bound, one stage per thread (each thread sums / scans its own prefix: O(Nt) steps of
+    // independent loads, three short phases):
     //   tailmin_k  = sum_{i>=k} min(cmin_i, 0): trivial bound on the cost-to-go from ANY state
     //   moving window: stage k covers [band_k - 2 shifts, band_k + 1 shift], the band clamped to what is reachable at
     //   that stage and slew-limited -- the state climbs by at most the largest shift per stage and falls by at most
     //   the most negative one, so after a jump of the band the window follows the states that are catching up, not the
     //   band itself:  env_lo_k = min(lo_k, env_lo_k-1 + smax_k-1) = P_k + min_{j<=k} (lo_j - P_j),  P = prefix sum of
     //   smax (likewise env_hi with the most negative shifts).  Every stage has the same width (the widest of them, at
-    //   least 5.4 shifts so that a translation plus the drift of the window between two stages stays within the guard
-    //   cells of the stage buffers).
+    //   least 5.4 shifts).
+    double* x_lo = c.scr + 6 * Nt; double* x_hi = c.scr + 7 * Nt; double* x_w = c.scr + 8 * Nt;
+    double margin = 0.0, rlo = 0.0, rhi = 0.0, pp = 0.0, pm = 0.0;
+    if (tid < Nt) {
+        const int k = tid;
+        for (int i = 0; i < Nt; ++i) margin = fmax(margin, s_marg[i]);
+        for (int i = 0; i < k; ++i) {
+            const double a = s_smin[i], bq = s_smax[i];
+            rlo += a; rhi += bq; pp += bq > 0.0 ? bq : 0.0; pm += a < 0.0 ? a : 0.0;
+        }
+        double tail = 0.0;
+        for (int i = Nt - 1; i >= k; --i) { const double cm = s_cmin[i]; tail += cm < 0.0 ? cm : 0.0; }
+        c.tailmin[k] = tail;
+        if (k == 0) c.tailmin[Nt] = 0.0;
+        const double lo_c = fmin(fmax(s_lo[k], rlo), rhi), hi_c = fmax(fmin(s_hi[k], rhi), rlo);
+        x_lo[k] = lo_c - pp; x_hi[k] = hi_c - pm;
+    }
+    __syncthreads();
+    if (tid < Nt) {
+        const int k = tid;
+        double mn = INFINITY, mx = -INFINITY;
+        for (int j = 0; j <= k; ++j) { const double a = x_lo[j], bq = x_hi[j]; mn = a < mn ? a : mn; mx = bq > mx ? bq : mx; }
+        const double env_lo = pp + mn, env_hi = pm + mx;
+        const double a0 = fmax(fmin(env_lo, env_hi) - 2.0 * margin, rlo - 0.01 * margin);
+        double b0 = fmin(fmax(env_lo, env_hi) + margin, rhi + 0.01 * margin);
+        if (!(b0 > a0)) b0 = a0;
+        s_lo[k] = a0; x_w[k] = b0 - a0;
+    }
+    __syncthreads();
     if (tid < 32) {
-        const int per = (Nt + 31) / 32, k0 = tid * per, k1 = min(k0 + per, Nt);
-        auto scan_add = [&](double v) {      // exclusive prefix sum across lanes; returns (exclusive, total)
-            double inc = v;
+        double Wmax = 0.0, mg = 0.0;
+        for (int k = tid; k < Nt; k += 32) { Wmax = fmax(Wmax, x_w[k]); mg = fmax(mg, s_marg[k]); }
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const double t = __shfl_up_sync(0xffffffffu, inc, o); if (tid >= o) inc += t; }
-            return make_double2(inc - v, __shfl_sync(0xffffffffu, inc, 31));
-        };
-        double a_neg = 0.0, a_min = 0.0, a_max = 0.0, a_pp = 0.0, a_pm = 0.0, margin = 0.0;
-        for (int k = k0; k < k1; ++k) {
-            a_neg += fmin(s_cmin[k], 0.0); a_min += s_smin[k]; a_max += s_smax[k];
-            a_pp += fmax(s_smax[k], 0.0); a_pm += fmin(s_smin[k], 0.0); margin = fmax(margin, s_marg[k]);
+        for (int o = 16; o > 0; o >>= 1) {
+            Wmax = fmax(Wmax, __shfl_xor_sync(0xffffffffu, Wmax, o)); mg = fmax(mg, __shfl_xor_sync(0xffffffffu, mg, o));
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) margin = fmax(margin, __shfl_xor_sync(0xffffffffu, margin, o));
-        const double2 x_neg = scan_add(a_neg), x_min = scan_add(a_min), x_max = scan_add(a_max), x_pp = scan_add(a_pp), x_pm = scan_add(a_pm);
-        // pass 1: clamped band edges relative to the slew prefix; lane-local running minima / maxima
-        double rlo = x_min.x, rhi = x_max.x, pp = x_pp.x, pm = x_pm.x, tail = x_neg.y - x_neg.x;
-        double lmin = INFINITY, lmax = -INFINITY;
-        for (int k = k0; k < k1; ++k) {
-            c.tailmin[k] = tail; tail -= fmin(s_cmin[k], 0.0);
-            const double lo_c = fmin(fmax(s_lo[k], rlo), rhi), hi_c = fmax(fmin(s_hi[k], rhi), rlo);
-            lmin = fmin(lmin, lo_c - pp); lmax = fmax(lmax, hi_c - pm);
-            s_lo[k] = lmin; s_hi[k] = lmax;                      // running extrema within the lane's block
-            s_cmin[k] = rlo; s_marg[k] = rhi;                    // (scratch reuse: reachable range of the stage)
-            rlo += s_smin[k]; rhi += s_smax[k]; pp += fmax(s_smax[k], 0.0); pm += fmin(s_smin[k], 0.0);
-        }
-        if (tid == 0) c.tailmin[Nt] = 0.0;
-        // exclusive prefix min / max of the lanes' block extrema
-        double imin = lmin, imax = lmax;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const double t1 = __shfl_up_sync(0xffffffffu, imin, o), t2 = __shfl_up_sync(0xffffffffu, imax, o);
-            if (tid >= o) { imin = fmin(imin, t1); imax = fmax(imax, t2); }
-        }
-        double emin = __shfl_up_sync(0xffffffffu, imin, 1), emax = __shfl_up_sync(0xffffffffu, imax, 1);
-        if (tid == 0) { emin = INFINITY; emax = -INFINITY; }
-        // pass 2: envelopes -> window start of every stage, widest window
-        pp = x_pp.x; pm = x_pm.x;
-        double Wmax = 0.0;
-        for (int k = k0; k < k1; ++k) {
-            const double env_lo = pp + fmin(emin, s_lo[k]), env_hi = pm + fmax(emax, s_hi[k]);
-            const double rlo_k = s_cmin[k], rhi_k = s_marg[k];
-            const double a0 = fmax(fmin(env_lo, env_hi) - 2.0 * margin, rlo_k - 0.01 * margin);
-            double b0 = fmin(fmax(env_lo, env_hi) + margin, rhi_k + 0.01 * margin);
-            if (!(b0 > a0)) b0 = a0;
-            s_lo[k] = a0; Wmax = fmax(Wmax, b0 - a0);
-            pp += fmax(s_smax[k], 0.0); pm += fmin(s_smin[k], 0.0);
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) Wmax = fmax(Wmax, __shfl_xor_sync(0xffffffffu, Wmax, o));
-        double W = fmax(Wmax, 5.4 * margin * (1.0 + 16.0 / (double)c.G));
-        if (!(W > 0.0) || !isfinite(W)) W = 1.0;
-        const double w = W / (double)c.G, invw = 1.0 / w;
-        for (int k = k0; k < k1; ++k) c.off[k] = (int)fmax(fmin(floor(s_lo[k] * invw), 1.0e9), -1.0e9);
-        __syncwarp();
         if (tid == 0) {
-            c.off[Nt] = c.off[Nt - 1]; c.off[Nt + 1] = c.off[Nt - 1];
-            c.misc[MISC_W] = w; c.misc[MISC_INVW] = invw; c.misc[MISC_SIMPLE] = 1.0;
+            double W = fmax(Wmax, 5.4 * mg * (1.0 + 16.0 / (double)c.G));
+            if (!(W > 0.0) || !isfinite(W)) W = 1.0;
+            const double w = W / (double)c.G;
+            c.misc[MISC_W] = w; c.misc[MISC_INVW] = 1.0 / w; c.misc[MISC_SIMPLE] = 1.0;
             c.loinf[Nt] = 0.0; c.hiinf[Nt] = 0.0;
         }
     }
+    __syncthreads();
+    if (tid < Nt) {
+        const double invw = c.misc[MISC_INVW];
+        c.off[tid] = (int)fmax(fmin(floor(s_lo[tid] * invw), 1.0e9), -1.0e9);
+    }
+    __syncthreads();
+    if (tid == 0) { c.off[Nt] = c.off[Nt - 1]; c.off[Nt + 1] = c.off[Nt - 1]; }
     __syncthreads();
 }
 
@@ -662,21 +651,22 @@ __device__ __forceinline__ unsigned long long warp_min_key(double v) { return wa
 //                  guard cells), bit1 samepen (row violations do not depend on the action: F = 0, G D = 0)
 //   z[k]           cells [z0, z1) of a samepen stage violate no row
 template <int NC, int NACT, int FMT>
-__global__ void __launch_bounds__(kTableThreads) stage_dp_table_kernel(const DpArgs A);
+__global__ void __launch_bounds__(kTableBlock) stage_dp_table_kernel(const DpArgs A);
 
 struct Node { double s, cost, bound; unsigned long long p0, p1; int k, pad; };
 
 __device__ bool dp_search(const DpArgs& A, const DpCtx& c, int b, Node* stack, double* ptraj, int lane, int budget);
 
 template <int NC, int NACT, int FMT>
-__global__ void __launch_bounds__(kTableThreads) stage_dp_table_kernel(const DpArgs A) {
+__global__ void __launch_bounds__(kTableBlock) stage_dp_table_kernel(const DpArgs A) {
     typedef typename Cell<FMT>::T TT;
     extern __shared__ __align__(16) unsigned char smem[];
-    __shared__ unsigned long long s_part[2][kTableThreads / 32][4];
+    __shared__ double s_kins[kTableBlock / 32];
     __shared__ int s_tail;
     const int b = blockIdx.x;
-    const int nthr = kTableThreads;
+    const int nthr = kTableBlock;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool helper = warp == kTableThreads / 32;
     DpCtx c = bind_ctx(A, smem);
     const DpPlan plan = make_dp_plan(c.Nt, c.nb, c.nc, c.T);
     TT* buf0 = reinterpret_cast<TT*>(smem + (size_t)plan.total * 8);
@@ -810,11 +800,11 @@ __global__ void __launch_bounds__(kTableThreads) stage_dp_table_kernel(const DpA
             else if ((fl & 1) && (fl & 2) && nact == 2) kins += 4.0 * zc + (5.0 + 3.0 * nc) * (G - zc);
             else kins += (double)G * nact * (3.0 + 3.0 * nc);
         }
-        if (warp < (Nt + 31) / 32) { kins = warp_sum(kins); if (lane == 0) s_part[0][warp][0] = (unsigned long long)__double_as_longlong(kins); }
+        if (warp < (Nt + 31) / 32) { kins = warp_sum(kins); if (lane == 0) s_kins[warp] = kins; }
         __syncthreads();
         if (tid == 0) {
             double tot = 0.0;
-            for (int wv = 0; wv < (Nt + 31) / 32; ++wv) tot += __longlong_as_double((long long)s_part[0][wv][0]);
+            for (int wv = 0; wv < (Nt + 31) / 32; ++wv) tot += s_kins[wv];
             c.misc[MISC_KINS] = tot;
             c.misc[MISC_LINOK] = lin_ok ? 1.0 : 0.0;
         }
@@ -832,64 +822,48 @@ __global__ void __launch_bounds__(kTableThreads) stage_dp_table_kernel(const DpA
     }
     const unsigned long long t_setup = global_ns();
     // bounds of the two semi-infinite cells: S_k = f(minima of stage k+1 over the cells their images can touch, S_k+1).
-    // Iteration k (a) finishes S_k+1 from the per-warp minima that iteration k+1 left in shared memory, (b) leaves the
-    // minima for S_k (over `cur` = stage k+1), (c) sweeps the cells of stage k -- one barrier per stage.
-    Semi S_next; S_next.lo = 0.0; S_next.hi = 0.0;        // S_k+1 (the terminal stage costs nothing)
-    auto finish_semi = [&](int kk, Semi above) -> Semi {  // S_kk from the minima of parity kk & 1 and S_kk+1 = above
-        const int jl0 = c.sc_semi[8 * kk], jl1 = c.sc_semi[8 * kk + 1], jh0 = c.sc_semi[8 * kk + 2], jh1 = c.sc_semi[8 * kk + 3];
-        const unsigned long long* part = &s_part[kk & 1][0][0];
-        const int pl = lane < kTableThreads / 32 ? lane : 0;
-        double m0 = INFINITY, m1 = INFINITY, m2 = INFINITY, m3 = INFINITY;
-        if (jl0 >= 0) m0 = key_value(warp_min_key_u(part[pl * 4 + 0]));
-        if (jl1 >= 0) m1 = key_value(warp_min_key_u(part[pl * 4 + 1]));
-        if (jh0 < G) m2 = key_value(warp_min_key_u(part[pl * 4 + 2]));
-        if (jh1 < G) m3 = key_value(warp_min_key_u(part[pl * 4 + 3]));
-        // images that reach beyond the next window on either side
-        if (jl0 != INT_MIN) { m0 = dmin(m0, above.lo); if (jl0 >= G) m0 = dmin(m0, above.hi); m2 = dmin(m2, above.hi); if (jh0 < 0) m2 = dmin(m2, above.lo); }
-        if (jl1 != INT_MIN) { m1 = dmin(m1, above.lo); if (jl1 >= G) m1 = dmin(m1, above.hi); m3 = dmin(m3, above.hi); if (jh1 < 0) m3 = dmin(m3, above.lo); }
-        const double c_id = c.sc_semd[4 * kk], c_rest = c.sc_semd[4 * kk + 1];
-        Semi r;
-        r.lo = dmin(c_id + m0, c_rest + m1) + c.sc_semd[4 * kk + 2];
-        r.hi = dmin(c_id + m2, c_rest + m3) + c.sc_semd[4 * kk + 3];
-        if (tid == 0) { c.loinf[kk] = r.lo; c.hiinf[kk] = r.hi; }
-        return r;
-    };
+    // The HELPER warp computes S_k while the 16 sweep warps work on the cells of stage k (which only need S_k+1, in
+    // shared memory since the previous iteration): a chain of dependent shared-memory loads and warp reductions that
+    // would otherwise sit on every warp's critical path, 48 times.  One barrier per stage.
+    Semi S_help; S_help.lo = 0.0; S_help.hi = 0.0;        // helper warp: S_k+1 (the terminal stage costs nothing)
     const int wbase = warp * 32;
     const int nblocks = (G + kTableThreads - 1) / kTableThreads;
     for (int k = Nt - 1; k >= 1; --k) {
-        if (k < Nt - 1) S_next = finish_semi(k + 1, S_next);
         const int flags = c.sc_flags[k];
         const int mask = (int)c.amask[k];
         const int offk = c.off[k], d0 = offk - c.off[k + 1];
         const double* s_ca = c.sc_ca + k * nact; const double* s_base = c.sc_base + k * nc * nact;
         const double* s_slope = c.sc_slope + k * nc; const double* s_q = c.qs + k * nc;
         const int* s_i0 = c.sc_i0 + k * nact; const int* s_span = c.sc_span + k * nact;
-        // ---- (b) minima of stage k+1 over the cells the images of this stage's semi-infinite cells can touch
-        {
+        if (helper) {
             const int jl0 = c.sc_semi[8 * k], jl1 = c.sc_semi[8 * k + 1], jh0 = c.sc_semi[8 * k + 2], jh1 = c.sc_semi[8 * k + 3];
-            unsigned long long* part = &s_part[k & 1][warp][0];
             const int jl = min(max(jl0, jl1), G - 1), jh = min(jh0, jh1);
-            if (jl >= 0) {
-                double m0 = INFINITY, m1 = INFINITY;
-                for (int j = tid; j <= jl; j += nthr) {
-                    const double v = Cell<FMT>::lo(cur[j]);
-                    if (j <= jl0) m0 = dmin(m0, v);
-                    if (j <= jl1) m1 = dmin(m1, v);
-                }
-                if (jl0 >= 0) { const unsigned long long kk = warp_min_key(m0); if (lane == 0) part[0] = kk; }
-                if (jl1 >= 0) { const unsigned long long kk = warp_min_key(m1); if (lane == 0) part[1] = kk; }
+            double m0 = INFINITY, m1 = INFINITY, m2 = INFINITY, m3 = INFINITY;
+            for (int j = lane; j <= jl; j += 32) {
+                const double v = Cell<FMT>::lo(cur[j]);
+                if (j <= jl0) m0 = dmin(m0, v);
+                if (j <= jl1) m1 = dmin(m1, v);
             }
-            if (jh < G) {
-                double m2 = INFINITY, m3 = INFINITY;
-                for (int j = max(jh, 0) + tid; j < G; j += nthr) {
-                    const double v = Cell<FMT>::lo(cur[j]);
-                    if (j >= jh0) m2 = dmin(m2, v);
-                    if (j >= jh1) m3 = dmin(m3, v);
-                }
-                if (jh0 < G) { const unsigned long long kk = warp_min_key(m2); if (lane == 0) part[2] = kk; }
-                if (jh1 < G) { const unsigned long long kk = warp_min_key(m3); if (lane == 0) part[3] = kk; }
+            if (jh < G) for (int j = max(jh, 0) + lane; j < G; j += 32) {
+                const double v = Cell<FMT>::lo(cur[j]);
+                if (j >= jh0) m2 = dmin(m2, v);
+                if (j >= jh1) m3 = dmin(m3, v);
             }
+            m0 = jl0 >= 0 ? key_value(warp_min_key(m0)) : INFINITY;
+            m1 = jl1 >= 0 ? key_value(warp_min_key(m1)) : INFINITY;
+            m2 = jh0 < G ? key_value(warp_min_key(m2)) : INFINITY;
+            m3 = jh1 < G ? key_value(warp_min_key(m3)) : INFINITY;
+            // images that reach beyond the next window on either side
+            const Semi above = S_help;
+            if (jl0 != INT_MIN) { m0 = dmin(m0, above.lo); if (jl0 >= G) m0 = dmin(m0, above.hi); m2 = dmin(m2, above.hi); if (jh0 < 0) m2 = dmin(m2, above.lo); }
+            if (jl1 != INT_MIN) { m1 = dmin(m1, above.lo); if (jl1 >= G) m1 = dmin(m1, above.hi); m3 = dmin(m3, above.hi); if (jh1 < 0) m3 = dmin(m3, above.lo); }
+            const double c_id = c.sc_semd[4 * k], c_rest = c.sc_semd[4 * k + 1];
+            S_help.lo = dmin(c_id + m0, c_rest + m1) + c.sc_semd[4 * k + 2];
+            S_help.hi = dmin(c_id + m2, c_rest + m3) + c.sc_semd[4 * k + 3];
+            if (lane == 0) { c.loinf[k] = S_help.lo; c.hiinf[k] = S_help.hi; }
         }
+        Semi S_next; S_next.lo = c.loinf[k + 1]; S_next.hi = c.hiinf[k + 1];
+        if (!helper) {
         // ---- (c) the cells of the window.  Blocks [na, nb) of this warp are interior: every cell they read is inside
         // the next stage's window.
         const bool fast = (flags & 1) && NC > 0;
@@ -898,8 +872,8 @@ __global__ void __launch_bounds__(kTableThreads) stage_dp_table_kernel(const DpA
             const int rd_lo = c.sc_semi[8 * k + 4], rd_hi = c.sc_semi[8 * k + 5];
             const int lo_need = -(wbase + d0 + rd_lo);                    // n * 512 >= lo_need
             const int hi_room = G - 1 - wbase - 31 - d0 - max(rd_hi, -d0);  // n * 512 <= hi_room (and the cells exist)
-            na = max((lo_need + kTableThreads - 1) >> 9, 0);
-            nb_ = hi_room >= 0 ? (hi_room >> 9) + 1 : 0;
+            na = max((lo_need + kTableThreads - 1) >> kTableShift, 0);
+            nb_ = hi_room >= 0 ? (hi_room >> kTableShift) + 1 : 0;
             if (nb_ < na) nb_ = na;
         }
         Semi out = S_next;
@@ -939,7 +913,7 @@ __global__ void __launch_bounds__(kTableThreads) stage_dp_table_kernel(const DpA
             const int i1 = s_i0[1];
             // penalty-free blocks of this warp: all 32 cells inside [z0, z1)
             const int z0 = c.sc_z[2 * k], z1 = c.sc_z[2 * k + 1];
-            int za = max((z0 - wbase + kTableThreads - 1) >> 9, 0), zb = ((z1 - 32 - wbase) >> 9) + 1;
+            int za = max((z0 - wbase + kTableThreads - 1) >> kTableShift, 0), zb = ((z1 - 32 - wbase) >> kTableShift) + 1;
             za = min(max(za, na), nb_); zb = min(max(zb, za), nb_);
             sweep_same2<NCc, true, true, ST>(curs, nxts, G, 0, na, d0, i1, slope, hq, base, c0, c1, out);
             sweep_same2<NCc, true, false, ST>(curs, nxts, G, na, za, d0, i1, slope, hq, base, c0, c1, out);
@@ -998,6 +972,7 @@ __global__ void __launch_bounds__(kTableThreads) stage_dp_table_kernel(const DpA
                 nxt[cell] = Cell<FMT>::pack(best);
             }
         }
+        }
         // the buffer the NEXT stage overwrites is the source of the bulk copy issued at most D stages ago: it must have
         // been read completely before anybody passes the barrier
         if (tid == 0) bulk_wait_source_free();
@@ -1006,7 +981,6 @@ __global__ void __launch_bounds__(kTableThreads) stage_dp_table_kernel(const DpA
             bulk_store_stage(tab + (int64_t)(k / A.D - 1) * G, nxt, (unsigned)G * sizeof(TT));   // stage k -> L2 / HBM, asynchronously
         TT* t = cur; cur = nxt; nxt = t;
     }
-    if (Nt > 1) S_next = finish_semi(1, S_next);      // (stage 1 is read by the search when D == 1)
     if (tid == 0) {
         bulk_wait_all(); asm volatile("fence.proxy.async;" ::: "memory");
         c.misc[MISC_T_SETUP] = (double)(t_setup - t_start); c.misc[MISC_T_SWEEP] = (double)(global_ns() - t_setup);
@@ -1458,7 +1432,7 @@ extern "C" int hmpc_stage_dp_solve_f64(const hmpc_dims* dims, const double* cons
     HMPC_CUDA_TRY(cudaFuncSetAttribute(stage_dp_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
     cudaStream_t s = (cudaStream_t)stream;
     // one fat CTA per SM: measured, two 256-thread CTAs per SM sweep 40 % fewer agents per second than one 512-thread CTA
-    table_kernel<<<dims->B, kTableThreads, smem1, s>>>(a);
+    table_kernel<<<dims->B, kTableBlock, smem1, s>>>(a);
     HMPC_LAUNCH_CHECK("stage_dp_table_kernel");
     stage_dp_search_kernel<<<ceil_div(dims->B, kSearchWarps), kSearchWarps * 32, smem2, s>>>(a);
     HMPC_LAUNCH_CHECK("stage_dp_search_kernel");

@@ -27,6 +27,23 @@ def allreduce_aggregate(p_local):
     return p_local
 
 
+def allreduce_max_int(value, device=None):
+    """Largest ``value`` over the ranks (every rank gets it): loop bounds that must agree wherever a collective sits
+    inside the loop."""
+    if not is_distributed():
+        return int(value)
+    t = torch.tensor([int(value)], dtype=torch.int64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return int(t.item())
+
+
+def response_blocks(num_local, groups):
+    """Blocks of one best-response pass: ``groups`` (the same on every rank) spans [lo, hi) of the local agents.  A
+    rank with fewer agents than blocks gets EMPTY spans -- it still has to take part in the block's all-reduce, so
+    the spans are yielded, not skipped."""
+    return [shard_range(num_local, g, groups) for g in range(int(groups))]
+
+
 def allgather_trajectories(traj_local, counts=None):
     """[B_local, Nt] per rank -> [B_total, Nt] on every rank, rank-major (the order the reference stacks devices)."""
     if not is_distributed():

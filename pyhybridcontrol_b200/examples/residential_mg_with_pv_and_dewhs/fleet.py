@@ -186,33 +186,35 @@ class DewhFleet(object):
             cabi.coupling_sums(v_cur.view(B, Nt, 3)[:, :, 0], self.P_nom, pen_cur, None, sums_cand)
             distributed.allreduce_aggregate(sums_cand)
             cabi.coupling_accept(sums_cand, p_other, price, a_lo, a_hi, sums_cur, brs)
-            cabi.coupling_restore(lo, hi, brs, v_bak, pen_bak, v_cur, pen_cur)
+            if hi > lo:
+                cabi.coupling_restore(lo, hi, brs, v_bak, pen_bak, v_cur, pen_cur)
 
         # load the starting plan: the whole fleet is one block, accepted against +inf
         cabi.coupling_merge(0, B, Nt, 3, plan["v"], plan["obj"].contiguous(), plan["status"], cost, v_cur, pen_cur, v_bak,
                             pen_bak)
         evaluate(0, B)
-        G = max(1, min(int(groups), B))
+        # every block ends in an all-reduce, so the number of blocks per pass must be the same on every rank: it is
+        # capped by the LARGEST shard (shards differ by one agent), and a rank whose block is empty still evaluates
+        B_max = distributed.allreduce_max_int(B, dev)
+        G = max(1, min(int(groups), B_max))
         solves, last = 0, float(brs[0].cpu())
         for _ in range(int(passes)):
-            for g in range(G):
-                lo, hi = distributed.shard_range(B, g, G)
-                if hi == lo:
-                    continue
-                cabi.coupling_response_cost(sums_cur, v_cur, self.P_nom, p_other, price, cost, 3, 0)
-                sub = cabi.make_dims(hi - lo, d.Nt, nx=d.nx, nu=d.nu, ndelta=d.ndelta, nz=d.nz, nmu=d.nmu,
-                                     nomega=d.nomega, ny=d.ny, nc=d.nc)
-                mats = {k: (m[lo:hi] if m.shape[0] == B and B > 1 else m) for k, m in batch.mats.items()}
-                v_new, obj_new, status_new, _ = cabi.stage_dp_solve(sub, mats, rhs[lo:hi], cost[lo:hi], lb, ub, isb,
-                                                                    batch.dp_opts)
-                solves += 1
-                cabi.coupling_merge(lo, hi, Nt, 3, v_new, obj_new, status_new, cost, v_cur, pen_cur, v_bak, pen_bak)
+            for lo, hi in distributed.response_blocks(B, G):
+                if hi > lo:
+                    cabi.coupling_response_cost(sums_cur, v_cur, self.P_nom, p_other, price, cost, 3, 0)
+                    sub = cabi.make_dims(hi - lo, d.Nt, nx=d.nx, nu=d.nu, ndelta=d.ndelta, nz=d.nz, nmu=d.nmu,
+                                         nomega=d.nomega, ny=d.ny, nc=d.nc)
+                    mats = {k: (m[lo:hi] if m.shape[0] == B and B > 1 else m) for k, m in batch.mats.items()}
+                    v_new, obj_new, status_new, _ = cabi.stage_dp_solve(sub, mats, rhs[lo:hi], cost[lo:hi], lb, ub, isb,
+                                                                        batch.dp_opts)
+                    solves += 1
+                    cabi.coupling_merge(lo, hi, Nt, 3, v_new, obj_new, status_new, cost, v_cur, pen_cur, v_bak, pen_bak)
                 evaluate(lo, hi)
-            now = float(brs[0].cpu())                                    # one read-back per pass
+            now = float(brs[0].cpu())                                    # one read-back per pass (the same on every rank)
             if not now < last:
-                if G >= B:
+                if G >= B_max:
                     break
-                G = min(B, 2 * G)
+                G = min(B_max, 2 * G)
             last = now
         st = brs.cpu().numpy()
         return dict(v=v_cur, pen=pen_cur, total=float(st[0]), solves=solves, accepted=int(st[2]) - 1)

@@ -282,8 +282,23 @@ def test_controller_on_a_symbolic_model_and_batch_from_front_end(cuda_device):
     assert abs(objs[0] - objs[1]) <= 1e-9 * max(1.0, abs(objs[1]))
     assert res["host"][0][0] == pytest.approx(objs[1], rel=1e-9)
     # a parameter change re-evaluates the model and asks for a rebuild (controller_base.py:503-505)
-    sym_ctrl.control_model.update_param_struct(T_h_max=p0["T_h_max"] + 5.0)
+    sym_ctrl.control_model.update_param_struct(T_h_max=p0["T_h_max"] - 7.0, P_h_Nom=p0["P_h_Nom"] * 0.8)
     assert sym_ctrl.build_required
+    # ... and the rebuild really recondenses: same matrices and objective as a controller made from the new parameters
+    sym_ctrl.build()
+    assert not sym_ctrl.build_required
+    x_hot = wl["x0"][0] * 0.0 + (p0["T_h_max"] - 4.0)      # above the lowered T_h_max: the new limit costs slack
+    obj_new = sym_ctrl.solve(k=0, x_k=x_hot, omega_tilde_k=wl["omega"][0])
+    p1 = dict(p0, T_h_max=p0["T_h_max"] - 7.0, P_h_Nom=p0["P_h_Nom"] * 0.8)
+    fresh = MpcController(model=M.DewhModel(param_struct=p1, const_heat=True), N_p=N_p)
+    fresh.set_std_obj_atoms(q_u=wl["q_u"][0], q_mu=wl["q_mu"][0])
+    fresh.build()
+    obj_fresh = fresh.solve(k=0, x_k=x_hot, omega_tilde_k=wl["omega"][0])
+    for grp in ("state_input", "constraint"):
+        for nm, mat in fresh.mld_evo_matrices[grp].items():
+            assert np.array_equal(mat, sym_ctrl.mld_evo_matrices[grp][nm]), nm
+    assert obj_new == pytest.approx(obj_fresh, rel=1e-12)
+    assert abs(obj_new - objs[0]) > 1e-6 * max(1.0, abs(objs[0]))          # (the change is visible in the objective)
 
 
 @pytest.mark.skipif(__import__("os").environ.get("HMPC_EXPERIMENTAL", "0") != "1",

@@ -48,3 +48,39 @@ def test_aggregate_exchange_world2():
     out = mgr.dict()
     mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
     assert out[0] and out[1]
+
+
+def _worker_blocks(rank, world, port, out):
+    """the loop skeleton of DewhFleet._best_response on uneven shards: every rank must issue the same number of
+    all-reduces per pass, whatever its own shard size"""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.distributed.init_process_group("gloo", rank=rank, world_size=world)
+    lo, hi = D.shard_range(5, rank, world)          # 3 agents on rank 0, 2 on rank 1
+    B = hi - lo
+    B_max = D.allreduce_max_int(B)
+    calls, covered, G = 0, set(), max(1, min(2, B_max))
+    sums = []
+    for _ in range(3):                              # the block count doubles up to the LARGEST shard
+        for blo, bhi in D.response_blocks(B, G):
+            covered.update(range(blo, bhi))
+            t = torch.tensor([float(bhi - blo)], dtype=torch.float64)
+            D.allreduce_aggregate(t)                # (would hang or mispair if the ranks disagreed on the count)
+            sums.append(float(t))
+            calls += 1
+        G = min(B_max, 2 * G)
+    out[rank] = (calls, B_max, sorted(covered) == list(range(B)), sums)
+    torch.distributed.destroy_process_group()
+
+
+def test_best_response_blocks_agree_on_uneven_shards():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker_blocks, args=(2, port, out), nprocs=2, join=True)
+    assert out[0][0] == out[1][0] == 2 + 3 + 3 and out[0][1] == out[1][1] == 3
+    assert out[0][2] and out[1][2]
+    assert out[0][3] == out[1][3]                   # every all-reduce paired the same block on both ranks
