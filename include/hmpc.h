@@ -137,6 +137,32 @@ int  hmpc_milp_solve_f64(int32_t B, int32_t n, int32_t m,
                          void* workspace, size_t workspace_bytes,
                          double* v, double* obj, int32_t* status, int32_t* stats, void* stream);
 
+/* ---- K3q/K4q mixed-integer QUADRATIC solve for any MLD: the same call of the reference as hmpc_milp_solve_f64
+ *      (controllers/controller_base.py:509-512) when the cost carries Quadratic / L22 atoms with dense weights
+ *      (controllers/components/objective_atoms.py:320-343, 185-206), L1 / Linf atoms (:338-363; the caller adds their
+ *      epigraph columns and rows) or non-linear rate atoms (:297-305):
+ *        minimise 0.5 v'P v + c'v  s.t.  H v <= rhs,  lb <= v <= ub,  v[j] in {0,1} where is_bin[j] != 0,   P >= 0.
+ *      One CTA per problem: depth-first branch and bound over an ADMM (OSQP-style splitting) relaxation whose linear
+ *      system is factorised once per problem.  Accuracy is that of `eps` (objectives to
+ *      ~1e-7 relative at the default).
+ *  P [B|1,n,n] (stride_P_b; NULL: an MILP), c [B|1,n], H [B|1,m,n], rhs [B,m], lb/ub/is_bin [n] shared by the batch.
+ *  stats [B,8] = {nodes, ADMM iterations, incumbent updates, binaries, 0, 0, 0, thousands of FMAs}.            */
+typedef struct {
+    double  mip_rel_gap;   /* 0 = prove optimality (up to eps)                        */
+    double  int_tol;       /* integrality tolerance of a relaxation, default 1e-6      */
+    double  eps;           /* absolute = relative ADMM tolerance (scaled problem), default 1e-9 */
+    double  rho;           /* initial step parameter, default 0.1 (adapted at the root) */
+    int32_t max_nodes;     /* per problem, default 100000                              */
+    int32_t max_iter;      /* ADMM iterations per node, default 50000                  */
+} hmpc_miqp_opts;
+void hmpc_miqp_default_opts(hmpc_miqp_opts* opts);
+int  hmpc_miqp_workspace_bytes(int32_t B, int32_t n, int32_t m, size_t* bytes);
+int  hmpc_miqp_solve_f64(int32_t B, int32_t n, int32_t m, const double* P, int64_t stride_P_b,
+                         const double* c, int64_t stride_c_b, const double* H, int64_t stride_H_b,
+                         const double* rhs, const double* lb, const double* ub, const uint8_t* is_bin,
+                         const hmpc_miqp_opts* opts, void* workspace, size_t workspace_bytes,
+                         double* v, double* obj, int32_t* status, int32_t* stats, void* stream);
+
 /* ---- K3s/K4s exact solve for SCALAR-STATE MLDs (the reference example's water heaters): same problem and
  *      same boundary as hmpc_milp_solve_f64 (controllers/controller_base.py:509-512), for the class
  *        nx == 1, nz == 0, every input/delta binary (nb = nu + ndelta <= 4), Psi = -diag(d) (each row owns at most

@@ -277,9 +277,11 @@ class BatchMpc(object):
         for ec in extra_constraints:
             w2 = ec.get("omega_tilde_k")
             sc = ec.get("omega_scenarios_k")
+            xk = ec.get("x_k")                 # a set may carry its own state (controller_base.py:411-456)
             w2 = omega if w2 is None else _dev_tensor(w2, self.device).reshape(d.B, self.nwt)
             sc = None if sc is None else _dev_tensor(sc, self.device).reshape(d.B, self.nwt, -1)
-            H, r = self.constraint_rows(x0, w2, scenarios=sc, N_tilde=ec.get("N_tilde"))
+            xk = x0 if xk is None or not d.nx else _dev_tensor(xk, self.device).reshape(d.B, d.nx)
+            H, r = self.constraint_rows(xk, w2, scenarios=sc, N_tilde=ec.get("N_tilde"))
             Hs.append(H)
             rs.append(r)
         lb, ub, isb = self._bounds_dev()

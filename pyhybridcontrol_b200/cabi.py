@@ -19,7 +19,8 @@ EVO_NAMES = ("Phi_x", "Gamma_v", "Gamma_omega", "Gamma_5", "L_x", "L_v", "L_omeg
              "H_x", "H_v", "H_omega", "H_5")
 EXPORTS = ("hmpc_version", "hmpc_last_cuda_error", "hmpc_device_info", "hmpc_condense_f64",
            "hmpc_condense_bytes_per_agent", "hmpc_constraint_rhs_f64", "hmpc_predict_f64", "hmpc_linear_cost_f64",
-           "hmpc_milp_default_opts", "hmpc_milp_workspace_bytes", "hmpc_milp_solve_f64", "hmpc_stage_dp_default_opts",
+           "hmpc_milp_default_opts", "hmpc_milp_workspace_bytes", "hmpc_milp_solve_f64", "hmpc_miqp_default_opts", "hmpc_miqp_workspace_bytes", "hmpc_miqp_solve_f64",
+           "hmpc_stage_dp_default_opts",
            "hmpc_stage_dp_supported", "hmpc_stage_dp_workspace_bytes", "hmpc_stage_dp_max_cells", "hmpc_stage_dp_solve_f64", "hmpc_lsim_step_f64",
            "hmpc_dewh_sim_step_f64", "hmpc_dewh_control_model_f64", "hmpc_dewh_thermostat_f64",
            "hmpc_param_eval_f64", "hmpc_param_eval_v2_f64", "hmpc_param_eval_bytes_per_agent",
@@ -58,6 +59,11 @@ class StageDpOpts(C.Structure):
                 ("table_fp64", C.c_int32), ("bound", C.c_int32), ("fuse_search", C.c_int32), ("reserved", C.c_int32)]
 
 
+class MiqpOpts(C.Structure):
+    _fields_ = [("mip_rel_gap", C.c_double), ("int_tol", C.c_double), ("eps", C.c_double), ("rho", C.c_double),
+                ("max_nodes", C.c_int32), ("max_iter", C.c_int32)]
+
+
 class StageTerms(C.Structure):
     _fields_ = [("T", C.c_int32), ("reserved", C.c_int32), ("h", C.c_void_p), ("h_stride_b", C.c_int64),
                 ("ga", C.c_void_p), ("ga_stride_b", C.c_int64), ("r", C.c_void_p), ("wq", C.c_void_p),
@@ -89,6 +95,11 @@ _lib.hmpc_milp_default_opts.restype = None
 _lib.hmpc_milp_workspace_bytes.argtypes = [C.c_int32] * 3 + [C.POINTER(MilpOpts), C.POINTER(C.c_size_t)]
 _lib.hmpc_milp_solve_f64.argtypes = [C.c_int32] * 3 + [_P, C.c_int64, _P, C.c_int64, _P, _P, _P, C.c_int64, _P,
                                                        C.POINTER(MilpOpts), _P, C.c_size_t, _P, _P, _P, _P, _P]
+_lib.hmpc_miqp_default_opts.argtypes = [C.POINTER(MiqpOpts)]
+_lib.hmpc_miqp_default_opts.restype = None
+_lib.hmpc_miqp_workspace_bytes.argtypes = [C.c_int32] * 3 + [C.POINTER(C.c_size_t)]
+_lib.hmpc_miqp_solve_f64.argtypes = [C.c_int32] * 3 + [_P, C.c_int64, _P, C.c_int64, _P, C.c_int64, _P, _P, _P, _P,
+                                                       C.POINTER(MiqpOpts), _P, C.c_size_t, _P, _P, _P, _P, _P]
 _lib.hmpc_stage_dp_default_opts.argtypes = [C.POINTER(StageDpOpts)]
 _lib.hmpc_stage_dp_default_opts.restype = None
 _lib.hmpc_stage_dp_supported.argtypes = [C.POINTER(Dims)]
@@ -289,6 +300,49 @@ def milp_solve(c, H, rhs, lb, ub, is_bin, opts=None):
                                     _ptr(rhs) if m else None, _ptr(lb2), _ptr(ub2),
                                     n if lb2.shape[0] == B and B > 1 else 0, _ptr(is_bin), C.byref(o), None, 0,
                                     _ptr(v), _ptr(obj), _ptr(status), _ptr(stats), _stream()), "hmpc_milp_solve_f64")
+    launch_count += 1
+    return v, obj, status, stats
+
+
+def miqp_default_opts(**kw):
+    o = MiqpOpts()
+    _lib.hmpc_miqp_default_opts(C.byref(o))
+    for k, v in kw.items():
+        setattr(o, k, v)
+    return o
+
+
+_qp_workspaces = {}
+
+
+def miqp_solve(c, H, rhs, lb, ub, is_bin, P=None, opts=None):
+    """K3q/K4q.  c [B|1,n], H [B|1,m,n], rhs [B,m], lb/ub [n], is_bin uint8 [n], P [B|1,n,n] or None
+    -> (v [B,n], obj [B], status [B], stats [B,8])."""
+    global launch_count
+    dev = rhs.device
+    B, m = rhs.shape
+    n = c.shape[-1]
+    c2 = c.reshape(-1, n).contiguous()
+    H3 = H.reshape(-1, m, n).contiguous()
+    P3 = None if P is None else P.reshape(-1, n, n).contiguous()
+    o = opts if opts is not None else miqp_default_opts()
+    need = C.c_size_t()
+    _check(_lib.hmpc_miqp_workspace_bytes(B, n, m, C.byref(need)), "hmpc_miqp_workspace_bytes")
+    key = (dev.index, torch.cuda.current_stream().cuda_stream)
+    ws = _qp_workspaces.get(key)
+    if ws is None or ws.numel() < need.value:
+        ws = torch.empty((need.value,), dtype=torch.uint8, device=dev)
+        _qp_workspaces[key] = ws
+    v = torch.empty((B, n), dtype=torch.float64, device=dev)
+    obj = torch.empty((B,), dtype=torch.float64, device=dev)
+    status = torch.empty((B,), dtype=torch.int32, device=dev)
+    stats = torch.empty((B, 8), dtype=torch.int32, device=dev)
+    _check(_lib.hmpc_miqp_solve_f64(B, n, m, None if P3 is None else _ptr(P3), 0 if (P3 is None or P3.shape[0] == 1 and B > 1) else n * n,
+                                    _ptr(c2), 0 if (c2.shape[0] == 1 and B > 1) else n,
+                                    _ptr(H3), 0 if (H3.shape[0] == 1 and B > 1) else m * n, _ptr(rhs.contiguous()),
+                                    _ptr(lb.reshape(-1)), _ptr(ub.reshape(-1)), _ptr(is_bin), C.byref(o),
+                                    C.c_void_p(ws.data_ptr()), need.value, _ptr(v), _ptr(obj), _ptr(status), _ptr(stats),
+                                    _stream()), "hmpc_miqp_solve_f64")
     launch_count += 1
     return v, obj, status, stats
 

@@ -358,8 +358,6 @@ class ConstraintSolvedController(ControllerBase):
                     and not with_std):
                 with_std = True
                 continue
-            if con.x_k is not None and not np.array_equal(con.x_k, self._x_k):
-                raise NotImplementedError("constraint sets with their own x_k are not supported")
             sc = con.omega_scenarios_k
             if sc is not None:
                 sc = sc[:info.nomega * self.N_tilde]
@@ -371,11 +369,28 @@ class ConstraintSolvedController(ControllerBase):
                 full = np.zeros((1, info.nomega * self.N_tilde))
                 full[0, :ww.size] = ww.ravel()
                 ww = full
-            extra.append(dict(omega_tilde_k=ww, omega_scenarios_k=sc, N_tilde=con.N_tilde))
+            xk = None if con.x_k is None else np.asarray(con.x_k, dtype=np.float64).reshape(1, -1)
+            extra.append(dict(omega_tilde_k=ww, omega_scenarios_k=sc, N_tilde=con.N_tilde, x_k=xk))
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
-        res = batch.solve(x0, w, cost_v=terms["cost_v"], w_x=terms["w_x"], w_y=terms["w_y"], extra_constraints=extra,
-                          with_std_constraints=with_std, quad=terms.get("quad"))
+        if getattr(self, "_general_path", False):
+            # a general MIQP: assembled on the device from the condensed matrices, solved by the ADMM branch and bound
+            from .. import miqp
+            sign = -1.0 if getattr(self, "_sense", "minimize").lower().startswith("max") else 1.0
+            atoms = list(self._std_obj_atoms.iter_atoms()) if (self._with_std_objective and self._std_obj_atoms) else []
+            prev = {name: np.asarray(val, dtype=np.float64).ravel() for name, val in (self.variables_k_neg1 or {}).items()
+                    if val is not None and name in ("x", "u", "delta", "z", "omega", "y", "mu", "v")}
+            prob = miqp.assemble(batch, x0, w, atoms, prev=prev, constraint_sets=extra, with_std_constraints=with_std,
+                                 sign=sign)
+            qopts = cabi.miqp_default_opts(mip_rel_gap=opts.mip_rel_gap)
+            if "max_nodes" in solver_kwargs:
+                qopts.max_nodes = int(solver_kwargs["max_nodes"])
+            res = miqp.solve(prob, qopts)
+            terms = dict(const=0.0)
+            res["obj"] = sign * res["obj"]           # (assemble() already applied the sense to the linear atoms)
+        else:
+            res = batch.solve(x0, w, cost_v=terms["cost_v"], w_x=terms["w_x"], w_y=terms["w_y"], extra_constraints=extra,
+                              with_std_constraints=with_std, quad=terms.get("quad"))
         status = int(res["status"].cpu()[0])
         if status in (2, 5) and res.get("solver") == "stage_dp" and not terms.get("quad"):
             # search budget exhausted (or the agent fell outside the class): the general kernel takes over
@@ -392,7 +407,11 @@ class ConstraintSolvedController(ControllerBase):
         self._solve_time_solver = ev0.elapsed_time(ev1) * 1e-3
         self._status_name = cabi.SOLVE_STATUS.get(status, str(status))
         self._stats = dict(zip(cabi.STAT_NAMES, res["stats"].cpu().numpy()[0].tolist()))
-        if status != 0:
+        obj_dev = float(res["obj"].cpu()[0])
+        # a search that ran out of budget still returns its incumbent, like a solver stopped by a node or time limit
+        # (the reference runs Gurobi with TimeLimit / MIPGap, micro_grid_control_simulation.py:232); the status and the
+        # certified gap stay readable in status_name / solver_stats
+        if status not in (0, 2, 3) or not np.isfinite(obj_dev):
             self._solution = None
             return float("inf") if status == 1 else float("nan")
         sign = -1.0 if getattr(self, "_sense", "minimize").lower().startswith("max") else 1.0
@@ -401,7 +420,9 @@ class ConstraintSolvedController(ControllerBase):
         self._solution = StructDict(v=v.cpu().numpy().reshape(-1, 1),
                                     x=(xt.cpu().numpy().reshape(-1, 1) if xt is not None else np.empty((0, 1))),
                                     y=(yt.cpu().numpy().reshape(-1, 1) if yt is not None else np.empty((0, 1))))
-        return sign * (float(res["obj"].cpu()[0]) + terms["const"])
+        if getattr(self, "_general_path", False):
+            return obj_dev                            # (sense and constants are part of the assembled problem)
+        return sign * (obj_dev + terms["const"])
 
     def feedback(self, k, x_k=None, omega_tilde_k=None, external_solve=None, solver=None, verbose=False,
                  warm_start=True, parallel=False, *args, method=None, **kwargs):

@@ -1,9 +1,11 @@
 """``MpcController``: constraint controller + objective built from the cost-atom grammar.
 
 Mirror of the reference's controllers/mpc_controller.py:20-101.  Linear atoms (everything the reference example
-uses: ``q_mu``, ``q_u``, ``q_z``) run on the GPU mixed-integer LP solver.  Quadratic / L1 / Linf atoms are
-parsed and validated like the reference but ``build()`` rejects them for now: the ADMM-based QP relaxation is
-the next row of the scope table.
+uses: ``q_mu``, ``q_u``, ``q_z``) run on the exact stage-DP / branch-and-cut kernels; separable Quadratic / L22 / L1
+atoms on a scalar-state MLD run on the stage-DP kernels as convex stage terms; every other combination of the
+grammar -- dense matrix weights, Linf, non-linear rate atoms, non-linear atoms on a vector-state MLD -- is assembled
+into the canonical mixed-integer QP (pyhybridcontrol_b200/miqp.py) and solved by the ADMM branch-and-bound kernel
+(csrc/miqp_admm.cu).
 """
 import numpy as np
 
@@ -54,34 +56,29 @@ class MpcController(PredictiveController):
         if not (sense.lower().startswith("min") or sense.lower().startswith("max")):
             raise ValueError("Problem 'sense' must be either 'minimize' or 'maximize', got '%s'." % sense)
         self._sense = sense
+        self._general_path = False
         if self._with_std_objective and self._std_obj_atoms is not None:
             for atom in self._std_obj_atoms.iter_atoms():
-                self._check_atom(atom)
+                if self._needs_general_path(atom):
+                    self._general_path = True
         self._finish_build()
 
-    def _check_atom(self, atom):
-        """Linear atoms run on both solve kernels; Quadratic / L22 / L1 atoms (an MIQP) run on the stage-DP kernels
-        when the MLD is in their class, with per-step diagonal weights and no rate form."""
+    def _needs_general_path(self, atom):
+        """Linear atoms run on both exact kernels; Quadratic / L22 / L1 atoms run on the stage-DP kernels when the MLD
+        is in their class, with per-step diagonal weights and no rate form.  Everything else is a general MIQP."""
         if atom.atom_type == "Linear":
-            return
+            return False
+        if self._sense.lower().startswith("max"):
+            raise NotImplementedError("cost atom %s on '%s': maximising a convex term is not a convex problem"
+                                      % (atom.atom_type, atom.var_name))
         batch = self._mld_evo_matrices.batch
-        why = None
-        if atom.atom_type == "Linf":
-            why = "Linf atoms are not supported"
-        elif not batch.stage_dp_ok:
-            why = "the MLD is outside the stage-DP class (scalar state, binary inputs) and branch-and-cut is an MILP solver"
-        elif atom.is_rate_atom:
-            why = "non-linear rate atoms couple consecutive stages"
-        elif atom.var_name in ("v", "z", "omega"):
-            why = "only x, y, u, delta and mu carry non-linear atoms"
-        elif self._sense.lower().startswith("max"):
-            why = "maximising a convex term is not a convex problem"
-        elif atom.weight_type == "matrix":
+        if atom.atom_type == "Linf" or not batch.stage_dp_ok or atom.is_rate_atom or atom.var_name in ("v", "z", "omega"):
+            return True
+        if atom.weight_type == "matrix":
             W = atom.weight_N_tilde
             if np.any(W - np.diag(np.diag(W)) != 0.0):
-                why = "matrix weights must be diagonal (stage-separable)"
-        if why:
-            raise NotImplementedError("cost atom %s on '%s': %s" % (atom.atom_type, atom.var_name, why))
+                return True
+        return False
 
     def _cost_terms(self, k):
         info = self.mld_info_k

@@ -159,6 +159,5 @@ def test_mpc_controller_miqp_atoms(cuda_device):
     fb = ctrl.feedback(k=0)
     if second - oref > 1e-6 * max(1.0, abs(oref)):
         assert fb.u[0, 0] == round(vref[0])
-    with pytest.raises(NotImplementedError):
-        ctrl.set_std_obj_atoms(q_Linf_x=1.0)
-        ctrl.build()
+    with pytest.raises(NotImplementedError):             # maximising a convex atom is not a convex problem
+        ctrl.build(sense="maximize")
