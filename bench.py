@@ -50,6 +50,10 @@ def parse_args():
     ap.add_argument("--solver", default="auto", choices=("auto", "bnc", "stage_dp"),
                     help="auto = exact stage-DP kernels for the scalar-state DEWH class, bnc = general branch-and-cut")
     ap.add_argument("--cells", type=int, default=0, help="stage-DP value-table cells per stage (0 = library default)")
+    ap.add_argument("--recondense", action="store_true",
+                    help="run K1 inside every timed step although the models do not change (the reference condenses "
+                         "only when the model's version changed, mld_evolution_matrices.py:79)")
+    ap.add_argument("--no-extra-configs", action="store_true", help="skip the BASELINE configs[2] / configs[3] blocks")
     return ap.parse_args()
 
 
@@ -186,6 +190,113 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
+# ------------------------------------------------------------------------------------------------ BASELINE configs[2], [3]
+def extra_configs(world, rank, dev):
+    """BASELINE.json configs[2] and configs[3], strong-scaled over the ranks of this run, through the public fleet API:
+      config3  residential micro-grid: 1,000 DEWHs + PV + residential demand + grid agent, N_p = 48 -- per step every
+               rank solves its contiguous shard, the aggregate power is all-reduced, the grid MLD is evaluated;
+      config4  10,000 DEWHs, closed loop over 24 h (96 steps of 15 min): per step MLD re-parametrisation, MILP solve,
+               simulation step, aggregate exchange.
+    Times are CUDA events, max over ranks; every solve is proven optimal unless `not_optimal` says otherwise."""
+    import torch
+    import torch.distributed as dist
+    from pyhybridcontrol_b200 import distributed
+    from pyhybridcontrol_b200.examples.residential_mg_with_pv_and_dewhs import synthetic as syn
+    from pyhybridcontrol_b200.examples.residential_mg_with_pv_and_dewhs.fleet import DewhFleet
+    out = {}
+    N_p = 48
+    Nt = N_p + 1
+
+    def params(lo, hi):
+        base = [syn.dewh_agent_params(a) for a in range(256)]
+        return [base[b % 256] for b in range(lo, hi)]
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([float(x)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---- config 3
+    total = 1000
+    lo, hi = distributed.shard_range(total, rank, world)
+    B = hi - lo
+    fleet = DewhFleet(params(lo, hi), N_p, device=dev)
+    rng = np.random.default_rng(0)
+    T0_all = rng.integers(55, 65, size=total).astype(float)
+    T0 = torch.as_tensor(T0_all[lo:hi]).to(dev)
+    demand = torch.as_tensor(np.stack([syn.dhw_demand_profile(Nt, seed=b % 256) for b in range(lo, hi)])).to(dev)
+    price = syn.price_profile(Nt, seed=1)
+    k = np.arange(Nt)
+    p_pv = torch.as_tensor(-3000.0 * total * np.clip(np.sin((k / 96.0) * 2 * np.pi - 0.5 * np.pi), 0, None)).to(dev)
+    p_res = torch.as_tensor(1200.0 * total * (1.0 + 0.3 * np.sin(k / 96.0 * 4 * np.pi))).to(dev)
+    fleet.build()
+    cost = fleet.cost_from_prices(price)
+
+    def microgrid_step():
+        res = fleet.control_step(T0.reshape(B, 1), demand, cost)
+        p_dev = fleet.aggregate_power(res["u"])            # + NCCL all-reduce when several ranks run
+        grid = distributed.grid_evaluate(p_dev, p_pv, p_res)
+        return res, grid
+    for _ in range(3):
+        res, grid = microgrid_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    reps = 20
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        res, grid = microgrid_step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = max_over_ranks(e0.elapsed_time(e1) / reps)
+    out["config3"] = {"workload": "configs[2]: 1,000 DEWHs + PV + demand + grid agent, N_p=48, agents sharded over %d GPU(s), "
+                                  "all-reduce of the aggregate power, grid MLD evaluated every step" % world,
+                      "agents": total, "scaling": "strong", "ms_per_step": ms, "solves_per_s": total / ms * 1e3,
+                      "not_optimal": int(sum_over_ranks(int((res["status"] != 0).sum()))),
+                      "grid_import_cost": float((grid["p_imp"] * torch.as_tensor(price).to(dev)).sum())}
+    del fleet
+    torch.cuda.empty_cache()
+    # ---- config 4
+    total, steps = 10000, 96
+    lo, hi = distributed.shard_range(total, rank, world)
+    B = hi - lo
+    fleet = DewhFleet(params(lo, hi), N_p, device=dev)
+    T0 = np.random.default_rng(1).integers(55, 65, size=total).astype(float)[lo:hi]
+    prof = np.stack([syn.dhw_demand_profile(steps + Nt, seed=b) for b in range(256)])
+    demand = prof[np.arange(lo, hi) % 256]
+    price = syn.price_profile(steps + Nt, seed=2)
+    fleet.closed_loop(T0, demand, price, 2)                 # warm-up (allocations, first launches)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    log = fleet.closed_loop(T0, demand, price, steps)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    out["config4"] = {"workload": "configs[3]: 10,000 DEWHs closed loop 24 h (96 x 15 min: re-parametrisation + MILP solve + "
+                                  "sim step + aggregate exchange), agents sharded over %d GPU(s)" % world,
+                      "agents": total, "sim_steps": steps, "scaling": "strong", "wall_ms": ms,
+                      "ms_per_control_step": ms / steps, "solves_per_s": total * steps / ms * 1e3,
+                      "not_optimal": int(sum_over_ranks(int((log["status"] != 0).sum()))),
+                      "T_min": float(log["T"].min()), "T_max": float(log["T"].max()),
+                      "heater_duty": float(log["u"].mean())}
+    del fleet, log
+    torch.cuda.empty_cache()
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ GPU arm
 def main_ours(args):
     import torch
@@ -225,12 +336,14 @@ def main_ours(args):
     dp_opts = cabi.stage_dp_default_opts(**({"cells": args.cells} if args.cells else {}))
     kernel_ms = {k: 0.0 for k in names}
     solve_stats, statuses = [], []
+    fleet.build()                                  # K1 once: the models do not change between the control instants
 
     def one_step(inp, timed_events=None):
         ev = timed_events
         if ev:
             ev[0].record()
-        fleet.build()
+        if args.recondense or ev:                  # (the per-kernel breakdown pass always runs K1, to time it)
+            fleet.build()
         if ev:
             ev[1].record()
         rhs = cabi.constraint_rhs(fleet.batch.dims, fleet.batch.evo, inp["x0"], inp["omega"])
@@ -401,7 +514,7 @@ def main_ours(args):
     t_wall = time.perf_counter() - t_wall0
     sampler.stop_flag = True
     note("timed region done")
-    launches_per_step = 1 + 1 + (2 if use_dp else 1) + 1 + 2      # K1, K2, K3/K4, K5, K6 (two-pass reduction)
+    launches_per_step = (1 if args.recondense else 0) + 1 + (2 if use_dp else 1) + 1 + 2      # [K1], K2, K3/K4, K5, K6 (two passes)
     launches = launches_per_step * K if graph is not None else cabi.launch_count - launches0
     if graph is not None:
         step_ms = [e[0].elapsed_time(e[1]) - flush_one_ms for e in evs.values()]
@@ -440,7 +553,7 @@ def main_ours(args):
         st = o[2].cpu().numpy()
         ss = o[3].cpu().numpy()
         not_opt += int((st != 0).sum())
-        fma += float(ss[:, 7].astype(np.float64).sum()) * 1024.0
+        fma += float(ss[:, 7].astype(np.float64).sum()) * 1000.0          # FP64-pipe instructions executed (kernel-counted)
         piv.append(ss[:, 1])
         solve_stats.append(ss)
     piv = np.concatenate(piv)
@@ -451,30 +564,41 @@ def main_ours(args):
     plan = cabi.StepPlan(fleet.batch.dims, cabi.default_opts(force_general=0 if use_dp else 1))
     hmats = dict(wl0["mats"])
     hmats["C"] = np.ones((1, 1, 1))
-    e2e_times, e2e_dev = [], []
-    for s in range(W + K):
-        inp = steps_in[s % P]
-        flush.fill_(float(s))
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        v_h, obj_h, st_h, stats_h, tm = plan.step(hmats, inp["host"]["x0"], inp["host"]["omega"], inp["host_cost"],
-                                                  fleet.batch.lb_v, fleet.batch.ub_v, fleet.batch.is_bin_v,
-                                                  recondense=True)
-        u0 = v_h[:, 0].sum()  # the step's result is read on the host
-        dt = time.perf_counter() - t0
-        if s >= W:
-            e2e_times.append(dt)
-            e2e_dev.append(tm)
-    h2d, d2h = plan.bytes_per_step(True)
-    e2e_total = float(sum(e2e_times))
-    if world > 1:
-        t = torch.tensor([e2e_total], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_total = float(t.item())
+    def run_e2e(recondense):
+        times, devt = [], []
+        for s in range(W + K):
+            inp = steps_in[s % P]
+            flush.fill_(float(s))
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            v_h, obj_h, st_h, stats_h, tm = plan.step(hmats, inp["host"]["x0"], inp["host"]["omega"], inp["host_cost"],
+                                                      fleet.batch.lb_v, fleet.batch.ub_v, fleet.batch.is_bin_v,
+                                                      recondense=bool(recondense or s == 0))
+            u0 = v_h[:, 0].sum()  # the step's result is read on the host
+            dt = time.perf_counter() - t0
+            if s >= W:
+                times.append(dt)
+                devt.append(tm)
+        total = float(sum(times))
+        if world > 1:
+            t = torch.tensor([total], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            total = float(t.item())
+        return total, devt, obj_h
+    e2e_total_rc, e2e_dev_rc, _ = run_e2e(True)
+    e2e_total, e2e_dev, obj_h = run_e2e(args.recondense)
+    h2d, d2h = plan.bytes_per_step(bool(args.recondense))
+    h2d_rc, _ = plan.bytes_per_step(True)
     e2e_value = world * B * K / e2e_total
     # parity spot check inside the bench: e2e path and device path agree on the last step
     assert np.allclose(obj_h, last_obj.cpu().numpy(), rtol=1e-9, atol=1e-12), "host and device paths disagree"
     plan.close()
+    extra = {}
+    if not args.no_extra_configs:
+        try:
+            extra = extra_configs(world, rank, dev)
+        except Exception as exc:          # (never let the side measurements break the headline line)
+            extra = {"extra_configs_error": repr(exc)}
 
     if rank != 0:
         if world > 1:
@@ -496,10 +620,24 @@ def main_ours(args):
     # bytes K1 writes per launch in this pipeline (the four constraint matrices) -- algorithmic, see DESIGN.md
     cond_bytes = 8 * B * (d.nc * Nt) * (d.nx + d.nv * Nt + d.nomega * Nt + 1)
     achieved_tf = (2.0 * fma / K) / (solve_ms * 1e-3) / 1e12 if solve_ms > 0 else 0.0
+    D_search = 5                                   # depth of one search expansion for one binary per step
+    table_bytes = B * ((Nt - 1) // D_search) * int(dp_opts.cells) * tab_bytes if use_dp else None
+    allst = np.concatenate(solve_stats, axis=0).astype(np.float64) if solve_stats else np.zeros((1, 8))
+    phase_us = [[float(allst[:, c].mean() / 10.0), float(allst[:, c].max() / 10.0)] for c in (1, 2, 4)]
+    # FP64-pipe utilisation of the sweep phase alone, on the SMs that have a CTA: sweep instructions of one agent over
+    # its own sweep time against one SM's share of the peak
+    sweep_frac = None
+    if use_dp and phase_us[1][0] > 0 and fp64_peak:
+        per_agent_ins = (fma / K) / B
+        sweep_frac = (2.0 * per_agent_ins / (phase_us[1][0] * 1e-6) / 1e12) / (fp64_peak / 148.0)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic", "config": dict(workload_config(args, world), solver="stage_dp" if use_dp else "bnc",
+        "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
+        "run_config": dict(solver="stage_dp" if use_dp else "bnc",
+                       K1="inside every step (--recondense)" if args.recondense else
+                          "once, before the timed region: the models do not change (reference: mld_evolution_matrices.py:79); "
+                          "ms_per_step_with_recondense adds the measured K1 launch",
                        launch="one CUDA graph per step" if graph is not None else "kernel by kernel",
                        timing="one event pair around the K steps minus K L2 flushes (%.4f ms each, calibrated before the "
                               "timed region; the flush is the first node of each step's graph); the NCCL exchange of "
@@ -510,26 +648,41 @@ def main_ours(args):
         "ms_per_step_by_rank": rank_ms, "sm_mhz_by_rank_after_timed_region": rank_mhz,
         "host_ms_per_step": {"loop": 1e3 * t_host_loop / K, "graph_launch": 1e3 * host_us[0] / K,
                              "exchange_enqueue": 1e3 * host_us[1] / K},
+        "ms_per_step_with_recondense": total_ms / K + (0.0 if args.recondense else cond_ms),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": 1e3 * e2e_total / K, "api": "hmpc_mpc_step_host_f64 via cabi.StepPlan.step",
+                "recondense": bool(args.recondense),
+                "with_recondense_every_step": {"value": world * B * K / e2e_total_rc, "ms_per_step": 1e3 * e2e_total_rc / K,
+                                               "h2d_bytes_per_step": int(h2d_rc)},
                 "device_ms_per_step": dict(zip(("h2d", "kernels", "d2h", "total"),
                                                [float(x) for x in np.mean(np.array(e2e_dev), axis=0)]))},
         "gpu_launches": int(launches),
         "kernel_ms_per_step": dict({k: v / K for k, v in kernel_ms.items()},
                                    note="untimed eager pass with events between the launches (%d steps)" % Kb),
-        "roofline": {"kernel": "stage_dp_table_kernel + stage_dp_search_kernel" if use_dp else "milp_bnc_kernel",
-                     "bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak,
-                     "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak if fp64_peak else None,
-                     "traffic": (B * (Nt - 1) * dp_opts.cells * tab_bytes) if use_dp else None,
-                     "peak_source": "hmpc_fp64_peak_probe (DFMA micro-benchmark, measured in this run)",
-                     "share_of_step": solve_ms / (total_ms / K),
-                     "note": ("value-table sweep + exact search: algorithmic FP64 FMAs counted by the kernels "
-                              "(cells x actions x (4 + 3 rows)); `traffic` = value-table bytes streamed to HBM per "
-                              "launch (hbm_write_gbs below); SURVEY 8(d) names the FP64 pipe / latency, not HBM, "
-                              "as the bound of the solve") if use_dp else
-                             ("latency-bound tree search: algorithmic FMAs (pivots, row transforms) counted by the "
-                              "kernel itself; SURVEY 8(d) names FP64 pipe / latency, not HBM, as the bound"),
-                     "hbm_write_gbs": (B * (Nt - 1) * dp_opts.cells * tab_bytes / (solve_ms * 1e-3) / 1e9) if use_dp else None},
+        "roofline": ({"kernel": "stage_dp_table_kernel (+ stage_dp_search_kernel)", "bound": "fp64",
+                      "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+                      "frac": achieved_tf / fp64_peak if fp64_peak else None,
+                      "traffic": table_bytes, "peak_source": "hmpc_fp64_peak_probe (DFMA micro-benchmark, measured in this run; "
+                                                              "not in MEASURED_PEAKS.json)",
+                      "share_of_step": solve_ms / (total_ms / K),
+                      "fp64_pipe_instructions_per_launch": fma / K,
+                      "sweep_phase": {"us_mean": phase_us[1][0], "us_max": phase_us[1][1],
+                                      "frac_of_peak_while_sweeping": sweep_frac},
+                      "phases_us_mean_max": {"setup": phase_us[0], "sweep": phase_us[1], "search": phase_us[2]},
+                      "hbm_write_gbs": table_bytes / (solve_ms * 1e-3) / 1e9 if solve_ms > 0 else None,
+                      "note": "achieved = 2 x FP64-pipe instructions the kernels EXECUTE (DFMA, DADD, DMUL, DSETP each "
+                              "occupy one issue slot of the FP64 pipe; counted per path by the kernel: 4 per cell where no "
+                              "row is violated, 5 + 3 rows elsewhere on the DEWH path, + the search's) / the solve launch's "
+                              "CUDA-event duration, i.e. the fraction is FP64-pipe utilisation over the whole launch, "
+                              "set-up and search tail included, on the SMs' aggregate peak (100 of 148 SMs have a CTA at "
+                              "B = 100); `traffic` = value-table bytes leaving the SMs per launch (only the stages the "
+                              "search can read are stored: k = D, 2D, ...)"} if use_dp else
+                     {"kernel": "milp_bnc_kernel", "bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak,
+                      "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak if fp64_peak else None, "traffic": None,
+                      "peak_source": "hmpc_fp64_peak_probe (DFMA micro-benchmark, measured in this run)",
+                      "share_of_step": solve_ms / (total_ms / K),
+                      "note": "latency-bound tree search: algorithmic FMAs (pivots, row transforms) counted by the "
+                              "kernel itself; SURVEY 8(d) names FP64 pipe / latency, not HBM, as the bound"}),
         "roofline_condense": {"kernel": "condense_kernel", "bound": "hbm", "achieved": cond_bytes / (cond_ms * 1e-3) / 1e9,
                               "peak": hbm_peak, "unit": "GB/s",
                               "frac": cond_bytes / (cond_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
@@ -544,6 +697,7 @@ def main_ours(args):
         "wall_s_timed_region": t_wall,
         "clocks": sampler.summary(),
     }
+    line.update(extra)
     # K1 at a batch that fills the GPU (the bench batch of 100 agents writes 15 MB: launch/latency-bound)
     try:
         Bl = 8192

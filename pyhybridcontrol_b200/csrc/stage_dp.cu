@@ -838,17 +838,27 @@ __global__ void __launch_bounds__(kTableBlock) stage_dp_table_kernel(const DpArg
         if (helper) {
             const int jl0 = c.sc_semi[8 * k], jl1 = c.sc_semi[8 * k + 1], jh0 = c.sc_semi[8 * k + 2], jh1 = c.sc_semi[8 * k + 3];
             const int jl = min(max(jl0, jl1), G - 1), jh = min(jh0, jh1);
-            double m0 = INFINITY, m1 = INFINITY, m2 = INFINITY, m3 = INFINITY;
-            for (int j = lane; j <= jl; j += 32) {
-                const double v = Cell<FMT>::lo(cur[j]);
-                if (j <= jl0) m0 = dmin(m0, v);
-                if (j <= jl1) m1 = dmin(m1, v);
-            }
-            if (jh < G) for (int j = max(jh, 0) + lane; j < G; j += 32) {
-                const double v = Cell<FMT>::lo(cur[j]);
-                if (j >= jh0) m2 = dmin(m2, v);
-                if (j >= jh1) m3 = dmin(m3, v);
-            }
+            // (the helper warp is the only one on this chain: its loads are batched eight deep so that the scan of a
+            // range costs a few shared-memory latencies, not one per 32 cells)
+            auto range_min = [&](int a, int bq) -> double {      // min over cells [a, bq] (this lane's share)
+                double acc[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) acc[u] = INFINITY;
+                int j = a + lane;
+                for (; j + 7 * 32 <= bq; j += 8 * 32) {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) acc[u] = dmin(acc[u], Cell<FMT>::lo(cur[j + u * 32]));
+                }
+                for (; j <= bq; j += 32) acc[0] = dmin(acc[0], Cell<FMT>::lo(cur[j]));
+#pragma unroll
+                for (int u = 1; u < 8; ++u) acc[0] = dmin(acc[0], acc[u]);
+                return acc[0];
+            };
+            (void)jl; (void)jh;
+            double m0 = jl0 >= 0 ? range_min(0, min(jl0, G - 1)) : INFINITY;
+            double m1 = jl1 >= 0 ? range_min(0, min(jl1, G - 1)) : INFINITY;
+            double m2 = jh0 < G ? range_min(max(jh0, 0), G - 1) : INFINITY;
+            double m3 = jh1 < G ? range_min(max(jh1, 0), G - 1) : INFINITY;
             m0 = jl0 >= 0 ? key_value(warp_min_key(m0)) : INFINITY;
             m1 = jl1 >= 0 ? key_value(warp_min_key(m1)) : INFINITY;
             m2 = jh0 < G ? key_value(warp_min_key(m2)) : INFINITY;
