@@ -24,50 +24,120 @@ class ControllerSolverError(RuntimeError):
     pass
 
 
-class MldSimLog(dict):
-    """k -> LogEntry_k of column vectors, NaN padded (reference: controllers/controller_base.py:58-146)."""
+class MldSimLog(object):
+    """Columnar simulation log: one ``[rows, dim]`` array per logged variable plus the list of instants k, so that a
+    closed loop appends rows and the result frame (``get_concat_log``; reference layout: controllers/
+    controller_base.py:116-146, columns ``(var_names, var_index)``, index k) is a concatenation of whole arrays.  An
+    entry that lacks a variable reads as NaN (None for non-numeric variables).  ``log[k]`` gives the entry of instant k
+    as a struct of column vectors, the form ``ControllerBase.sim_step_k`` and the rate atoms consume."""
 
     def __init__(self):
-        super(MldSimLog, self).__init__()
-        self._nan_insert = {}
+        self._row_of = {}            # k -> row
+        self._ks = []                # row -> k
+        self._cols = {}              # name -> [capacity, dim] array (float or object)
+        self._has = {}               # name -> [capacity] bool: the entry has this variable
+
+    # -- mapping surface
+    def __contains__(self, k):
+        return k in self._row_of
+
+    def __len__(self):
+        return len(self._ks)
+
+    def __iter__(self):
+        return iter(list(self._ks))
+
+    def keys(self):
+        return list(self._ks)
+
+    def get(self, k, default=None):
+        return self[k] if k in self._row_of else default
+
+    def __getitem__(self, k):
+        r = self._row_of[k]
+        out = StructDict()
+        for name, col in self._cols.items():
+            out[name] = col[r].reshape(-1, 1) if self._has[name][r] else self._blank(col)[0].reshape(-1, 1)
+        return out
+
+    def pop(self, k, default=None):
+        if k not in self._row_of:
+            return default
+        entry = self[k]
+        r = self._row_of.pop(k)
+        self._ks.pop(r)
+        for name in self._cols:
+            self._cols[name] = np.delete(self._cols[name], r, axis=0)
+            self._has[name] = np.delete(self._has[name], r, axis=0)
+        self._row_of = {kk: i for i, kk in enumerate(self._ks)}
+        return entry
 
     @staticmethod
-    def _nan_if_num(var):
-        var = np.asarray(var)
-        if np.issubdtype(var.dtype, np.number) or np.issubdtype(var.dtype, np.bool_):
-            return var * np.nan
-        return atleast_2d_col([None] * var.size)
+    def _blank(col, rows=1):
+        if col.dtype == object:
+            return np.full((rows, col.shape[1]), None, dtype=object)
+        return np.full((rows, col.shape[1]), np.nan)
 
+    def _row(self, k):
+        r = self._row_of.get(k)
+        if r is None:
+            r = len(self._ks)
+            self._row_of[k] = r
+            self._ks.append(k)
+            for name, col in self._cols.items():
+                if r >= col.shape[0]:
+                    grow = max(16, col.shape[0])
+                    self._cols[name] = np.concatenate([col, self._blank(col, grow)], axis=0)
+                    self._has[name] = np.concatenate([self._has[name], np.zeros(grow, dtype=bool)])
+        return r
+
+    # -- writers (same call forms as the reference's log)
     def set_sim_k(self, k, sim_k=None, **kwargs):
         self.pop(k, None)
         self.update_sim_k(k=k, sim_k=sim_k, **kwargs)
 
     def update_sim_k(self, k, sim_k=None, **kwargs):
-        sim_k = dict(sim_k) if sim_k is not None else {}
-        sim_k.update(kwargs)
-        insert = StructDict(self._nan_insert)
-        if self.get(k):
-            insert.update(self[k])
-        for name, var in sim_k.items():
-            if var is not None:
-                var = atleast_2d_col(var)
-                prev = insert.get(name)
-                if prev is not None and np.shape(prev) != var.shape:
-                    raise ValueError("shape of var_k must match previous inserts")
-                insert[name] = var
-        dict.__setitem__(self, k, insert)
-        if set(insert).difference(self._nan_insert):
-            self._nan_insert = {n: self._nan_if_num(v) for n, v in insert.items()}
+        items = dict(sim_k) if sim_k is not None else {}
+        items.update(kwargs)
+        r = self._row(k)
+        for name, var in items.items():
+            if var is None:
+                continue
+            var = np.asarray(atleast_2d_col(var))
+            numeric = np.issubdtype(var.dtype, np.number) or np.issubdtype(var.dtype, np.bool_)
+            col = self._cols.get(name)
+            if col is None:
+                cap = max(16, len(self._ks))
+                col = (np.full((cap, var.shape[0]), np.nan) if numeric else np.full((cap, var.shape[0]), None, dtype=object))
+                self._cols[name] = col
+                self._has[name] = np.zeros(cap, dtype=bool)
+            if var.shape != (col.shape[1], 1):
+                raise ValueError("shape of var_k must match previous inserts")
+            if numeric and col.dtype != object:
+                col[r] = var[:, 0]
+            else:
+                if col.dtype != object:
+                    col = col.astype(object)
+                    self._cols[name] = col
+                col[r] = list(var[:, 0])
+            self._has[name][r] = True
 
     def get_concat_log(self, add_column_levels=None):
         import pandas as pd
-        index = sorted(self)
-        dfs = {}
-        for name in self._nan_insert:
-            seq = np.array([np.asarray(self[k].get(name, self._nan_insert[name])) for k in index])
-            if seq.size:
-                dfs[name] = pd.DataFrame(seq.squeeze(axis=2))
-        df = pd.concat(dfs, keys=list(dfs), axis=1)
+        order = np.argsort(np.array(self._ks, dtype=object)) if self._ks else np.zeros(0, dtype=int)
+        index = [self._ks[i] for i in order]
+        frames = {}
+        for name, col in self._cols.items():
+            if col.shape[1]:
+                block = col[:len(self._ks)][order]
+                if col.dtype == object:
+                    block = np.array(block.tolist(), dtype=object)
+                    try:
+                        block = block.astype(float)
+                    except (TypeError, ValueError):
+                        pass
+                frames[name] = pd.DataFrame(block)
+        df = pd.concat(frames, keys=list(frames), axis=1)
         df.columns.names = ["var_names", "var_index"]
         df.index = index
         df.index.name = "k"

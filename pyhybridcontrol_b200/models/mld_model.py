@@ -372,10 +372,8 @@ class MldSystemModel(object):
             self._mld_numeric, self._mld_callable, self._mld_symbolic = mlds
         param_struct = param_struct if param_struct is not None else (self._param_struct or {})
         try:
-            self._param_struct = self._validate_param_struct(param_struct=param_struct,
-                                                             param_struct_subset=param_struct_subset,
-                                                             missing_param_check=missing_param_check,
-                                                             invalid_param_check=invalid_param_check, **kwargs)
+            self._param_struct = self._resolve_params(param_struct, param_struct_subset, kwargs, missing_param_check,
+                                                      invalid_param_check)
         except ValueError as ve:
             raise ValueError("A valid 'param_struct' is required, the argument was not provided or is invalid. %s"
                              % ve.args[0])
@@ -409,66 +407,63 @@ class MldSystemModel(object):
     def version(self):
         return (self._version, self._mld_numeric.version if self._mld_numeric is not None else 0)
 
-    def update_param_struct(self, param_struct=None, param_struct_subset=None, missing_param_check=True,
-                            invalid_param_check=False, **kwargs):
-        """New parameter set -> new ``mld_numeric`` (reference: models/mld_model.py:1072-1081)."""
-        param_struct = self._validate_param_struct(param_struct=param_struct, param_struct_subset=param_struct_subset,
-                                                   missing_param_check=missing_param_check,
-                                                   invalid_param_check=invalid_param_check, **kwargs)
-        self._mld_numeric = self.get_mld_numeric(param_struct=param_struct, _bypass_param_struct_validation=True)
-        self._param_struct = param_struct
-        self._version = _next_version()
-
-    def _validate_param_struct(self, param_struct=None, param_struct_subset=None, missing_param_check=False,
-                               invalid_param_check=False, **kwargs):
-        # reference: models/mld_model.py:1083-1126
-        param_struct_subset = param_struct_subset if param_struct_subset is not None else {}
-        param_struct = param_struct if param_struct is not None else self._param_struct
-        try:
-            param_struct_subset.update(kwargs)
-        except AttributeError:
+    # ---- parameters.  The stored parameter set is a table (name -> value); every call that takes parameters resolves
+    # them against that table with the same three inputs the reference accepts (models/mld_model.py:1072-1149): a full
+    # replacement (`param_struct`), a partial override (`param_struct_subset` and keyword arguments), and two checks.
+    def _resolve_params(self, replacement, overrides, keywords, require_all, known_only):
+        """-> the parameter table a call works with; the STORED table itself when nothing was given (callers test
+        identity to reuse the stored numeric model)."""
+        stored = self._param_struct
+        if overrides is None:
+            overrides = {}
+        if not hasattr(overrides, "update") or not hasattr(overrides, "keys"):
             raise TypeError("Invalid type for 'param_struct_subset', must be dictionary like or None.")
-        if not param_struct_subset and param_struct is self._param_struct:
-            return self._param_struct
-        elif param_struct is self._param_struct:
-            param_struct = StructDict(self._param_struct)
-            given_params = param_struct_subset
-            param_struct.update(param_struct_subset)
-        else:
-            try:
-                param_struct = StructDict(param_struct)
-                param_struct.update(param_struct_subset)
-            except (AttributeError, TypeError, ValueError):
-                raise TypeError("Invalid type for 'param_struct', must be dictionary like or None.")
-            given_params = param_struct
-        if missing_param_check:
-            missing_keys = set(self.get_required_params()).difference(param_struct.keys())
-            if missing_keys:
-                raise ValueError("The following keys are missing from param_struct: '%s'" % missing_keys)
-        if invalid_param_check:
-            invalid_params = set(given_params.keys()).difference((self._param_struct or {}).keys())
-            if invalid_params:
+        overrides.update(keywords)
+        replacing = replacement is not None and replacement is not stored
+        if not replacing and not overrides:
+            return stored
+        try:
+            table = StructDict(replacement if replacing else stored)
+            table.update(overrides)
+        except (AttributeError, TypeError, ValueError):
+            raise TypeError("Invalid type for 'param_struct', must be dictionary like or None.")
+        if require_all:
+            absent = set(self.get_required_params()) - set(table.keys())
+            if absent:
+                raise ValueError("The following keys are missing from param_struct: '%s'" % absent)
+        if known_only:
+            named = table if replacing else overrides          # what the caller spelled out
+            unknown = set(named.keys()) - set((stored or {}).keys())
+            if unknown:
                 raise ValueError("Invalid keys:'%s' in kwargs/param_struct - keys must all exist in "
                                  "self.param_struct. Hint: either disable 'invalid_param_check' or update "
-                                 "self.param_struct." % invalid_params)
-        return param_struct
+                                 "self.param_struct." % unknown)
+        return table
+
+    def update_param_struct(self, param_struct=None, param_struct_subset=None, missing_param_check=True,
+                            invalid_param_check=False, **kwargs):
+        """Store a new parameter table and re-evaluate the numeric model from it (one param-eval launch)."""
+        table = self._resolve_params(param_struct, param_struct_subset, kwargs, missing_param_check, invalid_param_check)
+        self._mld_numeric = self._evaluate(table)
+        self._param_struct = table
+        self._version = _next_version()
+
+    def _evaluate(self, table):
+        if table is self._param_struct:
+            return self._mld_numeric
+        if self._mld_callable is None:
+            raise TypeError("AgentModel does not contain valid mld_callable.")
+        return self._mld_callable.to_numeric(table)
 
     def get_mld_numeric(self, param_struct=None, param_struct_subset=None, missing_param_check=False,
                         invalid_param_check=True, copy=False, **kwargs):
-        """``mld_numeric`` for the stored parameters, or a fresh evaluation for other ones
-        (reference: models/mld_model.py:1128-1149)."""
-        if kwargs.pop("_bypass_param_struct_validation", False):
-            compute_param_struct = param_struct
-        else:
-            compute_param_struct = self._validate_param_struct(param_struct=param_struct,
-                                                               param_struct_subset=param_struct_subset,
-                                                               missing_param_check=missing_param_check,
-                                                               invalid_param_check=invalid_param_check, **kwargs)
-        if compute_param_struct is not self._param_struct:
-            if self._mld_callable is None:
-                raise TypeError("AgentModel does not contain valid mld_callable.")
-            return self._mld_callable.to_numeric(compute_param_struct, copy=copy)
-        return self._mld_numeric
+        """The stored numeric model, or a fresh evaluation when other parameters are given."""
+        table = self._resolve_params(param_struct, param_struct_subset, kwargs, missing_param_check, invalid_param_check)
+        if table is self._param_struct:
+            return self._mld_numeric
+        if self._mld_callable is None:
+            raise TypeError("AgentModel does not contain valid mld_callable.")
+        return self._mld_callable.to_numeric(table, copy=copy)
 
     def get_mld_numeric_batch(self, overrides=None, B=None, param_struct=None, device="cuda"):
         """The model of B agents at once: name -> CUDA tensor ``[B|1, rows, cols]`` (one kernel launch).  ``overrides``

@@ -286,7 +286,7 @@ class ExprProgram(object):
 
     @property
     def instructions_v2(self):
-        """(instructions, n_regs) for the experimental kernel hmpc_param_eval_v2_f64: registers 0..P-1 are the
+        """(instructions, n_regs) for the kernel hmpc_param_eval_v2_f64: registers 0..P-1 are the
         parameters (preloaded, never written), no PARAM instructions; same operations in the same order otherwise."""
         if self._v2 is None:
             ins, n_regs = self._compile(preload_params=True)
@@ -327,12 +327,15 @@ class ExprProgram(object):
 
     def evaluate(self, params, version=None):
         """params: CUDA float64 tensor [B, P] -> dict name -> CUDA tensor [B, rows, cols] (views of one buffer).
-        version: 1 = hmpc_param_eval_f64 (default); 2 = the experimental kernel (also HMPC_PARAM_EVAL=v2)."""
+        version: 2 = hmpc_param_eval_v2_f64 (default); 1 = hmpc_param_eval_f64 (also HMPC_PARAM_EVAL=v1)."""
         from .. import cabi
         if params.dim() != 2 or params.shape[1] != len(self.param_names):
             raise ValueError("params must be [B, %d]" % len(self.param_names))
         if version is None:
-            version = 2 if os.environ.get("HMPC_PARAM_EVAL", "v1").lower() in ("v2", "2") else 1
+            # v2 (parameters preloaded as registers, two agents per thread) is the default since round 2: bit-identical
+            # results on the golden fixtures and the fuzz programs, 11-15 % faster at 2 M agents on a B200
+            # (profiles/r2_notes.md); HMPC_PARAM_EVAL=v1 selects the first kernel
+            version = 1 if os.environ.get("HMPC_PARAM_EVAL", "v2").lower() in ("v1", "1") else 2
         if int(version) == 1:
             flat = cabi.param_eval(self._program_on(params.device), self.n_regs, self.mat_sizes, params)
         else:

@@ -301,9 +301,7 @@ def test_controller_on_a_symbolic_model_and_batch_from_front_end(cuda_device):
     assert abs(obj_new - objs[0]) > 1e-6 * max(1.0, abs(objs[0]))          # (the change is visible in the objective)
 
 
-@pytest.mark.skipif(__import__("os").environ.get("HMPC_EXPERIMENTAL", "0") != "1",
-                    reason="experimental kernel hmpc_param_eval_v2_f64: opt-in (HMPC_EXPERIMENTAL=1), not yet run on a B200")
-def test_experimental_kernel_v2_matches_v1(cuda_device):
+def test_kernel_v2_matches_v1(cuda_device):
     """parameters preloaded as registers + two agents per thread: bit-identical to the first kernel (same operations,
     same order, same math functions), on the golden fixtures, ragged tiles and the fuzz programs"""
     import torch
