@@ -180,7 +180,8 @@ int  hmpc_miqp_solve_f64(int32_t B, int32_t n, int32_t m, const double* P, int64
 typedef struct {
     double  mip_rel_gap;   /* 0 = prove optimality                                     */
     double  feas_tol;      /* tolerance of hard (slack-free) rows, default 1e-9        */
-    int32_t cells;         /* value-table cells per stage, default 8192                */
+    int32_t cells;         /* value-table cells per stage, default 4096 (the optimum does not depend on it: fewer
+                              cells = a shorter sweep and a few more search expansions)                          */
     int32_t max_nodes;     /* search nodes per agent, default 4,000,000                */
     int32_t table_fp64;    /* 1 (default): FP64 value table -- sequences that TIE with the incumbent (piecewise-constant
                               tariffs) are pruned at mip_rel_gap = 0;  0: FP32 table rounded down -- half the

@@ -86,13 +86,12 @@ class BatchMpc(object):
         if solver not in ("auto", "bnc", "stage_dp"):
             raise ValueError("solver must be 'auto', 'bnc' or 'stage_dp'")
         self.solver = solver
-        # table resolution: 8192 cells per stage keep the search at its minimum (the first dive is optimal) when the
-        # batch is small and the step time is the slowest agent's latency; with many agents per SM the sweep is what
-        # costs, and 4096 cells give the same optimum with ~6 % more search expansions at half the sweep
+        # table resolution: the optimum does not depend on it; since the grid follows the violation-free band stage by
+        # stage (round 2) 4096 cells resolve what 8192 cells of one global window did, at two thirds of the sweep time
         if dp_bound not in ("constant", "linear"):
             raise ValueError("dp_bound must be 'constant' or 'linear'")
         if dp_opts is None:
-            dp_opts = cabi.stage_dp_default_opts(cells=8192 if self.B <= 2 * 148 else 4096)
+            dp_opts = cabi.stage_dp_default_opts()
             if dp_bound == "linear":
                 dp_opts.bound = cabi.DP_BOUND_LINEAR
             if cabi.stage_dp_supported(d):       # the two stage buffers must fit shared memory in this format

@@ -15,6 +15,7 @@ N_p = 96 take it minutes); an instance it does not finish is compared through it
 proven, can only be better or equal), and is counted."""
 import multiprocessing as mp
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -25,20 +26,11 @@ pytestmark = pytest.mark.gpu
 SAMPLE = 32
 
 
-def _highs_job(job):
-    from oracle import mld as omld, condense as oc, assemble as oa, solve as osv
-    mats, Nt, x0, omega, q_u, q_mu, scen, extra = job
-    full, d, vt = omld.complete(mats, nu_l=1)
-    prob = oa.build_problem(oc.condense(full, d, Nt), d, vt, Nt, x0, omega, atoms=dict(q_u=q_u, q_mu=q_mu),
-                            omega_scenarios=scen, extra_constraints=extra)
-    st, obj, v = osv.solve_milp(prob, polish=True, time_limit=30.0)
-    u = None if v is None else np.round(np.asarray(v)[prob.is_bin])
-    return st, obj, u
-
-
 def _highs_many(jobs):
-    with mp.get_context("fork").Pool(min(len(jobs), os.cpu_count() or 1)) as pool:
-        return pool.map(_highs_job, jobs, chunksize=1)
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from highs_worker import highs_job
+    with mp.get_context("spawn").Pool(min(len(jobs), os.cpu_count() or 1)) as pool:
+        return pool.map(highs_job, jobs, chunksize=1)
 
 
 def _check_sample(tag, res_obj, res_u, res_status, jobs, idx):
