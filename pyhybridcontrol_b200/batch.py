@@ -23,14 +23,15 @@ def _dev_tensor(a, device, dtype=torch.float64):
 
 class BatchMpc(object):
     def __init__(self, mats, N_p, N_tilde=None, nu_l=0, nmu_l=0, B=None, device="cuda", opts=None, solver="auto",
-                 dp_opts=None, dp_bound="constant"):
+                 dp_opts=None, dp_bound="auto"):
         """mats: name -> array [B|1, r, c] (or [r, c]); missing blocks are zero, C defaults to I (nx == ny).
 
         solver: "auto" -- the exact stage-DP kernels (csrc/stage_dp.cu) when the MLD is in their class (scalar
         state, binary inputs, one slack per row: every DEWH of the reference example), else the general
         branch-and-cut kernel (csrc/milp_bnc.cu); "bnc" / "stage_dp" force one of them.
-        dp_bound: "constant" (one value per table cell) or "linear" (a line per cell: the bound to use when slack
-        penalties are active along the whole trajectory -- full-horizon robust constraint sets)."""
+        dp_bound: "constant" (one value per table cell), "linear" (a line per cell: the bound to use when slack
+        penalties are active along the whole trajectory -- full-horizon robust constraint sets) or "auto" (default:
+        linear for a solve whose constraint sets carry scenarios over more than half of the horizon, else constant)."""
         self.device = torch.device(device)
         self.N_p = int(N_p)
         self.Nt = int(N_tilde) if N_tilde is not None else self.N_p + 1
@@ -88,14 +89,17 @@ class BatchMpc(object):
         self.solver = solver
         # table resolution: the optimum does not depend on it; since the grid follows the violation-free band stage by
         # stage (round 2) 4096 cells resolve what 8192 cells of one global window did, at two thirds of the sweep time
-        if dp_bound not in ("constant", "linear"):
-            raise ValueError("dp_bound must be 'constant' or 'linear'")
+        if dp_bound not in ("constant", "linear", "auto"):
+            raise ValueError("dp_bound must be 'constant', 'linear' or 'auto'")
+        self.dp_bound = dp_bound
         if dp_opts is None:
             dp_opts = cabi.stage_dp_default_opts()
             if dp_bound == "linear":
                 dp_opts.bound = cabi.DP_BOUND_LINEAR
             if cabi.stage_dp_supported(d):       # the two stage buffers must fit shared memory in this format
                 dp_opts.cells = min(dp_opts.cells, cabi.stage_dp_max_cells(d, dp_opts))
+        else:
+            self.dp_bound = "linear" if dp_opts.bound == cabi.DP_BOUND_LINEAR else "constant"
         self.dp_opts = dp_opts
         self.stage_dp_ok = self._stage_dp_class()
         if solver == "stage_dp" and not self.stage_dp_ok:
@@ -104,6 +108,17 @@ class BatchMpc(object):
         self.evo = None
         self._lb_dev = self._ub_dev = self._bin_dev = None
         self.disable_soft_constraints = False
+
+    def _dp_opts_for(self, robust):
+        """the stage-DP options of one solve: under dp_bound="auto" a robust solve (scenario sets over most of the
+        horizon) gets linear cells, with the cell count its stage buffers allow"""
+        if self.dp_bound != "auto" or not robust or self.dims.nc != 2 or self.dims.nu + self.dims.ndelta != 1:
+            return self.dp_opts
+        o = cabi.stage_dp_default_opts(bound=cabi.DP_BOUND_LINEAR, mip_rel_gap=self.dp_opts.mip_rel_gap,
+                                       max_nodes=self.dp_opts.max_nodes, feas_tol=self.dp_opts.feas_tol,
+                                       fuse_search=self.dp_opts.fuse_search)
+        o.cells = min(self.dp_opts.cells, cabi.stage_dp_max_cells(self.dims, o))
+        return o
 
     def _stage_dp_class(self):
         """One-time host check that every agent of the batch is in the class of hmpc_stage_dp_solve_f64."""
@@ -263,6 +278,10 @@ class BatchMpc(object):
             c, c0 = self.linear_cost(cost_v, w_x, w_y, x0, omega)
         Hs, rs = [], []
         use_dp = self.solver == "stage_dp" or (self.solver == "auto" and self.stage_dp_ok)
+        robust = scenarios is not None and with_std_constraints
+        for ec in extra_constraints:
+            if ec.get("omega_scenarios_k") is not None and (ec.get("N_tilde") is None or 2 * int(ec["N_tilde"]) > self.Nt):
+                robust = True
         if rhs is not None:
             if not use_dp or quad:
                 raise NotImplementedError("a cached right-hand side is taken on the stage-DP MILP path only")
@@ -299,8 +318,8 @@ class BatchMpc(object):
                 rhs[:, :r.shape[1]] = torch.minimum(rhs[:, :r.shape[1]], r)
             if len(rs) == 1 and rs[0].shape[1] == self.mrows:
                 rhs = rs[0]
-            v, obj, status, stats = cabi.stage_dp_solve(d, self.mats, rhs, c.contiguous(), lb, ub, isb, self.dp_opts,
-                                                        terms=terms)
+            v, obj, status, stats = cabi.stage_dp_solve(d, self.mats, rhs, c.contiguous(), lb, ub, isb,
+                                                        self._dp_opts_for(robust and terms is None), terms=terms)
             return dict(v=v, obj=obj + c0, status=status, stats=stats, c0=c0, solver="stage_dp", rhs=rhs)
         if len(Hs) == 1 and Hs[0].shape[1] == self.mrows:
             H, rhs = self.evo["H_v"], rs[0]

@@ -81,7 +81,8 @@ def test_stage_dp_terms_reproduce_the_reference_objective():
         assert abs(val - f) <= 1e-10 * max(1.0, abs(f)), (val, f)
 
 
-def test_atoms_outside_the_stage_dp_class_are_refused():
+def test_atoms_outside_the_stage_dp_class_take_the_general_path():
+    """which atoms of the reference's all-atom fixture leave the exact fast paths for the general MIQP assembly"""
     g, prob, evo, dims, Nt = _load("dewh_N6_all_atoms")
     mats = {k: g["in_" + k] for k in MAT_NAMES if g["in_" + k].size}
     mld = MldModel(nu_l=1, **mats)
@@ -89,14 +90,15 @@ def test_atoms_outside_the_stage_dp_class_are_refused():
     oas = ObjectiveAtoms(mld.mld_info, int(g["N_p"]), Nt, None, **atoms)
     batch = types.SimpleNamespace(stage_dp_ok=True)
     ctrl = types.SimpleNamespace(_mld_evo_matrices=types.SimpleNamespace(batch=batch), _sense="minimize")
-    refused = []
-    for atom in oas.iter_atoms():
-        try:
-            MpcController._check_atom(ctrl, atom)
-        except NotImplementedError:
-            refused.append((atom.atom_type, atom.var_name, atom.is_rate_atom))
-    assert ("L1", "u", True) in refused and any(a[0] == "Linf" for a in refused)
-    assert not any(a[0] == "Linear" for a in refused)
+    general = [(atom.atom_type, atom.var_name, atom.is_rate_atom) for atom in oas.iter_atoms()
+               if MpcController._needs_general_path(ctrl, atom)]
+    assert ("L1", "u", True) in general and any(a[0] == "Linf" for a in general)
+    assert not any(a[0] == "Linear" for a in general)
+    # maximising a convex atom is refused outright
+    ctrl._sense = "maximize"
+    with pytest.raises(NotImplementedError):
+        for atom in oas.iter_atoms():
+            MpcController._needs_general_path(ctrl, atom)
 
 
 def test_update_std_obj_atoms_sequence():
