@@ -80,7 +80,10 @@ __device__ inline void small_mm(double* C, const double* A, const double* B, int
 
 // Writes rows [row_lo, row_hi) of a dense block-Toeplitz output:
 //   block(i, j) = lag[i-j-1] (i > j), diag (i == j, may be null -> 0), 0 (i < j); value is multiplied by sgn.
-// rb x cb is the block shape, ncol = cb * Nt.  Thread <-> column so that a warp stores 256 contiguous bytes.
+// rb x cb is the block shape, ncol = cb * Nt.  Thread <-> column and all lanes walk the rows in lockstep, so that a
+// warp stores 256 contiguous bytes per row.  Down a column (j, cj) the source is linear in the row -- zeros above row
+// j*rb, then the rb rows of the diagonal block, then lag[(row - (j+1) rb) * cb + cj] -- so a thread keeps one running
+// pointer per source and an element costs two compares, a predicated shared-memory load and the store.
 __device__ inline void write_toeplitz(double* __restrict__ out, const double* __restrict__ lag,
                                       const double* __restrict__ diag, int rb, int cb, int Nt, double sgn,
                                       int row_lo, int row_hi) {
@@ -88,15 +91,16 @@ __device__ inline void write_toeplitz(double* __restrict__ out, const double* __
     if (ncol == 0 || rb == 0) return;
     for (int col = threadIdx.x; col < ncol; col += blockDim.x) {
         const int j = col / cb, cj = col - j * cb;
-        int i = row_lo / rb, ri = row_lo - i * rb;
+        const int r_diag = j * rb, r_lag = r_diag + rb;             // first row of the diagonal block / of the lags
         double* p = out + (int64_t)row_lo * ncol + col;
-        for (int row = row_lo; row < row_hi; ++row) {
+        const double* lp = lag + (int64_t)(row_lo - r_lag) * cb + cj;
+        const double* dp = diag ? diag + (int64_t)(row_lo - r_diag) * cb + cj : nullptr;
+#pragma unroll 4
+        for (int row = row_lo; row < row_hi; ++row, p += ncol, lp += cb, dp += cb) {
             double v = 0.0;
-            if (i > j) v = sgn * lag[((i - j - 1) * rb + ri) * cb + cj];
-            else if (i == j && diag) v = sgn * diag[ri * cb + cj];
+            if (row >= r_lag) v = sgn * lp[0];
+            else if (row >= r_diag && diag) v = sgn * dp[0];
             *p = v;
-            p += ncol;
-            if (++ri == rb) { ri = 0; ++i; }
         }
     }
 }
