@@ -362,7 +362,13 @@ def main_ours(args):
         T1, cons = fleet.sim_step(inp["x0"][:, 0].contiguous(), u[:, 0].contiguous(), inp["omega"][:, 0].contiguous())
         if ev:
             ev[4].record()
-        p_agg = cabi.aggregate_power(u, fleet.P_nom)          # this rank's agents; ranks are summed by exchange()
+        if peer_ex is not None:
+            # K6 with the exchange fused in: the reduction's last pass stores this rank's sums into every rank's window
+            # over NVLink; the gather adds the world's contributions of the PREVIOUS step (pipelined: no rank waits)
+            peer_ex.publish(u, fleet.P_nom, out_prev=p_total_prev)
+            p_agg = p_total_prev
+        else:
+            p_agg = cabi.aggregate_power(u, fleet.P_nom)      # this rank's agents; ranks are summed by exchange()
         if ev:
             ev[5].record()
         return v, obj, status, stats, T1, p_agg
@@ -370,14 +376,32 @@ def main_ours(args):
     # K6 across ranks: NCCL all-reduce of the [Nt] aggregate power.  Nothing in the NEXT control step depends on it
     # (the agents are decentralised; the sum goes to the grid agent), so it runs on a side stream, pipelined with the
     # following steps through a small ring of buffers, and is joined before the timed region ends.
+    peer_ex, peer_note = None, "single GPU: no exchange"
+    p_total_prev = torch.zeros(Nt, dtype=torch.float64, device=dev)
+    if world > 1 and not os.environ.get("HMPC_NCCL_EXCHANGE"):
+        try:
+            from pyhybridcontrol_b200.distributed import PeerExchange
+            peer_ex = PeerExchange(Nt, dev)
+            peer_note = ("peer-store exchange inside the step's CUDA graph (symmetric memory over NVLink; publish fused "
+                         "into the reduction's last pass, gather of the previous step): no host call per step")
+        except Exception as exc:
+            peer_ex = None
+            peer_note = "NCCL all-reduce on a side stream (symmetric memory unavailable: %r)" % (exc,)
+    elif world > 1:
+        peer_note = "NCCL all-reduce on a side stream, pipelined with the next steps (HMPC_NCCL_EXCHANGE)"
+    ok_all = torch.tensor([1.0 if (peer_ex is not None or world == 1) else 0.0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ok_all, op=dist.ReduceOp.MIN)          # every rank must take the same path
+        if float(ok_all.item()) < 1.0:
+            peer_ex = None
     xstream = torch.cuda.Stream() if world > 1 else None
     ring = [torch.empty(Nt, dtype=torch.float64, device=dev) for _ in range(4)]
     ring_ev = [None] * 4
     ring_evobj = [torch.cuda.Event() for _ in range(4)]
 
     def exchange(p_agg, s):
-        if world == 1 or os.environ.get("HMPC_NO_EXCHANGE"):      # (debug switch: isolate the cost of the exchange)
-            return p_agg
+        if world == 1 or peer_ex is not None or os.environ.get("HMPC_NO_EXCHANGE"):
+            return p_agg                              # (the peer-store exchange is part of the step itself)
         main = torch.cuda.current_stream()
         buf = ring[s % 4]
         if ring_ev[s % 4] is not None:
@@ -509,12 +533,17 @@ def main_ours(args):
             solve_stats.append(out[3].clone())
     t_host_loop = time.perf_counter() - t_wall0
     join_exchange()
+    if peer_ex is not None:
+        peer_ex.gather(out=p_total_prev, lag=0)          # the last step's sum (the loop gathered the previous ones)
     ev_end.record()
     barrier()
     t_wall = time.perf_counter() - t_wall0
     sampler.stop_flag = True
     note("timed region done")
-    launches_per_step = (1 if args.recondense else 0) + 1 + (2 if use_dp else 1) + 1 + 2      # [K1], K2, K3/K4, K5, K6 (two passes)
+    if peer_ex is not None:
+        assert peer_ex.error() == 0, "peer exchange: a rank never published step %d" % peer_ex.error()
+        assert bool(torch.isfinite(p_total_prev).all())
+    launches_per_step = (1 if args.recondense else 0) + 1 + (2 if use_dp else 1) + 1 + 2  # [K1], K2, K3/K4, K5, K6 (two launches)
     launches = launches_per_step * K if graph is not None else cabi.launch_count - launches0
     if graph is not None:
         step_ms = [e[0].elapsed_time(e[1]) - flush_one_ms for e in evs.values()]
@@ -634,7 +663,8 @@ def main_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
-        "run_config": dict(solver="stage_dp" if use_dp else "bnc",
+        "run_config": dict(solver="stage_dp" if use_dp else "bnc", exchange=peer_note if peer_ex is not None or world == 1 else
+                           (peer_note if "NCCL" in peer_note else "NCCL all-reduce on a side stream (a rank could not map the peers' windows)"),
                        K1="inside every step (--recondense)" if args.recondense else
                           "once, before the timed region: the models do not change (reference: mld_evolution_matrices.py:79); "
                           "ms_per_step_with_recondense adds the measured K1 launch",

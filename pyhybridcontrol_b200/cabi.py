@@ -24,7 +24,8 @@ EXPORTS = ("hmpc_version", "hmpc_last_cuda_error", "hmpc_device_info", "hmpc_con
            "hmpc_stage_dp_supported", "hmpc_stage_dp_workspace_bytes", "hmpc_stage_dp_max_cells", "hmpc_stage_dp_solve_f64", "hmpc_lsim_step_f64",
            "hmpc_dewh_sim_step_f64", "hmpc_dewh_control_model_f64", "hmpc_dewh_thermostat_f64",
            "hmpc_param_eval_f64", "hmpc_param_eval_v2_f64", "hmpc_param_eval_bytes_per_agent",
-           "hmpc_aggregate_power_f64", "hmpc_coupling_price_cost_f64", "hmpc_coupling_sums_f64",
+           "hmpc_aggregate_power_f64", "hmpc_aggregate_window_doubles", "hmpc_aggregate_publish_f64",
+           "hmpc_aggregate_gather_f64", "hmpc_coupling_price_cost_f64", "hmpc_coupling_sums_f64",
            "hmpc_coupling_dual_step_f64", "hmpc_coupling_keep_best_f64", "hmpc_coupling_response_cost_f64",
            "hmpc_coupling_merge_f64", "hmpc_coupling_accept_f64", "hmpc_coupling_restore_f64", "hmpc_step_plan_create", "hmpc_step_plan_destroy", "hmpc_mpc_step_host_f64", "hmpc_mpc_step_host_bytes",
            "hmpc_step_plan_last_solver",
@@ -623,6 +624,39 @@ def aggregate_power(u, P_nom=None):
     _check(_lib.hmpc_aggregate_power_f64(B, Nt, C.c_void_p(u.data_ptr()), u.stride(0), u.stride(1), _ptr(P_nom),
                                          _ptr(partial), _ptr(out), _stream()), "hmpc_aggregate_power_f64")
     launch_count += 2
+    return out
+
+
+_lib.hmpc_aggregate_window_doubles.argtypes = [C.c_int32, C.c_int32]
+_lib.hmpc_aggregate_window_doubles.restype = C.c_int64
+
+
+def aggregate_window_doubles(Nt, world):
+    return int(_lib.hmpc_aggregate_window_doubles(int(Nt), int(world)))
+
+
+def aggregate_publish(u, P_nom, world, rank, windows_dev, out_prev=None):
+    """K6 local reduction + publication into every rank's exchange window (windows_dev: int64 CUDA tensor of `world`
+    device pointers)."""
+    global launch_count
+    B, Nt = u.shape
+    chunks = max(1, (B + 15) // 16)
+    partial = torch.empty((chunks, Nt), dtype=torch.float64, device=u.device)
+    _check(_lib.hmpc_aggregate_publish_f64(B, Nt, C.c_void_p(u.data_ptr()), C.c_int64(u.stride(0)), C.c_int32(u.stride(1)),
+                                           _ptr(P_nom), _ptr(partial), C.c_int32(world), C.c_int32(rank),
+                                           C.c_void_p(windows_dev.data_ptr()), _ptr(out_prev), _stream()),
+           "hmpc_aggregate_publish_f64")
+    launch_count += 2
+    return partial
+
+
+def aggregate_gather(Nt, world, rank, window, out=None, spin_limit=0, lag=0):
+    global launch_count
+    out = out if out is not None else torch.empty((Nt,), dtype=torch.float64, device=window.device)
+    _check(_lib.hmpc_aggregate_gather_f64(C.c_int32(Nt), C.c_int32(world), C.c_int32(rank), C.c_void_p(window.data_ptr()),
+                                          _ptr(out), C.c_int64(spin_limit), C.c_int32(lag), _stream()),
+           "hmpc_aggregate_gather_f64")
+    launch_count += 1
     return out
 
 

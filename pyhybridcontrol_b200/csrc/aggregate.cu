@@ -46,6 +46,95 @@ __global__ void __launch_bounds__(128) aggregate_final_kernel(int chunks, int Nt
     out[k] = acc;
 }
 
+// ---- K6 across the GPUs of one box without a collective library.  Every rank owns an exchange WINDOW in memory its peers
+// can address (torch symmetric memory: NVLink peer mappings); the last pass of the local reduction writes this rank's
+// [Nt] sums straight into the window of EVERY rank (plain stores to peer memory, 392 B per peer at N_p = 48), fences,
+// and raises that step's flag in each of them.  The gather kernel of a rank waits for the world's flags of its own
+// latest step (bounded spin on local memory) and adds the contributions in rank order (bit-reproducible).  Both are
+// ordinary kernels on the step's stream: they sit inside the step's CUDA graph, no host call per step.
+// Window (doubles unless noted): [0] step counter of the owner (u64), [1] error word (u64), [2 .. 2 + RING*W) flags
+// (u64, [slot][rank]), then data [slot][rank][Nt].
+constexpr int kXRing = 4;
+__host__ __device__ inline int64_t xwin_flags(int slot, int world, int r) { return 2 + (int64_t)slot * world + r; }
+__host__ __device__ inline int64_t xwin_data(int slot, int world, int r, int Nt) {
+    return 2 + (int64_t)kXRing * world + ((int64_t)slot * world + r) * Nt;
+}
+
+__global__ void __launch_bounds__(128) aggregate_publish_kernel(int chunks, int Nt, const double* __restrict__ partial,
+                                                                int world, int rank, double* const* __restrict__ windows,
+                                                                double* __restrict__ out_prev, long long spin_limit) {
+    unsigned long long* mine = reinterpret_cast<unsigned long long*>(windows[rank]);
+    const unsigned long long seq = mine[0] + 1ull;
+    const int slot = (int)(seq % kXRing);
+    for (int k = threadIdx.x; k < Nt; k += blockDim.x) {
+        double acc = 0.0;
+        for (int c = 0; c < chunks; ++c) acc += partial[(int64_t)c * Nt + k];          // chunk order: deterministic
+        for (int r = 0; r < world; ++r) windows[r][xwin_data(slot, world, rank, Nt) + k] = acc;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < world) {
+        unsigned long long* flag = reinterpret_cast<unsigned long long*>(windows[threadIdx.x]) + xwin_flags(slot, world, rank);
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(seq) : "memory");
+    }
+    if (threadIdx.x == 0) mine[0] = seq;
+    // the same launch gathers the PREVIOUS step (pipelined loops: the peers' contributions of step seq - 1 arrived long
+    // ago, nobody waits) -- one launch less per control step
+    if (out_prev) {
+        if (seq <= 1ull) { for (int k = threadIdx.x; k < Nt; k += blockDim.x) out_prev[k] = 0.0; return; }
+        const unsigned long long want = seq - 1ull;
+        const int pslot = (int)(want % kXRing);
+        __shared__ int s_bad;
+        if (threadIdx.x == 0) s_bad = 0;
+        __syncthreads();
+        if (threadIdx.x < world) {
+            const unsigned long long* flag = mine + xwin_flags(pslot, world, threadIdx.x);
+            unsigned long long seen = 0;
+            long long n = 0;
+            do {
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(flag) : "memory");
+            } while (seen < want && ++n < spin_limit);
+            if (seen < want) { s_bad = 1; mine[1] = want; }
+        }
+        __syncthreads();
+        const double* win = windows[rank];
+        for (int k = threadIdx.x; k < Nt; k += blockDim.x) {
+            double acc = 0.0;
+            for (int r = 0; r < world; ++r) acc += win[xwin_data(pslot, world, r, Nt) + k];
+            out_prev[k] = s_bad ? nan("") : acc;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) aggregate_gather_kernel(int Nt, int world, int rank, double* __restrict__ window,
+                                                               double* __restrict__ out, long long spin_limit, int lag) {
+    unsigned long long* mine = reinterpret_cast<unsigned long long*>(window);
+    if (mine[0] <= (unsigned long long)lag) {                 // nothing that old has been published yet
+        for (int k = threadIdx.x; k < Nt; k += blockDim.x) out[k] = 0.0;
+        return;
+    }
+    const unsigned long long seq = mine[0] - (unsigned long long)lag;
+    const int slot = (int)(seq % kXRing);
+    __shared__ int s_bad;
+    if (threadIdx.x == 0) s_bad = 0;
+    __syncthreads();
+    if (threadIdx.x < world) {
+        const unsigned long long* flag = mine + xwin_flags(slot, world, threadIdx.x);
+        unsigned long long seen = 0;
+        long long n = 0;
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(flag) : "memory");
+        } while (seen < seq && ++n < spin_limit);
+        if (seen < seq) { s_bad = 1; mine[1] = seq; }         // a peer never arrived: report instead of hanging
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < Nt; k += blockDim.x) {
+        double acc = 0.0;
+        for (int r = 0; r < world; ++r) acc += window[xwin_data(slot, world, r, Nt) + k];
+        out[k] = s_bad ? nan("") : acc;
+    }
+}
+
 // FP64 FMA peak probe: 8 independent dependency chains per thread, 4096 FMAs each.
 __global__ void __launch_bounds__(256) fp64_peak_kernel(double* sink, int iters) {
     double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
@@ -73,6 +162,37 @@ extern "C" int hmpc_aggregate_power_f64(int32_t B, int32_t Nt, const double* u, 
     }
     aggregate_final_kernel<<<ceil_div(Nt, 128), 128, 0, (cudaStream_t)stream>>>(chunks, Nt, partial, P_agg);
     HMPC_LAUNCH_CHECK("aggregate_final_kernel");
+    return HMPC_OK;
+}
+
+extern "C" int64_t hmpc_aggregate_window_doubles(int32_t Nt, int32_t world) {
+    return hmpc::xwin_data(hmpc::kXRing, world, 0, Nt);
+}
+
+extern "C" int hmpc_aggregate_publish_f64(int32_t B, int32_t Nt, const double* u, int64_t u_stride_b,
+                                          int32_t u_stride_k, const double* P_nom, double* partial, int32_t world,
+                                          int32_t rank, double* const* windows, void* stream) {
+    using namespace hmpc;
+    if (B < 0 || Nt < 1 || !u || !partial || !windows || world < 1 || world > 128 || rank < 0 || rank >= world) return HMPC_ERR_ARG;
+    const int chunks = B > 0 ? ceil_div(B, kAggChunk) : 0;
+    if (chunks) {
+        aggregate_partial_kernel<<<chunks, 128, 0, (cudaStream_t)stream>>>(B, Nt, u, u_stride_b, u_stride_k, P_nom,
+                                                                           partial);
+        HMPC_LAUNCH_CHECK("aggregate_partial_kernel");
+    }
+    aggregate_publish_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(chunks, Nt, partial, world, rank, windows, P_total_prev,
+                                                                  400000000ll);
+    HMPC_LAUNCH_CHECK("aggregate_publish_kernel");
+    return HMPC_OK;
+}
+
+extern "C" int hmpc_aggregate_gather_f64(int32_t Nt, int32_t world, int32_t rank, double* window, double* P_total,
+                                         int64_t spin_limit, int32_t lag, void* stream) {
+    using namespace hmpc;
+    if (Nt < 1 || !window || !P_total || world < 1 || world > 128 || rank < 0 || rank >= world || lag < 0 || lag > 2) return HMPC_ERR_ARG;
+    aggregate_gather_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(Nt, world, rank, window, P_total,
+                                                                 spin_limit > 0 ? spin_limit : 400000000ll, lag);
+    HMPC_LAUNCH_CHECK("aggregate_gather_kernel");
     return HMPC_OK;
 }
 

@@ -44,6 +44,57 @@ def response_blocks(num_local, groups):
     return [shard_range(num_local, g, groups) for g in range(int(groups))]
 
 
+class PeerExchange(object):
+    """The per-step exchange of the [Nt] aggregate power WITHOUT a collective call: every rank owns a window in
+    symmetric memory (peer-mapped over NVLink), `publish` is the last pass of the local reduction storing this rank's
+    sums into every rank's window, `gather` adds the world's contributions in rank order (csrc/aggregate.cu).  Both are
+    ordinary kernels on the current stream, so the whole control step -- exchange included -- is one CUDA graph and the
+    host issues nothing per step (the NCCL all-reduce cannot be captured on this stack: tools/gpu_nccl_graph_probe.py).
+    `windows` lets a test emulate several ranks on one GPU."""
+
+    def __init__(self, Nt, device, world=None, rank=None, windows=None):
+        from . import cabi
+        self.Nt = int(Nt)
+        self.world = int(world) if world is not None else (dist.get_world_size() if is_distributed() else 1)
+        self.rank = int(rank) if rank is not None else (dist.get_rank() if is_distributed() else 0)
+        n = cabi.aggregate_window_doubles(self.Nt, self.world)
+        if windows is not None:                         # emulation: all windows live on this device
+            self.window = windows[self.rank]
+            ptrs = [w.data_ptr() for w in windows]
+        elif self.world > 1:
+            import torch.distributed._symmetric_memory as symm
+            self.window = symm.empty(n, dtype=torch.float64, device=device)
+            self.window.zero_()
+            self._hdl = symm.rendezvous(self.window, dist.group.WORLD)
+            ptrs = [int(p) for p in self._hdl.buffer_ptrs]
+            torch.cuda.synchronize()
+            dist.barrier()
+        else:
+            self.window = torch.zeros(n, dtype=torch.float64, device=device)
+            ptrs = [self.window.data_ptr()]
+        self.windows_dev = torch.tensor(ptrs, dtype=torch.int64, device=device)
+
+    @staticmethod
+    def new_window(Nt, world, device):
+        from . import cabi
+        return torch.zeros(cabi.aggregate_window_doubles(Nt, world), dtype=torch.float64, device=device)
+
+    def publish(self, u, P_nom, out_prev=None):
+        """out_prev [Nt]: the same launch also writes the world's sum of the PREVIOUS step there (gather with lag 1)"""
+        from . import cabi
+        self._partial = cabi.aggregate_publish(u, P_nom, self.world, self.rank, self.windows_dev, out_prev=out_prev)
+
+    def gather(self, out=None, spin_limit=0, lag=0):
+        """sum over the ranks of the step published `lag` steps ago (0 = the latest; zeros while nothing that old
+        exists).  A pipelined loop uses lag = 1: the peers' contributions of the previous step have long arrived."""
+        from . import cabi
+        return cabi.aggregate_gather(self.Nt, self.world, self.rank, self.window, out=out, spin_limit=spin_limit, lag=lag)
+
+    def error(self):
+        """step number at which a peer never arrived (0 = none)"""
+        return int(self.window[:2].view(torch.int64)[1].item())
+
+
 def allgather_trajectories(traj_local, counts=None):
     """[B_local, Nt] per rank -> [B_total, Nt] on every rank, rank-major (the order the reference stacks devices)."""
     if not is_distributed():

@@ -317,3 +317,47 @@ def test_host_front_door_matches_device_path(solver, cuda_device):
 def test_smoke_entry(cuda_device):
     import __graft_entry__
     __graft_entry__.smoke()
+
+
+def test_peer_store_aggregate_exchange_emulated(cuda_device):
+    """K6 without a collective: publish / gather kernels of csrc/aggregate.cu with TWO (and three) ranks emulated on
+    one GPU -- all windows on this device, the ranks' publishes issued one after the other, so that every flag is up
+    before a gather looks at it.  Sums equal numpy's in rank order, step after step (the ring of four slots wraps);
+    a missing peer gives NaN and the error word, not a hang."""
+    import torch
+    from pyhybridcontrol_b200.distributed import PeerExchange
+    rng = np.random.default_rng(3)
+    Nt = 49
+    for world in (1, 2, 3):
+        wins = [PeerExchange.new_window(Nt, world, cuda_device) for _ in range(world)]
+        ex = [PeerExchange(Nt, cuda_device, world=world, rank=r, windows=wins) for r in range(world)]
+        Bs = [37, 100, 5][:world]
+        P = [torch.as_tensor(rng.uniform(2700, 3300, b)).to(cuda_device) for b in Bs]
+        for step in range(9):
+            us = [torch.as_tensor((rng.random((b, Nt)) > 0.5).astype(float)).to(cuda_device) for b in Bs]
+            prevs = [torch.empty(Nt, dtype=torch.float64, device=cuda_device) for _ in range(world)]
+            for r in range(world):
+                ex[r].publish(us[r], P[r], out_prev=prevs[r] if step % 2 else None)
+            ref = np.zeros(Nt)
+            for r in range(world):          # rank order, chunks of 16 agents in order: the kernel's summation order
+                loc = np.zeros(Nt)
+                un, pn = us[r].cpu().numpy(), P[r].cpu().numpy()
+                for c0 in range(0, Bs[r], 16):
+                    acc = np.zeros(Nt)
+                    for b in range(c0, min(c0 + 16, Bs[r])):
+                        acc = acc + pn[b] * un[b]
+                    loc = loc + acc
+                ref = ref + loc
+            for r in range(world):
+                got = ex[r].gather().cpu().numpy()
+                assert np.array_equal(got, ref), (world, step, r)
+                assert ex[r].error() == 0
+                if step % 2 and r == 0:     # (rank 0 publishes first: every peer's previous step was complete by then)
+                    assert np.array_equal(prevs[r].cpu().numpy(), last_ref), (world, step)
+            last_ref = ref
+    # a peer that never publishes: bounded wait, NaN result, error word = the step that was waited for
+    wins = [PeerExchange.new_window(Nt, 2, cuda_device) for _ in range(2)]
+    ex0 = PeerExchange(Nt, cuda_device, world=2, rank=0, windows=wins)
+    ex0.publish(torch.ones((4, Nt), dtype=torch.float64, device=cuda_device), torch.ones(4, dtype=torch.float64, device=cuda_device))
+    out = ex0.gather(spin_limit=1000).cpu().numpy()
+    assert np.isnan(out).all() and ex0.error() == 1
