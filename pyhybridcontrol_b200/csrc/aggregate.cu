@@ -171,7 +171,7 @@ extern "C" int64_t hmpc_aggregate_window_doubles(int32_t Nt, int32_t world) {
 
 extern "C" int hmpc_aggregate_publish_f64(int32_t B, int32_t Nt, const double* u, int64_t u_stride_b,
                                           int32_t u_stride_k, const double* P_nom, double* partial, int32_t world,
-                                          int32_t rank, double* const* windows, void* stream) {
+                                          int32_t rank, double* const* windows, double* P_total_prev, void* stream) {
     using namespace hmpc;
     if (B < 0 || Nt < 1 || !u || !partial || !windows || world < 1 || world > 128 || rank < 0 || rank >= world) return HMPC_ERR_ARG;
     const int chunks = B > 0 ? ceil_div(B, kAggChunk) : 0;
