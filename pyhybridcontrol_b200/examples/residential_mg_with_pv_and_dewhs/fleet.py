@@ -167,6 +167,61 @@ class DewhFleet(object):
                    iterations=int(st[5]), skipped=int(st[7]), u=best_plan["u"], plan=best_plan)
         return out
 
+    def coupled_step_exact(self, x0, omega_forecast, price, p_other, grid_limits=None, mip_rel_gap=0.0,
+                           max_nodes=2000000):
+        """The CENTRALISED micro-grid problem of one instant as ONE mixed-integer program, solved to optimality by the
+        general branch-and-cut kernel -- for fleets small enough for it (the reference itself runs 20 heaters;
+        micro_grid_agents.py:691-735 builds the same monolithic problem for cvxpy).  Decision vector: every heater's
+        v~ = [u; mu] over the horizon, then the grid import z_k.  With a non-negative price the grid MLD's
+        delta / z pair (micro_grid_models.py:145-168: z = [y >= 0] y) is equivalent to  z_k >= y_k, z_k >= 0  at
+        the optimum, so the import is carried by one continuous column per step and the big-M rows are not needed;
+        the grid limits, when given, bound the aggregate directly.  Single rank only (the problem does not shard).
+        -> dict(u [B, Nt], v [B, 3 Nt], z [Nt], obj, status, stats)"""
+        if distributed.is_distributed():
+            raise NotImplementedError("the monolithic problem lives on one GPU; use coupled_step() across ranks")
+        dev, B, Nt = self.device, self.B, self.Nt
+        price = torch.as_tensor(price, dtype=torch.float64).to(dev).reshape(Nt)
+        if bool((price < 0).any()):
+            raise NotImplementedError("a negative import price needs the grid MLD's delta / z rows")
+        p_other = torch.as_tensor(p_other, dtype=torch.float64).to(dev).reshape(Nt)
+        x0 = torch.as_tensor(x0, dtype=torch.float64).to(dev).reshape(B, 1)
+        omega = torch.as_tensor(omega_forecast, dtype=torch.float64).to(dev).reshape(B, Nt)
+        nva = 3 * Nt
+        n = B * nva + Nt
+        H_a, rhs_a = self.batch.constraint_rows(x0, omega)                  # [B, 2 Nt, 3 Nt], [B, 2 Nt]
+        ma = H_a.shape[1]
+        rows = B * ma + Nt + (2 * Nt if grid_limits is not None else 0)
+        H = torch.zeros((1, rows, n), dtype=torch.float64, device=dev)
+        rhs = torch.zeros((1, rows), dtype=torch.float64, device=dev)
+        for b in range(B):
+            H[0, b * ma:(b + 1) * ma, b * nva:(b + 1) * nva] = H_a[b]
+            rhs[0, b * ma:(b + 1) * ma] = rhs_a[b]
+        r0 = B * ma
+        k = torch.arange(Nt, device=dev)
+        for b in range(B):                                                   #  sum_i P_i u_i,k - z_k <= -p_other_k
+            H[0, r0 + k, b * nva + 3 * k] = self.P_nom[b]
+        H[0, r0 + k, B * nva + k] = -1.0
+        rhs[0, r0:r0 + Nt] = -p_other
+        if grid_limits is not None:
+            r1 = r0 + Nt
+            for b in range(B):
+                H[0, r1 + k, b * nva + 3 * k] = self.P_nom[b]
+                H[0, r1 + Nt + k, b * nva + 3 * k] = -self.P_nom[b]
+            rhs[0, r1:r1 + Nt] = float(grid_limits[1]) - p_other
+            rhs[0, r1 + Nt:r1 + 2 * Nt] = p_other - float(grid_limits[0])
+        cost = self.cost_from_prices(price).reshape(B, Nt, 3).clone()
+        cost[:, :, 0] = 0.0                                                  # the energy price sits on the import z
+        c = torch.cat([cost.reshape(-1), price]).reshape(1, n)
+        lb_a, ub_a, isb_a = self.batch._bounds_dev()
+        lb = torch.cat([lb_a.repeat(B), torch.zeros(Nt, dtype=torch.float64, device=dev)])
+        ub = torch.cat([ub_a.repeat(B), torch.full((Nt,), float("inf"), dtype=torch.float64, device=dev)])
+        isb = torch.cat([isb_a.repeat(B), torch.zeros(Nt, dtype=torch.uint8, device=dev)])
+        opts = cabi.default_opts(mip_rel_gap=float(mip_rel_gap), max_nodes=int(max_nodes))
+        v, obj, status, stats = cabi.milp_solve(c, H, rhs, lb, ub, isb, opts)
+        va = v[0, :B * nva].reshape(B, nva)
+        return dict(u=va.view(B, Nt, 3)[:, :, 0], v=va, z=v[0, B * nva:], obj=float(obj[0]), status=int(status[0]),
+                    stats=stats[0])
+
     def _best_response(self, plan, cost, price, p_other, a_lo, a_hi, passes, groups):
         """Descent on the true centralised cost from the coordination's plan (hmpc.h: hmpc_coupling_response_cost_f64
         ..): blocks of agents answer their marginal price in turn, a block's answer is kept only if the total went

@@ -267,3 +267,29 @@ def test_closed_loop_with_coordination(cuda_device):
     bill = lambda lg: float((price[:steps] * np.maximum(0, lg["P_agg"][:, 0] + p_other[:steps])).sum())
     assert bill(co) <= bill(de) * (1 + 1e-12)
     assert np.isfinite(co["T"]).all() and co["mu_hat"].shape == (steps, N_h, 2)
+
+
+@pytest.mark.parametrize("N_h,N_p,seed", [(3, 8, 0), (4, 10, 1), (5, 12, 2)])
+def test_centralised_problem_exact_small_fleets(N_h, N_p, seed, cuda_device):
+    """the monolithic micro-grid MILP on the GPU (DewhFleet.coupled_step_exact, branch-and-cut kernel) against HiGHS on
+    the reference's formulation with the grid MLD's delta / z rows: the same optimum to 1e-6, a plan whose true cost is
+    that optimum, and the price coordination's bounds around it"""
+    from oracle import coupled, solve as osv
+    from pyhybridcontrol_b200.examples.residential_mg_with_pv_and_dewhs.fleet import DewhFleet
+    from pyhybridcontrol_b200.examples.residential_mg_with_pv_and_dewhs.parameters import grid_param_struct
+    Nt = N_p + 1
+    params, T0, dem, price, P, p_other = _case(N_h, N_p, seed)
+    fleet = DewhFleet(params, N_p, device=cuda_device)
+    fleet.build()
+    ex = fleet.coupled_step_exact(T0, dem, price, p_other)
+    assert ex["status"] == 0
+    probs = [_agent_problem(params[b], Nt, T0[b], dem[b], price) for b in range(N_h)]
+    prob, _, _ = coupled.build_coupled_problem(probs, P, p_other, price, dict(grid_param_struct, P_g_min=-1e7, P_g_max=1e7))
+    st, opt, _ = osv.solve_milp(prob, polish=True)
+    assert st == 0
+    assert abs(ex["obj"] - opt) <= 1e-6 * max(1.0, abs(opt)), (ex["obj"], opt)
+    U = np.round(ex["u"].cpu().numpy())
+    np.testing.assert_allclose(coupled.coupled_cost(probs, U, P, p_other, price), opt, rtol=1e-6)
+    out = fleet.coupled_step(T0, dem, price, p_other, iters=300, rel_gap=1e-3)
+    tol = 1e-7 * max(1.0, abs(opt))
+    assert out["lower_bound"] <= ex["obj"] + tol and ex["obj"] <= out["upper_bound"] + tol
