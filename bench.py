@@ -364,8 +364,9 @@ def main_ours(args):
             ev[4].record()
         if peer_ex is not None:
             # K6 with the exchange fused in: the reduction's last pass stores this rank's sums into every rank's window
-            # over NVLink; the gather adds the world's contributions of the PREVIOUS step (pipelined: no rank waits)
-            peer_ex.publish(u, fleet.P_nom, out_prev=p_total_prev)
+            # over NVLink; the same launch adds the world's contributions of the step four publishes back (pipelined: a
+            # rank may run up to four steps ahead of the slowest one, as with the ring of four NCCL buffers before)
+            peer_ex.publish(u, fleet.P_nom, out_prev=p_total_prev, lag=4)
             p_agg = p_total_prev
         else:
             p_agg = cabi.aggregate_power(u, fleet.P_nom)      # this rank's agents; ranks are summed by exchange()
@@ -383,7 +384,7 @@ def main_ours(args):
             from pyhybridcontrol_b200.distributed import PeerExchange
             peer_ex = PeerExchange(Nt, dev)
             peer_note = ("peer-store exchange inside the step's CUDA graph (symmetric memory over NVLink; publish fused "
-                         "into the reduction's last pass, gather of the previous step): no host call per step")
+                         "into the reduction's last pass, gather four steps behind): no host call per step")
         except Exception as exc:
             peer_ex = None
             peer_note = "NCCL all-reduce on a side stream (symmetric memory unavailable: %r)" % (exc,)

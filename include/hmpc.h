@@ -302,15 +302,14 @@ int hmpc_aggregate_power_f64(int32_t B, int32_t Nt, const double* u, int64_t u_s
  * EVERY rank's window and then raises the step's flag there (release, system scope); gather waits (bounded spin on
  * local memory; a peer that never arrives turns the result into NaN and sets the window's error word instead of
  * hanging) for the world's flags of this rank's latest step and adds the contributions in rank order.  Both are plain
- * kernels on `stream`: capturable in the step's CUDA graph.  A ring of 4 steps: gather (any lag) at least once per
- * publish.                                                                                                        */
+ * kernels on `stream`: capturable in the step's CUDA graph.  A ring of 8 steps: the ranks may drift up to lag <= 6 steps apart.                                                                                                        */
 int64_t hmpc_aggregate_window_doubles(int32_t Nt, int32_t world);
 int hmpc_aggregate_publish_f64(int32_t B, int32_t Nt, const double* u, int64_t u_stride_b, int32_t u_stride_k,
                                const double* P_nom, double* partial, int32_t world, int32_t rank,
                                double* const* windows, double* P_total_prev /* NULL, or [Nt]: the same launch also
-                               gathers the previous step (= hmpc_aggregate_gather_f64 with lag 1) */, void* stream);
+                               gathers the step `lag` (1..6) publishes back */, int32_t lag, void* stream);
 int hmpc_aggregate_gather_f64(int32_t Nt, int32_t world, int32_t rank, double* window, double* P_total,
-                              int64_t spin_limit, int32_t lag /* 0: this rank's latest step; 1, 2: that many steps
+                              int64_t spin_limit, int32_t lag /* 0: this rank's latest step; 1..6: that many steps
                               back -- a pipelined loop gathers step s-1 while step s is published, so that no rank
                               ever waits for a slower one inside the control loop */, void* stream);
 

@@ -635,7 +635,7 @@ def aggregate_window_doubles(Nt, world):
     return int(_lib.hmpc_aggregate_window_doubles(int(Nt), int(world)))
 
 
-def aggregate_publish(u, P_nom, world, rank, windows_dev, out_prev=None):
+def aggregate_publish(u, P_nom, world, rank, windows_dev, out_prev=None, lag=1):
     """K6 local reduction + publication into every rank's exchange window (windows_dev: int64 CUDA tensor of `world`
     device pointers)."""
     global launch_count
@@ -644,7 +644,7 @@ def aggregate_publish(u, P_nom, world, rank, windows_dev, out_prev=None):
     partial = torch.empty((chunks, Nt), dtype=torch.float64, device=u.device)
     _check(_lib.hmpc_aggregate_publish_f64(B, Nt, C.c_void_p(u.data_ptr()), C.c_int64(u.stride(0)), C.c_int32(u.stride(1)),
                                            _ptr(P_nom), _ptr(partial), C.c_int32(world), C.c_int32(rank),
-                                           C.c_void_p(windows_dev.data_ptr()), _ptr(out_prev), _stream()),
+                                           C.c_void_p(windows_dev.data_ptr()), _ptr(out_prev), C.c_int32(lag), _stream()),
            "hmpc_aggregate_publish_f64")
     launch_count += 2
     return partial

@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(128) aggregate_final_kernel(int chunks, int Nt
 // ordinary kernels on the step's stream: they sit inside the step's CUDA graph, no host call per step.
 // Window (doubles unless noted): [0] step counter of the owner (u64), [1] error word (u64), [2 .. 2 + RING*W) flags
 // (u64, [slot][rank]), then data [slot][rank][Nt].
-constexpr int kXRing = 4;
+constexpr int kXRing = 8;
 __host__ __device__ inline int64_t xwin_flags(int slot, int world, int r) { return 2 + (int64_t)slot * world + r; }
 __host__ __device__ inline int64_t xwin_data(int slot, int world, int r, int Nt) {
     return 2 + (int64_t)kXRing * world + ((int64_t)slot * world + r) * Nt;
@@ -62,7 +62,7 @@ __host__ __device__ inline int64_t xwin_data(int slot, int world, int r, int Nt)
 
 __global__ void __launch_bounds__(128) aggregate_publish_kernel(int chunks, int Nt, const double* __restrict__ partial,
                                                                 int world, int rank, double* const* __restrict__ windows,
-                                                                double* __restrict__ out_prev, long long spin_limit) {
+                                                                double* __restrict__ out_prev, long long spin_limit, int lag) {
     unsigned long long* mine = reinterpret_cast<unsigned long long*>(windows[rank]);
     const unsigned long long seq = mine[0] + 1ull;
     const int slot = (int)(seq % kXRing);
@@ -78,11 +78,11 @@ __global__ void __launch_bounds__(128) aggregate_publish_kernel(int chunks, int 
         asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(seq) : "memory");
     }
     if (threadIdx.x == 0) mine[0] = seq;
-    // the same launch gathers the PREVIOUS step (pipelined loops: the peers' contributions of step seq - 1 arrived long
-    // ago, nobody waits) -- one launch less per control step
+    // the same launch gathers an EARLIER step (pipelined loops: the peers' contributions of step seq - lag arrived long
+    // ago, nobody waits; the ranks may drift `lag` steps apart) -- one launch less per control step
     if (out_prev) {
-        if (seq <= 1ull) { for (int k = threadIdx.x; k < Nt; k += blockDim.x) out_prev[k] = 0.0; return; }
-        const unsigned long long want = seq - 1ull;
+        if (seq <= (unsigned long long)lag) { for (int k = threadIdx.x; k < Nt; k += blockDim.x) out_prev[k] = 0.0; return; }
+        const unsigned long long want = seq - (unsigned long long)lag;
         const int pslot = (int)(want % kXRing);
         __shared__ int s_bad;
         if (threadIdx.x == 0) s_bad = 0;
@@ -171,9 +171,11 @@ extern "C" int64_t hmpc_aggregate_window_doubles(int32_t Nt, int32_t world) {
 
 extern "C" int hmpc_aggregate_publish_f64(int32_t B, int32_t Nt, const double* u, int64_t u_stride_b,
                                           int32_t u_stride_k, const double* P_nom, double* partial, int32_t world,
-                                          int32_t rank, double* const* windows, double* P_total_prev, void* stream) {
+                                          int32_t rank, double* const* windows, double* P_total_prev, int32_t lag,
+                                          void* stream) {
     using namespace hmpc;
     if (B < 0 || Nt < 1 || !u || !partial || !windows || world < 1 || world > 128 || rank < 0 || rank >= world) return HMPC_ERR_ARG;
+    if (P_total_prev && (lag < 1 || lag > kXRing - 2)) return HMPC_ERR_ARG;
     const int chunks = B > 0 ? ceil_div(B, kAggChunk) : 0;
     if (chunks) {
         aggregate_partial_kernel<<<chunks, 128, 0, (cudaStream_t)stream>>>(B, Nt, u, u_stride_b, u_stride_k, P_nom,
@@ -181,7 +183,7 @@ extern "C" int hmpc_aggregate_publish_f64(int32_t B, int32_t Nt, const double* u
         HMPC_LAUNCH_CHECK("aggregate_partial_kernel");
     }
     aggregate_publish_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(chunks, Nt, partial, world, rank, windows, P_total_prev,
-                                                                  400000000ll);
+                                                                  400000000ll, lag);
     HMPC_LAUNCH_CHECK("aggregate_publish_kernel");
     return HMPC_OK;
 }
@@ -189,7 +191,7 @@ extern "C" int hmpc_aggregate_publish_f64(int32_t B, int32_t Nt, const double* u
 extern "C" int hmpc_aggregate_gather_f64(int32_t Nt, int32_t world, int32_t rank, double* window, double* P_total,
                                          int64_t spin_limit, int32_t lag, void* stream) {
     using namespace hmpc;
-    if (Nt < 1 || !window || !P_total || world < 1 || world > 128 || rank < 0 || rank >= world || lag < 0 || lag > 2) return HMPC_ERR_ARG;
+    if (Nt < 1 || !window || !P_total || world < 1 || world > 128 || rank < 0 || rank >= world || lag < 0 || lag > kXRing - 2) return HMPC_ERR_ARG;
     aggregate_gather_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(Nt, world, rank, window, P_total,
                                                                  spin_limit > 0 ? spin_limit : 400000000ll, lag);
     HMPC_LAUNCH_CHECK("aggregate_gather_kernel");

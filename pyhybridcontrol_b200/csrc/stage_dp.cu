@@ -50,9 +50,13 @@ constexpr int kDpMaxAct = 1 << kDpMaxNb;
 constexpr int kDpMaxNc = 8;
 constexpr int kDpMaxNt = 128;
 constexpr int kDpMaxT = 4;           // extra state terms per stage
-constexpr int kSearchWarps = 4;
-constexpr int kStackCap = 512;        // open nodes per agent
-constexpr int kTailBudget = 64;       // expansions the fused tail search may spend before deferring to kernel 2
+constexpr int kSearchWarps = 16;      // warps of the search kernel's CTA (one agent per CTA)
+constexpr int kStackCap = 2048;       // open nodes per agent in the wide search kernel
+constexpr int kSoloStack = 896;       // ... per warp in the one-warp search kernel, at most (less when shared memory is short)
+constexpr int kSoloWarps = 4;         // agents per CTA in the one-warp search kernel
+constexpr int kSoloTail = 48;         // expansions beyond one descent that warp 0 spends alone in the fused tail before the CTA joins in
+constexpr int kSoloBudget = 128;      // ... and a warp of the one-warp kernel before it hands the agent to the wide kernel
+constexpr int kTailBudget = 20000;    // expansions the fused tail search may spend before deferring to the wide kernel
 constexpr int kPending = -1;          // status of an agent that kernel 2 still has to search
 constexpr double kEdgeEps = 1e-9;     // cell-boundary guard (fraction of a cell)
 constexpr double kLinSlop = 4e-15;    // relative floating-point slop subtracted per stage from a linear cell
@@ -71,6 +75,8 @@ struct DpArgs {
     hmpc_stage_terms t;                // optional convex state / slack terms (T == 0 and qmu == NULL: none)
     int G, nb, nact, nv, T;
     int D, nstore, fmt, fuse;          // search depth per expansion, stored stages (k = D, 2D, ...), cell format
+    int solo_cap;                      // open nodes per warp in the one-warp search kernel
+    long long buf_bytes;               // shared memory behind the plan (stage buffers / set-up staging / search stack)
     void* table;                       // [B, nstore, G] cells
     double* pblk;                      // [B, plan doubles]: the agent's stage data, handed from kernel 1 to kernel 2
     double* v; double* obj; int32_t* status; int32_t* stats;
@@ -122,7 +128,7 @@ __host__ __device__ inline DpPlan make_dp_plan(int Nt, int nb, int nc, int T = k
 }
 
 enum { MISC_W = 0, MISC_INVW, MISC_A, MISC_FLAG, MISC_SIMPLE, MISC_TERMS, MISC_LINOK, MISC_INC_OBJ, MISC_INC_P0,
-       MISC_INC_P1, MISC_NODES0, MISC_IMPR0, MISC_KINS, MISC_T_SETUP, MISC_T_SWEEP };
+       MISC_INC_P1, MISC_NODES0, MISC_IMPR0, MISC_KINS, MISC_T_SETUP, MISC_T_SWEEP, MISC_T_SEARCH };
 
 struct DpCtx {
     int Nt, nb, nc, nact, nmu, nv, G;
@@ -259,7 +265,7 @@ __device__ inline void dp_load(const DpArgs& A, int b, DpCtx& c, double* stage) 
         c.misc[MISC_FLAG] = (double)flag;
         c.misc[MISC_TERMS] = (c.T > 0 || A.t.qmu) ? 1.0 : 0.0;
         c.misc[MISC_INC_OBJ] = INFINITY; c.misc[MISC_INC_P0] = 0.0; c.misc[MISC_INC_P1] = 0.0;
-        c.misc[MISC_NODES0] = 0.0; c.misc[MISC_IMPR0] = 0.0;
+        c.misc[MISC_NODES0] = 0.0; c.misc[MISC_IMPR0] = 0.0; c.misc[MISC_T_SEARCH] = 0.0;
     }
     __syncthreads();
     // ---- per-stage data, one stage per thread
@@ -667,7 +673,18 @@ __global__ void __launch_bounds__(kTableBlock, MINB) stage_dp_table_kernel(const
 
 struct Node { double s, cost, bound; unsigned long long p0, p1; int k, pad; };
 
-__device__ bool dp_search(const DpArgs& A, const DpCtx& c, int b, Node* stack, double* ptraj, int lane, int budget);
+struct SearchShared {
+    double best, T, root_lb, delta, open_lb;
+    unsigned long long bp0, bp1;
+    int sp, nodes, improvements, cut_by_T, limit, defer, pass_done, cap;
+    double cand[kTableBlock / 32];
+    unsigned long long cp0[kTableBlock / 32], cp1[kTableBlock / 32];
+    int cnt[kTableBlock / 32];
+};
+
+template <bool SOLO>
+__device__ bool dp_search(const DpArgs& A, const DpCtx& c, int b, Node* stack, int cap, double* ptraj, SearchShared* sh,
+                          int W, int budget);
 
 // MINB = 1: the register budget of one CTA per SM (small batches: the step time is one agent's latency);  MINB = 2: half
 // the registers (a few spills outside the hot loops) so that two CTAs share an SM and hide each other's latencies -- 24 %
@@ -677,7 +694,7 @@ __global__ void __launch_bounds__(kTableBlock, MINB) stage_dp_table_kernel(const
     typedef typename Cell<FMT>::T TT;
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ double s_kins[kTableBlock / 32];
-    __shared__ int s_tail;
+    __shared__ SearchShared sh_search;
     const int b = blockIdx.x;
     const int nthr = kTableBlock;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -1013,17 +1030,19 @@ __global__ void __launch_bounds__(kTableBlock, MINB) stage_dp_table_kernel(const
     __syncthreads();
     const DpPlan plan2 = plan;
     if (A.fuse) {
-        // ---- tail: warp 0 searches this agent right away (stage data still in shared memory, table in L2)
-        if (tid == 0) s_tail = 0;
-        Node* stack = reinterpret_cast<Node*>(buf0);
-        double* ptraj = reinterpret_cast<double*>(stack + kStackCap);
+        // ---- tail: the whole CTA searches this agent right away (stage data still in shared memory, table in L2);
+        // the stage buffers become the stack of open nodes
+        double* ptraj = reinterpret_cast<double*>(buf0);
+        Node* stack = reinterpret_cast<Node*>(ptraj + (kDpMaxNt + 1));
+        const int cap = (int)((A.buf_bytes - 8 * (kDpMaxNt + 1)) / sizeof(Node));
+        // warp 0 starts alone (a first descent is sequential; most agents of a nominal batch are done within it) ...
+        int done = 0;
+        if (warp == 0) done = dp_search<true>(A, c, b, stack, cap, ptraj, &sh_search, 1, (c.Nt + A.D - 1) / A.D + kSoloTail);
+        done = __syncthreads_or(done);
+        // ... and the whole CTA takes over what is left
+        if (!done) done = dp_search<false>(A, c, b, stack, cap, ptraj, &sh_search, kTableBlock / 32, kTailBudget);
+        if (done) return;
         __syncthreads();
-        if (warp == 0) {
-            const bool done = dp_search(A, c, b, stack, ptraj, lane, kTailBudget);
-            if (lane == 0) s_tail = done ? 0 : 1;
-        }
-        __syncthreads();
-        if (s_tail == 0) return;
     }
     {   // hand the stage data to the search kernel
         const double* src = reinterpret_cast<const double*>(smem);
@@ -1136,34 +1155,38 @@ __device__ __forceinline__ bool expand_simple(const DpCtx& c, const TabRef& tr, 
     return ok;
 }
 
-// One warp per agent.  The unit of work is the depth-D subtree below one open node, D = the largest depth with
-// nact^D <= 32: lane l evaluates the action sequence whose base-nact digits are l -- exact stage costs, exact
-// states -- and closes it with the table bound of the state it reaches (one table read per lane per iteration).
-//   search : depth-first from the root; a sequence survives when cost + bound < min(incumbent, T), the best survivor
-//            goes on top of the stack; whole runs of dominated nodes are discarded in one step;
+// Exact search of one agent by a team of W warps: one warp (SOLO: the calling warp, synchronised with __syncwarp; the
+// other warps of the CTA are elsewhere) or a whole CTA.  The unit of work is the depth-D subtree below one open node,
+// D = the largest depth with nact^D <= 32: lane l of a warp evaluates the action sequence whose base-nact digits are l
+// -- exact stage costs, exact states -- and closes it with the table bound of the state it reaches (one table read
+// per lane).  The open nodes are a stack in shared memory; every ROUND the team takes the nodes on top of it
+// (depth-first order: the best child of the last expansion is on top, its siblings below), expands them side by side,
+// and pushes the survivors back in a fixed order (the top node's children end on top again), so the run is
+// deterministic.  A first descent is as sequential as the problem, so a nominal agent is searched by one warp; the
+// proof phase of the hard agents (robust configurations) runs W wide.  Nodes beyond the top one are taken only while
+// the stack keeps `reserve` entries free -- what a plain depth-first descent from any open node can need -- so that
+// working ahead never causes an overflow the sequential search would not have had.
 //   T      : threshold of the pass.  The first pass sets it a hair above the best bound of the root's children; a pass
 //            that exhausts the tree below T without a solution is repeated with four times the distance;
-//   dive   : on long horizons the siblings of a first descent would not fit the stack, so a separate greedy dive (best
-//            lane of every subtree, nothing pushed) produces an incumbent first.
-// Returns false when `budget` expansions were not enough (fused tail): the incumbent goes to misc[] for kernel 2.
-__device__ bool dp_search(const DpArgs& A, const DpCtx& c, int b, Node* stack, double* ptraj, int lane, int budget) {
+//   dive   : when the stack could not hold the siblings of a first descent, a greedy dive (warp 0, nothing pushed)
+//            produces an incumbent first; the same dive is the best effort of a search that hit its limits without one.
+// Returns false when `budget` expansions were not enough: the incumbent goes to misc[] for whoever continues.
+template <bool SOLO>
+__device__ bool dp_search(const DpArgs& A, const DpCtx& c, int b, Node* stack, int cap, double* ptraj, SearchShared* sh,
+                          int W, int budget) {
     const int Nt = c.Nt, nb = c.nb, nc = c.nc, nv = c.nv, nact = c.nact;
+    const int tid = SOLO ? (int)(threadIdx.x & 31) : (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nthreads = SOLO ? 32 : (int)blockDim.x;
+    auto bar = [] { if (SOLO) __syncwarp(); else __syncthreads(); };
     double* vout = A.v + (int64_t)b * Nt * nv;
     int32_t* st_out = A.stats + (int64_t)b * 8;
-    const double a = c.misc[MISC_A];
     const unsigned long long t_search = global_ns();
     TabRef tr;
     tr.fmt = A.fmt; tr.G = c.G; tr.D = A.D; tr.invw = c.misc[MISC_INVW]; tr.off = c.off; tr.loinf = c.loinf; tr.hiinf = c.hiinf;
     tr.linok = c.misc[MISC_LINOK] != 0.0;
     tr.tab = reinterpret_cast<const unsigned char*>(A.table) + (int64_t)b * A.nstore * c.G * fmt_bytes(A.fmt);
     const int D = A.D;
-
-    double best = c.misc[MISC_INC_OBJ];
-    unsigned long long bp0 = (unsigned long long)__double_as_longlong(c.misc[MISC_INC_P0]);
-    unsigned long long bp1 = (unsigned long long)__double_as_longlong(c.misc[MISC_INC_P1]);
-    int nodes = (int)c.misc[MISC_NODES0], improvements = (int)c.misc[MISC_IMPR0], max_sp = 0;
-    const int nodes_in = nodes;
-    bool limit = false, defer = false;
+    const int nodes_in = (int)c.misc[MISC_NODES0];
 
     const bool simple21 = c.misc[MISC_SIMPLE] != 0.0 && nb == 1 && nc == 2 && D == 5;
     // evaluate lane's action sequence below node (k0, s, cost, path); returns ok, and (k1, s, cost, path, bd)
@@ -1189,113 +1212,202 @@ __device__ bool dp_search(const DpArgs& A, const DpCtx& c, int b, Node* stack, d
         }
         return ok;
     };
-
-    const bool two_phase = ((Nt + D - 1) / D) * ((1 << (nb * D)) - 1) + 64 > kStackCap;
+    // warp 0: follow the best lane of every subtree down to the horizon, nothing pushed
     auto greedy_dive = [&]() {
-        int k0 = 0; double s0 = 0.0, cost0 = 0.0; unsigned long long r0 = 0, r1 = 0;
+        int k0 = 0, nodes = 0; double s0 = 0.0, cost0 = 0.0; unsigned long long r0 = 0, r1 = 0;
         while (k0 < Nt) {
             double s = s0, cost = cost0, bd; unsigned long long q0 = r0, q1 = r1; bool leaf;
             const bool ok = expand(k0, s, cost, q0, q1, INFINITY, bd, leaf);
             ++nodes;
             const int win = warp_argmin(ok, bd);
-            if (win < 0) break;                                   // dead end (hard rows): the search proper takes over
+            if (win < 0) break;                               // dead end (hard rows): the search proper takes over
             s0 = __shfl_sync(0xffffffffu, s, win); cost0 = __shfl_sync(0xffffffffu, cost, win);
             r0 = __shfl_sync(0xffffffffu, q0, win); r1 = __shfl_sync(0xffffffffu, q1, win);
             k0 += (Nt - k0) < D ? (Nt - k0) : D;
-            if (k0 >= Nt && cost0 < best) { best = cost0; bp0 = r0; bp1 = r1; ++improvements; }
+        }
+        if (lane == 0) {
+            sh->nodes += nodes;
+            if (k0 >= Nt && cost0 < sh->best) { sh->best = cost0; sh->bp0 = r0; sh->bp1 = r1; sh->improvements += 1; }
         }
     };
-    if (two_phase && !isfinite(best)) greedy_dive();
+
+    if (tid == 0) {
+        sh->best = c.misc[MISC_INC_OBJ];
+        sh->bp0 = (unsigned long long)__double_as_longlong(c.misc[MISC_INC_P0]);
+        sh->bp1 = (unsigned long long)__double_as_longlong(c.misc[MISC_INC_P1]);
+        sh->nodes = nodes_in; sh->improvements = (int)c.misc[MISC_IMPR0];
+        sh->T = INFINITY; sh->root_lb = INFINITY; sh->delta = 0.0; sh->open_lb = INFINITY;
+        sh->limit = 0; sh->defer = 0; sh->cap = cap;
+    }
+    bar();
+    const int fan = (1 << (nb * D)) - 1;
+    const int reserve = ((Nt + D - 1) / D) * fan;                 // growth of a sequential descent from any open node
+    if (reserve + 64 > cap && !isfinite(sh->best)) {
+        if (warp == 0) greedy_dive();
+        bar();
+    }
     // ---- exact search, pass by pass
-    double T = INFINITY, root_lb = INFINITY, delta = 0.0, open_lb = INFINITY;
-    for (int pass = 0; pass < 200 && !limit && !defer; ++pass) {
-        bool cut_by_T = false;
-        int sp = 1;
-        if (lane == 0) { Node r; r.s = 0.0; r.cost = 0.0; r.bound = -INFINITY; r.p0 = r.p1 = 0; r.k = 0; r.pad = 0; stack[0] = r; }
-        __syncwarp();
-        while (sp > 0) {
-            if (nodes >= A.o.max_nodes) { limit = true; break; }
-            if (nodes - nodes_in >= budget) { defer = true; break; }
+    for (int pass = 0; pass < 200; ++pass) {
+        if (tid == 0) {
+            Node r; r.s = 0.0; r.cost = 0.0; r.bound = pass == 0 ? -INFINITY : sh->root_lb; r.p0 = r.p1 = 0; r.k = 0; r.pad = 0;
+            stack[0] = r;
+            sh->sp = 1; sh->cut_by_T = 0; sh->pass_done = 0;
+        }
+        bar();
+        while (true) {
+            int sp = sh->sp;
+            const int nodes = sh->nodes;
+            const double best = sh->best, T = sh->T;
+            if (sp == 0) break;
+            if (nodes >= A.o.max_nodes) { if (tid == 0) sh->limit = 1; break; }
+            if (nodes - nodes_in >= budget) { if (tid == 0) sh->defer = 1; break; }
             const double tol = isfinite(best) ? fmax(1e-11 * fmax(1.0, fabs(best)), A.o.mip_rel_gap * fabs(best)) : 0.0;
             const double bcut = best - tol;
             const double cut = fmin(bcut, T);
-            // discard the run of dominated nodes on top of the stack, pop the first live one
-            const bool live = lane < sp && stack[sp - 1 - lane].bound < cut;
-            const unsigned lm = __ballot_sync(0xffffffffu, live);
-            if (lm == 0) { sp -= sp < 32 ? sp : 32; continue; }
-            const int first = __ffs(lm) - 1;
-            const Node nd = stack[sp - 1 - first];
-            sp -= first + 1;
-            __syncwarp();
-            double s = nd.s, cost = nd.cost, bd; unsigned long long q0 = nd.p0, q1 = nd.p1; bool leaf;
-            bool ok = expand(nd.k, s, cost, q0, q1, cut, bd, leaf);
-            ++nodes;
-            if (nd.k == 0 && pass == 0) {
-                // the root's children fix the first threshold: a hair above the best of their bounds
-                root_lb = warp_min(bd);
-                delta = fmax(1e-3 * fmax(1.0, fabs(root_lb)), 1e-9);
-                T = root_lb + delta;
-                ok = ok && bd < T;
+            // discard the run of dominated nodes on top of the stack (every warp finds the same new top; nothing is written)
+            while (sp > 0) {
+                const unsigned lm = __ballot_sync(0xffffffffu, lane < sp && stack[sp - 1 - lane].bound < cut);
+                if (lm) { sp -= __ffs(lm) - 1; break; }
+                sp -= sp < 32 ? sp : 32;
             }
-            if (__any_sync(0xffffffffu, !ok && bd < bcut)) cut_by_T = true;
-            if (leaf) {
-                const int win = warp_argmin(ok, cost);
-                if (win >= 0) {
-                    best = __shfl_sync(0xffffffffu, cost, win);
-                    bp0 = __shfl_sync(0xffffffffu, q0, win); bp1 = __shfl_sync(0xffffffffu, q1, win);
-                    ++improvements;
+            if (sp == 0) { if (tid == 0) sh->sp = 0; break; }
+            // how many nodes this round: the top one, and more while their children leave the reserve untouched
+            const int ahead = (cap - reserve - sp) / (fan + 1);
+            const int take = SOLO ? 1 : max(1, min(min(W, sp), ahead));
+            const bool mine = warp < take;
+            Node nd;
+            bool live = false;
+            if (mine) { nd = stack[sp - 1 - warp]; live = nd.bound < cut; }
+            bar();                                 // everybody holds its node: the stack may be overwritten from here
+            double s = 0.0, cost = 0.0, bd = INFINITY; unsigned long long q0 = 0, q1 = 0; bool leaf = false, ok = false;
+            double cand = INFINITY; int npush = 0, win = -1; unsigned pm = 0;
+            if (live) {
+                s = nd.s; cost = nd.cost; q0 = nd.p0; q1 = nd.p1;
+                ok = expand(nd.k, s, cost, q0, q1, cut, bd, leaf);
+                if (nd.k == 0 && pass == 0) {
+                    // the root's children fix the first threshold: a hair above the best of their bounds
+                    const double rl = warp_min(bd);
+                    const double dl = fmax(1e-3 * fmax(1.0, fabs(rl)), 1e-9);
+                    if (lane == 0) { sh->root_lb = rl; sh->delta = dl; sh->T = rl + dl; }
+                    ok = ok && bd < rl + dl;
                 }
-                continue;
+                if (__any_sync(0xffffffffu, !ok && bd < bcut) && lane == 0) atomicOr(&sh->cut_by_T, 1);
+                if (leaf) {
+                    win = warp_argmin(ok, cost);
+                    if (win >= 0) cand = __shfl_sync(0xffffffffu, cost, win);
+                } else {
+                    pm = __ballot_sync(0xffffffffu, ok);
+                    npush = __popc(pm);
+                    win = npush > 1 ? warp_argmin(ok, bd) : (npush ? __ffs(pm) - 1 : -1);
+                }
             }
-            const unsigned pm = __ballot_sync(0xffffffffu, ok);
-            const int npush = __popc(pm);
-            if (npush == 0) continue;
-            if (sp + npush > kStackCap) { limit = true; open_lb = fmin(open_lb, warp_min(ok ? bd : INFINITY)); break; }
-            // best survivor on top, the others below it in lane order
-            const int win = npush > 1 ? warp_argmin(ok, bd) : __ffs(pm) - 1;
-            if (ok) {
-                int pos = __popc(pm & ((1u << lane) - 1u));           // rank among the survivors
-                if (lane == win) pos = npush - 1;
-                else if (lane > win) pos -= 1;
-                Node ch; ch.s = s; ch.cost = cost; ch.bound = bd; ch.k = nd.k + D; ch.pad = 0; ch.p0 = q0; ch.p1 = q1;
-                stack[sp + pos] = ch;
+            if (mine && lane == 0) {
+                sh->cand[warp] = cand; sh->cnt[warp] = npush;
+                if (live) atomicAdd(&sh->nodes, 1);
             }
-            sp += npush;
-            max_sp = sp > max_sp ? sp : max_sp;
-            __syncwarp();
+            if (live && leaf && win >= 0) {          // the winning lane publishes its path
+                if (lane == win) { sh->cp0[warp] = q0; sh->cp1[warp] = q1; }
+            }
+            bar();
+            // ---- merge: new incumbent (lowest warp wins ties), push offsets (warp 0's children on top)
+            double nbest = best; int bw = -1, total = 0, above = 0;
+            for (int w2 = 0; w2 < take; ++w2) {
+                const double cv = sh->cand[w2];
+                if (cv < nbest) { nbest = cv; bw = w2; }
+                const int cn = sh->cnt[w2];
+                total += cn;
+                if (w2 < warp) above += cn;
+            }
+            const int base = sp - take;
+            if (base + total > cap) {               // the children do not fit: stop with what is known (never silently drop)
+                if (tid == 0) { sh->limit = 1; sh->sp = base; sh->open_lb = fmin(sh->open_lb, sh->root_lb); }
+                bar();
+                break;
+            }
+            if (live && !leaf && npush > 0) {
+                // this warp's block sits below the blocks of the warps with a smaller index (those are nearer the top)
+                const int blk = base + (total - above - npush);
+                if (ok) {
+                    int pos = __popc(pm & ((1u << lane) - 1u));           // rank among the survivors
+                    if (lane == win) pos = npush - 1;
+                    else if (lane > win) pos -= 1;
+                    Node ch; ch.s = s; ch.cost = cost; ch.bound = bd; ch.k = nd.k + D; ch.pad = 0; ch.p0 = q0; ch.p1 = q1;
+                    stack[blk + pos] = ch;
+                }
+            }
+            if (tid == 0) {
+                sh->sp = base + total;
+                if (bw >= 0) { sh->best = nbest; sh->bp0 = sh->cp0[bw]; sh->bp1 = sh->cp1[bw]; sh->improvements += 1; }
+            }
+            bar();
         }
-        if (limit || defer) {
+        bar();
+        if (sh->limit || sh->defer) {
             // what is still open bounds the optimum from below (certified gap of an unfinished search)
-            double m = INFINITY;
-            for (int i = lane; i < sp; i += 32) m = fmin(m, stack[i].bound);
-            open_lb = fmin(open_lb, warp_min(m));
-            if (cut_by_T) open_lb = fmin(open_lb, T);
+            if (warp == 0) {
+                double m = INFINITY;
+                for (int i = lane; i < sh->sp; i += 32) m = fmin(m, stack[i].bound);
+                m = warp_min(m);
+                if (lane == 0) { sh->open_lb = fmin(sh->open_lb, m); if (sh->cut_by_T) sh->open_lb = fmin(sh->open_lb, sh->T); }
+            }
+            bar();
             break;
         }
-        if (!cut_by_T || (isfinite(best) && best <= T)) break;       // nothing was held back by the threshold: done
-        delta *= 4.0;
-        T = root_lb + delta;
-        if (!isfinite(T)) T = INFINITY;
-    }
-    if (defer) {
-        if (lane == 0) {
-            double* misc = c.misc;
-            misc[MISC_INC_OBJ] = best;
-            misc[MISC_INC_P0] = __longlong_as_double((long long)bp0); misc[MISC_INC_P1] = __longlong_as_double((long long)bp1);
-            misc[MISC_NODES0] = (double)nodes; misc[MISC_IMPR0] = (double)improvements;
+        const bool finished = !sh->cut_by_T || (isfinite(sh->best) && sh->best <= sh->T);
+        bar();
+        if (finished) break;                                     // nothing was held back by the threshold: done
+        if (tid == 0) {
+            sh->delta *= 4.0;
+            double Tn = sh->root_lb + sh->delta;
+            sh->T = isfinite(Tn) ? Tn : INFINITY;
         }
-        __syncwarp();
+        bar();
+    }
+    if (sh->defer) {
+        if (tid == 0) {
+            double* misc = c.misc;
+            misc[MISC_INC_OBJ] = sh->best;
+            misc[MISC_INC_P0] = __longlong_as_double((long long)sh->bp0); misc[MISC_INC_P1] = __longlong_as_double((long long)sh->bp1);
+            misc[MISC_NODES0] = (double)sh->nodes; misc[MISC_IMPR0] = (double)sh->improvements;
+            misc[MISC_T_SEARCH] += (double)(global_ns() - t_search);
+        }
+        bar();
         return false;
     }
-    if (limit && !isfinite(best)) greedy_dive();     // budget gone before the first descent finished: best effort
+    if (sh->limit && !isfinite(sh->best)) {          // limits hit before the first descent finished: best effort
+        if (warp == 0) greedy_dive();
+        bar();
+    }
+    const double best = sh->best;
+    const unsigned long long bp0 = sh->bp0, bp1 = sh->bp1;
+    const bool limit = sh->limit != 0;
     // ---- write the solution: binaries from the path, mu in closed form along the exact trajectory
     const bool have = isfinite(best);
-    if (lane == 0 && have) {
-        double p = 0.0;
-        for (int k = 0; k < Nt; ++k) { ptraj[k] = p; p = fma(a, p, c.galpha[path_get(bp0, bp1, k, nb)]); }
+    if (warp == 0 && have) {
+        // exact trajectory: the scaled state is a prefix sum, s_k = sum_{j<k} galpha[al_j] / a^(j+1), and p_k = a^k s_k
+        const int ch = (Nt + 31) / 32;                       // consecutive steps per lane (kDpMaxNt = 128: at most 4)
+        double loc[4], sum = 0.0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int k = lane * ch + i;
+            loc[i] = sum;
+            if (i < ch && k < Nt) sum = fma(c.galpha[path_get(bp0, bp1, k, nb)], c.iak[k + 1], sum);
+        }
+        double incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const double t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        const double excl = incl - sum;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int k = lane * ch + i;
+            if (i < ch && k < Nt) ptraj[k] = c.ak[k] * (excl + loc[i]);
+        }
     }
-    __syncwarp();
-    for (int k = lane; k < Nt; k += 32) {
+    bar();
+    double rdi[kDpMaxNc];
+    if (c.nmu)
+        for (int i = 0; i < nc; ++i) rdi[i] = c.dscale[i] > 0.0 ? __drcp_rn(c.dscale[i]) : 0.0;
+    for (int k = tid; k < Nt; k += nthreads) {
         double* vk = vout + (int64_t)k * nv;
         if (!have) { for (int i = 0; i < nv; ++i) vk[i] = nan(""); continue; }
         const int ak_ = path_get(bp0, bp1, k, nb);
@@ -1304,54 +1416,77 @@ __device__ bool dp_search(const DpArgs& A, const DpCtx& c, int b, Node* stack, d
             const double p = ptraj[k];
             for (int i = 0; i < nc; ++i) {
                 const double viol = fma(c.e[i], p, c.falpha[i * nact + ak_] - c.rhs[k * nc + i]);
-                const double di = c.dscale[i];
-                vk[nb + i] = (di > 0.0 && !isinf(c.qs[k * nc + i])) ? fmax(viol, 0.0) / di : 0.0;
+                vk[nb + i] = !isinf(c.qs[k * nc + i]) ? fmax(viol, 0.0) * rdi[i] : 0.0;
             }
         }
     }
-    if (lane == 0) {
+    if (tid == 0) {
         A.obj[b] = have ? best : INFINITY;
         A.status[b] = limit ? HMPC_SOLVE_NODE_LIMIT : (have ? HMPC_SOLVE_OPTIMAL : HMPC_SOLVE_INFEASIBLE);
         // certified relative gap of an unfinished search, in units of 1e-9 (0 when proven)
         int gap9 = 0;
         if (limit) {
-            const double lbv = fmin(open_lb, best);
+            const double lbv = fmin(sh->open_lb, best);
             const double g = have ? (best - lbv) / fmax(fabs(best), 1e-300) : INFINITY;
             gap9 = (int)fmin(fmax(g, 0.0) * 1e9, 2.0e9);
         }
+        const int nodes = sh->nodes;
         // executed FP64-pipe instructions (sweep + search), in thousands (stats[7])
         const double kins = c.misc[MISC_KINS] + (double)nodes * 32.0 * D * (2.0 + 3.0 * nc);
-        // device time of this agent's phases in units of 0.1 us: [1] load + set-up, [2] sweep, [4] this search
+        // device time of this agent's phases in units of 0.1 us: [1] load + set-up, [2] sweep, [4] search (all legs)
         st_out[0] = nodes; st_out[1] = (int32_t)fmin(c.misc[MISC_T_SETUP] * 0.01, 2.0e9);
         st_out[2] = (int32_t)fmin(c.misc[MISC_T_SWEEP] * 0.01, 2.0e9); st_out[3] = c.G;
-        st_out[4] = (int32_t)fmin((double)(global_ns() - t_search) * 0.01, 2.0e9); st_out[5] = improvements;
+        st_out[4] = (int32_t)fmin((c.misc[MISC_T_SEARCH] + (double)(global_ns() - t_search)) * 0.01, 2.0e9);
+        st_out[5] = sh->improvements;
         st_out[6] = gap9;
         st_out[7] = (int32_t)fmin(kins / 1000.0, 2.0e9);
     }
-    __syncwarp();
+    bar();
     return true;
 }
 
-// kernel 2: the agents kernel 1 left pending (all of them when the tail search is off), four warps per CTA
+// One-warp search kernel (batches too large for the fused tail): kSoloWarps agents per CTA, each warp with its own copy
+// of the stage data and its own stack.  An agent that needs more than kSoloBudget expansions stays pending, incumbent
+// saved, for the wide kernel.
+__global__ void __launch_bounds__(kSoloWarps * 32) stage_dp_solo_kernel(const DpArgs A) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ SearchShared sh[kSoloWarps];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * kSoloWarps + warp;
+    if (b >= A.d.B || A.status[b] != kPending) return;
+    const DpPlan plan = make_dp_plan(A.d.Nt, A.nb, A.d.nc, A.T);
+    const size_t per_warp = (size_t)plan.nd * 8 + sizeof(Node) * A.solo_cap + 8 * (size_t)(kDpMaxNt + 1);
+    unsigned char* mine = smem + (size_t)warp * ((per_warp + 15) & ~(size_t)15);
+    DpCtx c = bind_ctx(A, mine);
+    Node* stack = reinterpret_cast<Node*>(mine + (size_t)plan.nd * 8);
+    double* ptraj = reinterpret_cast<double*>(stack + A.solo_cap);
+    double* pb = A.pblk + (int64_t)b * plan.nd;
+    double* dst = reinterpret_cast<double*>(mine);
+    for (int i = lane; i < plan.nd; i += 32) dst[i] = pb[i];
+    __syncwarp();
+    if (!dp_search<true>(A, c, b, stack, A.solo_cap, ptraj, &sh[warp], 1, kSoloBudget)) {
+        const int m0 = (int)(c.misc - dst);
+        if (lane < 16) pb[m0 + lane] = c.misc[lane];              // the incumbent and the counters travel on
+    }
+}
+
+// Wide search kernel: one CTA of kSearchWarps warps per agent still pending (the hard ones; every other CTA exits).
 __global__ void __launch_bounds__(kSearchWarps * 32) stage_dp_search_kernel(const DpArgs A) {
     extern __shared__ __align__(16) unsigned char smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.x * kSearchWarps + warp;
-    if (b >= A.d.B) return;
+    __shared__ SearchShared sh;
+    const int b = blockIdx.x;
     if (A.status[b] != kPending) return;
     const DpPlan plan = make_dp_plan(A.d.Nt, A.nb, A.d.nc, A.T);
-    const size_t per_warp = (size_t)plan.nd * 8 + sizeof(Node) * kStackCap + 8 * (kDpMaxNt + 1);
-    unsigned char* base = smem + per_warp * warp;
-    DpCtx c = bind_ctx(A, base);
-    Node* stack = reinterpret_cast<Node*>(base + (size_t)plan.nd * 8);
+    DpCtx c = bind_ctx(A, smem);
+    Node* stack = reinterpret_cast<Node*>(smem + (size_t)plan.nd * 8);
     double* ptraj = reinterpret_cast<double*>(stack + kStackCap);
     {
         const double* src = A.pblk + (int64_t)b * plan.nd;
-        double* dst = reinterpret_cast<double*>(base);
-        for (int i = lane; i < plan.nd; i += 32) dst[i] = src[i];
+        double* dst = reinterpret_cast<double*>(smem);
+        for (int i = threadIdx.x; i < plan.nd; i += blockDim.x) dst[i] = src[i];
     }
-    __syncwarp();
-    dp_search(A, c, b, stack, ptraj, lane, INT_MAX);
+    __syncthreads();
+    dp_search<false>(A, c, b, stack, kStackCap, ptraj, &sh, kSearchWarps, INT_MAX);
 }
 
 static size_t table_bytes(int B, int nstore, int G, int fmt) { return (size_t)B * nstore * G * fmt_bytes(fmt); }
@@ -1429,7 +1564,7 @@ extern "C" int hmpc_stage_dp_solve_f64(const hmpc_dims* dims, const double* cons
     int dev = 0, smem_optin = 0;
     HMPC_CUDA_TRY(cudaGetDevice(&dev));
     HMPC_CUDA_TRY(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    const size_t tail_bytes = sizeof(Node) * kStackCap + 8 * (kDpMaxNt + 1);
+    const size_t tail_bytes = sizeof(Node) * 1024 + 8 * (kDpMaxNt + 1);            // least stack of the fused tail
     auto smem_table = [&](int fmt) {
         size_t bufs = 2 * (size_t)a.G * fmt_bytes(fmt);
         if (bufs < tail_bytes) bufs = tail_bytes;
@@ -1448,8 +1583,20 @@ extern "C" int hmpc_stage_dp_solve_f64(const hmpc_dims* dims, const double* cons
     // the batch is at most two CTAs per SM, else kernel 2 searches many agents per SM concurrently
     a.fuse = a.o.fuse_search < 0 ? (dims->B <= 2 * kNumSM ? 1 : 0) : (a.o.fuse_search != 0);
     const size_t smem1 = smem_table(a.fmt) - 1024;
-    const size_t smem2 = ((size_t)plan.nd * 8 + tail_bytes) * kSearchWarps;
-    if (smem1 + 1024 > (size_t)smem_optin || smem2 > (size_t)smem_optin) return HMPC_ERR_ARG;
+    a.buf_bytes = (long long)(smem1 - (size_t)plan.total * 8);
+    const size_t smem2 = (size_t)plan.nd * 8 + sizeof(Node) * kStackCap + 8 * (kDpMaxNt + 1);
+    // one-warp kernel: a stack that holds a whole sequential descent when shared memory has the room (two CTAs per SM)
+    const size_t solo_fixed = (size_t)plan.nd * 8 + 8 * (size_t)(kDpMaxNt + 1) + 16;
+    const long long solo_room = ((long long)(114 * 1024) / kSoloWarps - (long long)solo_fixed) / (long long)sizeof(Node);
+    const int levels = (dims->Nt + a.D - 1) / a.D;
+    a.solo_cap = levels * ((1 << (a.nb * a.D)) - 1) + 72;
+    if (a.solo_cap > kSoloStack) a.solo_cap = kSoloStack;
+    if ((long long)a.solo_cap > solo_room) a.solo_cap = (int)solo_room;
+    if (a.solo_cap < 128) a.solo_cap = 128;
+    const size_t per_warp = ((solo_fixed - 16 + sizeof(Node) * a.solo_cap) + 15) & ~(size_t)15;
+    const size_t smem_solo = per_warp * kSoloWarps;
+    if (smem1 + 1024 > (size_t)smem_optin || smem2 + 1024 > (size_t)smem_optin || smem_solo + 1024 > (size_t)smem_optin)
+        return HMPC_ERR_ARG;
     const bool dewh_shape = dims->nc == 2 && a.nact == 2;
     void (*table_kernel)(const DpArgs) = nullptr;
     // two CTAs per SM when the batch has that many and their shared memory fits twice
@@ -1465,7 +1612,12 @@ extern "C" int hmpc_stage_dp_solve_f64(const hmpc_dims* dims, const double* cons
     // one fat CTA per SM: measured, two 256-thread CTAs per SM sweep 40 % fewer agents per second than one 512-thread CTA
     table_kernel<<<dims->B, kTableBlock, smem1, s>>>(a);
     HMPC_LAUNCH_CHECK("stage_dp_table_kernel");
-    stage_dp_search_kernel<<<ceil_div(dims->B, kSearchWarps), kSearchWarps * 32, smem2, s>>>(a);
+    if (!a.fuse) {
+        HMPC_CUDA_TRY(cudaFuncSetAttribute(stage_dp_solo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_solo));
+        stage_dp_solo_kernel<<<(dims->B + kSoloWarps - 1) / kSoloWarps, kSoloWarps * 32, smem_solo, s>>>(a);
+        HMPC_LAUNCH_CHECK("stage_dp_solo_kernel");
+    }
+    stage_dp_search_kernel<<<dims->B, kSearchWarps * 32, smem2, s>>>(a);
     HMPC_LAUNCH_CHECK("stage_dp_search_kernel");
     return HMPC_OK;
 }

@@ -79,10 +79,12 @@ class PeerExchange(object):
         from . import cabi
         return torch.zeros(cabi.aggregate_window_doubles(Nt, world), dtype=torch.float64, device=device)
 
-    def publish(self, u, P_nom, out_prev=None):
-        """out_prev [Nt]: the same launch also writes the world's sum of the PREVIOUS step there (gather with lag 1)"""
+    def publish(self, u, P_nom, out_prev=None, lag=1):
+        """out_prev [Nt]: the same launch also writes the world's sum of the step `lag` publishes back there; the ranks
+        can then drift up to `lag` steps apart without anybody waiting (lag <= 6: the windows hold a ring of 8 steps)"""
         from . import cabi
-        self._partial = cabi.aggregate_publish(u, P_nom, self.world, self.rank, self.windows_dev, out_prev=out_prev)
+        self._partial = cabi.aggregate_publish(u, P_nom, self.world, self.rank, self.windows_dev, out_prev=out_prev,
+                                               lag=lag)
 
     def gather(self, out=None, spin_limit=0, lag=0):
         """sum over the ranks of the step published `lag` steps ago (0 = the latest; zeros while nothing that old

@@ -23,6 +23,7 @@ def twin_kernel(monkeypatch):
         return torch.from_numpy(twin.run(program.cpu().numpy(), int(n_regs), list(mat_sizes), params.cpu().numpy()))
 
     orig = mu.ExprProgram.param_table
+    monkeypatch.setenv("HMPC_PARAM_EVAL", "v1")        # the CPU twin interprets the first kernel's instruction stream
     monkeypatch.setattr(cabi, "param_eval", fake_param_eval)
     monkeypatch.setattr(mu.ExprProgram, "param_table",
                         lambda self, ps, overrides=None, B=None, device="cuda": orig(self, ps, overrides, B, "cpu"))

@@ -361,3 +361,14 @@ def test_peer_store_aggregate_exchange_emulated(cuda_device):
     ex0.publish(torch.ones((4, Nt), dtype=torch.float64, device=cuda_device), torch.ones(4, dtype=torch.float64, device=cuda_device))
     out = ex0.gather(spin_limit=1000).cpu().numpy()
     assert np.isnan(out).all() and ex0.error() == 1
+    # lagged gathers of a longer run (ring of eight slots)
+    wins = [PeerExchange.new_window(Nt, 1, cuda_device)]
+    ex1 = PeerExchange(Nt, cuda_device, world=1, rank=0, windows=wins)
+    hist = []
+    one = torch.ones(1, dtype=torch.float64, device=cuda_device)
+    for step in range(20):
+        u1 = torch.full((1, Nt), float(step), dtype=torch.float64, device=cuda_device)
+        back = torch.empty(Nt, dtype=torch.float64, device=cuda_device)
+        ex1.publish(u1, one, out_prev=back, lag=4)
+        hist.append(back.cpu().numpy()[0])
+    assert hist[:4] == [0.0] * 4 and hist[4:] == [float(i) for i in range(16)]
