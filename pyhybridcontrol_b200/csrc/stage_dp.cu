@@ -92,7 +92,7 @@ struct DpPlan {
     int t_h, t_ga, t_r, t_wq, t_w1, qq;
     int scr;                                                                      // load-time scratch [9*Nt]
     int mst;                                                                      // staged MLD blocks [11][64]
-    int sc_ca, sc_base, sc_slope, sc_fr, sc_i0, sc_span, sc_flags, sc_z, sc_semi, sc_semd;   // per-stage sweep constants
+    int sc_ca, sc_base, sc_slope, sc_fr, sc_i0, sc_span, sc_flags, sc_z, sc_semi, sc_semd, sc_blk;   // per-stage sweep constants
     int total;
 };
 
@@ -122,7 +122,7 @@ __host__ __device__ inline DpPlan make_dp_plan(int Nt, int nb, int nc, int T = k
     const int nc_ = nc > 0 ? nc : 1;
     p.sc_ca = take(Nt * nact); p.sc_base = take(Nt * nc_ * nact); p.sc_slope = take(Nt * nc_); p.sc_fr = take(Nt * nact);
     p.sc_i0 = take((Nt * nact + 1) / 2); p.sc_span = take((Nt * nact + 1) / 2); p.sc_flags = take((Nt + 1) / 2);
-    p.sc_z = take(Nt + 1); p.sc_semi = take(4 * Nt); p.sc_semd = take(4 * Nt);
+    p.sc_z = take(Nt + 1); p.sc_semi = take(4 * Nt); p.sc_semd = take(4 * Nt); p.sc_blk = take(8 * Nt);
     p.total = (o + 1) & ~1;
     return p;
 }
@@ -134,7 +134,7 @@ struct DpCtx {
     int Nt, nb, nc, nact, nmu, nv, G;
     double *ak, *iak, *cu, *qs, *rhs, *tailmin, *amask, *e, *dscale, *galpha, *falpha, *misc, *scr, *mst;
     double *loinf, *hiinf; int* off;
-    double *sc_ca, *sc_base, *sc_slope, *sc_fr, *sc_semd; int *sc_i0, *sc_span, *sc_flags, *sc_z, *sc_semi;
+    double *sc_ca, *sc_base, *sc_slope, *sc_fr, *sc_semd; int *sc_i0, *sc_span, *sc_flags, *sc_z, *sc_semi, *sc_blk;
     double *x_eak, *x_foff, *x_hq, *x_ca, *x_shift;
     double *t_h, *t_ga, *t_r, *t_wq, *t_w1, *qq;
     int T;
@@ -155,6 +155,7 @@ __device__ inline DpCtx bind_ctx(const DpArgs& A, unsigned char* smem) {
     c.sc_i0 = reinterpret_cast<int*>(sd + p.sc_i0); c.sc_span = reinterpret_cast<int*>(sd + p.sc_span);
     c.sc_flags = reinterpret_cast<int*>(sd + p.sc_flags); c.sc_z = reinterpret_cast<int*>(sd + p.sc_z);
     c.sc_semi = reinterpret_cast<int*>(sd + p.sc_semi); c.sc_semd = sd + p.sc_semd;
+    c.sc_blk = reinterpret_cast<int*>(sd + p.sc_blk);
     c.x_eak = sd + p.x_eak; c.x_foff = sd + p.x_foff; c.x_hq = sd + p.x_hq; c.x_ca = sd + p.x_ca; c.x_shift = sd + p.x_shift;
     c.t_h = sd + p.t_h; c.t_ga = sd + p.t_ga; c.t_r = sd + p.t_r; c.t_wq = sd + p.t_wq; c.t_w1 = sd + p.t_w1; c.qq = sd + p.qq;
     c.feas_tol = A.o.feas_tol;
@@ -813,6 +814,28 @@ __global__ void __launch_bounds__(kTableBlock, MINB) stage_dp_table_kernel(const
         for (int i = 0; i < nc; ++i) if (isinf(c.qs[k * nc + i])) c.misc[MISC_SIMPLE] = 0.0;
     }
     __syncthreads();
+    // per (stage, sweep warp): the block ranges of the hand-tuned paths, one byte each -- blocks [0, na) and
+    // [nb, nblocks) read beyond the next stage's window (checked), [na, nb) are interior, of which [za, zb) are
+    // penalty-free.  Computed once here so that a warp starts a stage with one load instead of a chain of them.
+    for (int idx = tid; idx < Nt * (kTableThreads / 32); idx += nthr) {
+        const int k = idx / (kTableThreads / 32), wb = (idx % (kTableThreads / 32)) * 32;
+        const int nblk = (G + kTableThreads - 1) / kTableThreads;
+        int na = 0, nb_ = 0, za = 0, zb = 0;
+        if (k >= 1 && (c.sc_flags[k] & 1) && NC > 0) {
+            const int d0 = c.off[k] - c.off[k + 1];
+            const int rd_lo = c.sc_semi[8 * k + 4], rd_hi = c.sc_semi[8 * k + 5];
+            const int lo_need = -(wb + d0 + rd_lo);                    // n * 512 >= lo_need
+            const int hi_room = G - 1 - wb - 31 - d0 - max(rd_hi, -d0);  // n * 512 <= hi_room (and the cells exist)
+            na = min(max((lo_need + kTableThreads - 1) >> kTableShift, 0), nblk);
+            nb_ = hi_room >= 0 ? min((hi_room >> kTableShift) + 1, nblk) : 0;
+            if (nb_ < na) nb_ = na;
+            const int z0 = c.sc_z[2 * k], z1 = c.sc_z[2 * k + 1];
+            za = max((z0 - wb + kTableThreads - 1) >> kTableShift, 0); zb = ((z1 - 32 - wb) >> kTableShift) + 1;
+            za = min(max(za, na), nb_); zb = min(max(zb, za), nb_);
+        }
+        c.sc_blk[idx] = na | (nb_ << 8) | (za << 16) | (zb << 24);
+    }
+    __syncthreads();
     // linear cells proper need the DEWH shape on every stage (else the agent's cells carry constant lines)
     bool lin_ok = false;
     if (FMT == FMT_LIN && NACT == 2) {
@@ -858,7 +881,6 @@ __global__ void __launch_bounds__(kTableBlock, MINB) stage_dp_table_kernel(const
     // shared memory since the previous iteration): a chain of dependent shared-memory loads and warp reductions that
     // would otherwise sit on every warp's critical path, 48 times.  One barrier per stage.
     Semi S_help; S_help.lo = 0.0; S_help.hi = 0.0;        // helper warp: S_k+1 (the terminal stage costs nothing)
-    const int wbase = warp * 32;
     const int nblocks = (G + kTableThreads - 1) / kTableThreads;
     for (int k = Nt - 1; k >= 1; --k) {
         const int flags = c.sc_flags[k];
@@ -909,15 +931,8 @@ __global__ void __launch_bounds__(kTableBlock, MINB) stage_dp_table_kernel(const
         // ---- (c) the cells of the window.  Blocks [na, nb) of this warp are interior: every cell they read is inside
         // the next stage's window.
         const bool fast = (flags & 1) && NC > 0;
-        int na = 0, nb_ = 0;
-        if (fast) {
-            const int rd_lo = c.sc_semi[8 * k + 4], rd_hi = c.sc_semi[8 * k + 5];
-            const int lo_need = -(wbase + d0 + rd_lo);                    // n * 512 >= lo_need
-            const int hi_room = G - 1 - wbase - 31 - d0 - max(rd_hi, -d0);  // n * 512 <= hi_room (and the cells exist)
-            na = max((lo_need + kTableThreads - 1) >> kTableShift, 0);
-            nb_ = hi_room >= 0 ? (hi_room >> kTableShift) + 1 : 0;
-            if (nb_ < na) nb_ = na;
-        }
+        const unsigned blk = (unsigned)c.sc_blk[k * (kTableThreads / 32) + warp];
+        int na = blk & 255u, nb_ = (blk >> 8) & 255u;
         Semi out = S_next;
         if (FMT == FMT_LIN && lin_ok) {
             LinStage L;
@@ -954,9 +969,7 @@ __global__ void __launch_bounds__(kTableBlock, MINB) stage_dp_table_kernel(const
             const double c0 = s_ca[0], c1 = s_ca[1];
             const int i1 = s_i0[1];
             // penalty-free blocks of this warp: all 32 cells inside [z0, z1)
-            const int z0 = c.sc_z[2 * k], z1 = c.sc_z[2 * k + 1];
-            int za = max((z0 - wbase + kTableThreads - 1) >> kTableShift, 0), zb = ((z1 - 32 - wbase) >> kTableShift) + 1;
-            za = min(max(za, na), nb_); zb = min(max(zb, za), nb_);
+            const int za = (blk >> 16) & 255u, zb = blk >> 24;
             sweep_same2<NCc, true, true, ST>(curs, nxts, G, 0, na, d0, i1, slope, hq, base, c0, c1, out);
             sweep_same2<NCc, true, false, ST>(curs, nxts, G, na, za, d0, i1, slope, hq, base, c0, c1, out);
             sweep_same2<NCc, false, false, ST>(curs, nxts, G, za, zb, d0, i1, slope, hq, base, c0, c1, out);
