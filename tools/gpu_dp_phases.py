@@ -28,7 +28,7 @@ ub = torch.tensor(np.tile([1.0, np.inf, np.inf], Nt), dtype=torch.float64, devic
 isb = torch.tensor(np.tile([1, 0, 0], Nt).astype(np.uint8), device=dev)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 ref = None
-for name, kw in [("fused 8192", dict(cells=8192, fuse_search=1)), ("two kernels 8192", dict(cells=8192, fuse_search=0)),
+for name, kw in [("auto 4096", dict(cells=4096)), ("fused 8192", dict(cells=8192, fuse_search=1)), ("two kernels 8192", dict(cells=8192, fuse_search=0)),
                  ("fused 4096", dict(cells=4096, fuse_search=1)), ("fused 2048", dict(cells=2048, fuse_search=1)),
                  ("fused 8192 fp32", dict(cells=8192, fuse_search=1, table_fp64=0)),
                  ("fused linear 4096", dict(cells=4096, fuse_search=1, bound=1))]:
