@@ -695,7 +695,13 @@ def main_ours(args):
         "roofline": ({"kernel": "stage_dp_table_kernel (+ stage_dp_search_kernel)", "bound": "fp64",
                       "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
                       "frac": achieved_tf / fp64_peak if fp64_peak else None,
-                      "traffic": table_bytes, "peak_source": "hmpc_fp64_peak_probe (DFMA micro-benchmark, measured in this run; "
+                      # DRAM bytes of ONE launch from the round's `ncu --set full` capture of this very configuration
+                      # (profiles/r2_final_table_ncu_full_summary.csv: 388,352 B read + 159,488 B written); null elsewhere
+                      "traffic": (547840 if (B, N_p, int(dp_opts.cells)) == (100, 48, 4096) else None),
+                      "traffic_source": "profiles/r2_final_table_ncu_full_summary.csv (dram__bytes_read.sum + "
+                                        "dram__bytes_write.sum, one launch; the table itself stays in L2)",
+                      "table_bytes_leaving_sm": table_bytes,
+                      "peak_source": "hmpc_fp64_peak_probe (DFMA micro-benchmark, measured in this run; "
                                                               "not in MEASURED_PEAKS.json)",
                       "share_of_step": solve_ms / (total_ms / K),
                       "fp64_pipe_instructions_per_launch": fma / K,
@@ -708,8 +714,8 @@ def main_ours(args):
                               "row is violated, 5 + 3 rows elsewhere on the DEWH path, + the search's) / the solve launch's "
                               "CUDA-event duration, i.e. the fraction is FP64-pipe utilisation over the whole launch, "
                               "set-up and search tail included, on the SMs' aggregate peak (100 of 148 SMs have a CTA at "
-                              "B = 100); `traffic` = value-table bytes leaving the SMs per launch (only the stages the "
-                              "search can read are stored: k = D, 2D, ...)"} if use_dp else
+                              "B = 100); `table_bytes_leaving_sm` = value-table bytes bulk-stored per launch (only the stages "
+                              "the search can read: k = D, 2D, ...); they stay in L2, hence the small DRAM `traffic`"} if use_dp else
                      {"kernel": "milp_bnc_kernel", "bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak,
                       "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak if fp64_peak else None, "traffic": None,
                       "peak_source": "hmpc_fp64_peak_probe (DFMA micro-benchmark, measured in this run)",
