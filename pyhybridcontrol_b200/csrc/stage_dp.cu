@@ -351,56 +351,103 @@ __device__ inline void dp_load(const DpArgs& A, int b, DpCtx& c, double* stage) 
     //   band itself:  env_lo_k = min(lo_k, env_lo_k-1 + smax_k-1) = P_k + min_{j<=k} (lo_j - P_j),  P = prefix sum of
     //   smax (likewise env_hi with the most negative shifts).  Every stage has the same width (the widest of them, at
     //   least 5.4 shifts).
-    double* x_lo = c.scr + 6 * Nt; double* x_hi = c.scr + 7 * Nt; double* x_w = c.scr + 8 * Nt;
-    double margin = 0.0, rlo = 0.0, rhi = 0.0, pp = 0.0, pm = 0.0;
-    if (tid < Nt) {
-        const int k = tid;
-        for (int i = 0; i < Nt; ++i) margin = fmax(margin, s_marg[i]);
-        for (int i = 0; i < k; ++i) {
-            const double a = s_smin[i], bq = s_smax[i];
-            rlo += a; rhi += bq; pp += bq > 0.0 ? bq : 0.0; pm += a < 0.0 ? a : 0.0;
-        }
-        double tail = 0.0;
-        for (int i = Nt - 1; i >= k; --i) { const double cm = s_cmin[i]; tail += cm < 0.0 ? cm : 0.0; }
-        c.tailmin[k] = tail;
-        if (k == 0) c.tailmin[Nt] = 0.0;
-        const double lo_c = fmin(fmax(s_lo[k], rlo), rhi), hi_c = fmax(fmin(s_hi[k], rhi), rlo);
-        x_lo[k] = lo_c - pp; x_hi[k] = hi_c - pm;
-    }
-    __syncthreads();
-    if (tid < Nt) {
-        const int k = tid;
-        double mn = INFINITY, mx = -INFINITY;
-        for (int j = 0; j <= k; ++j) { const double a = x_lo[j], bq = x_hi[j]; mn = a < mn ? a : mn; mx = bq > mx ? bq : mx; }
-        const double env_lo = pp + mn, env_hi = pm + mx;
-        const double a0 = fmax(fmin(env_lo, env_hi) - 2.0 * margin, rlo - 0.01 * margin);
-        double b0 = fmin(fmax(env_lo, env_hi) + margin, rhi + 0.01 * margin);
-        if (!(b0 > a0)) b0 = a0;
-        s_lo[k] = a0; x_w[k] = b0 - a0;
-    }
-    __syncthreads();
+    // One warp does all of it with shuffle scans (lane l owns the CH consecutive stages l*CH ...; kDpMaxNt = 128: CH <= 4):
+    // thread-per-stage loops over the prefixes cost 19 k cycles of a 53 k-cycle set-up, and six barriers.
     if (tid < 32) {
-        double Wmax = 0.0, mg = 0.0;
-        for (int k = tid; k < Nt; k += 32) { Wmax = fmax(Wmax, x_w[k]); mg = fmax(mg, s_marg[k]); }
+        const int lane = tid, CH = (Nt + 31) / 32;
+        const unsigned full = 0xffffffffu;
+        double v_smin[4], v_smax[4], v_cmin[4], v_lo[4], v_hi[4];
+        double margin = 0.0;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            Wmax = fmax(Wmax, __shfl_xor_sync(0xffffffffu, Wmax, o)); mg = fmax(mg, __shfl_xor_sync(0xffffffffu, mg, o));
+        for (int i = 0; i < 4; ++i) {
+            const int k = lane * CH + i;
+            const bool in = i < CH && k < Nt;
+            v_smin[i] = in ? s_smin[k] : 0.0; v_smax[i] = in ? s_smax[k] : 0.0; v_cmin[i] = in ? s_cmin[k] : 0.0;
+            v_lo[i] = in ? s_lo[k] : INFINITY; v_hi[i] = in ? s_hi[k] : -INFINITY;
+            margin = fmax(margin, in ? s_marg[k] : 0.0);
         }
-        if (tid == 0) {
-            double W = fmax(Wmax, 5.4 * mg * (1.0 + 16.0 / (double)c.G));
-            if (!(W > 0.0) || !isfinite(W)) W = 1.0;
-            const double w = W / (double)c.G;
-            c.misc[MISC_W] = w; c.misc[MISC_INVW] = 1.0 / w; c.misc[MISC_SIMPLE] = 1.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) margin = fmax(margin, __shfl_xor_sync(full, margin, o));
+        // exclusive prefix sums: rlo / rhi (reachable states), pp / pm (positive / negative shifts only)
+        double e_rlo[4], e_rhi[4], e_pp[4], e_pm[4];
+        double t_rlo = 0.0, t_rhi = 0.0, t_pp = 0.0, t_pm = 0.0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            e_rlo[i] = t_rlo; e_rhi[i] = t_rhi; e_pp[i] = t_pp; e_pm[i] = t_pm;
+            t_rlo += v_smin[i]; t_rhi += v_smax[i]; t_pp += v_smax[i] > 0.0 ? v_smax[i] : 0.0; t_pm += v_smin[i] < 0.0 ? v_smin[i] : 0.0;
+        }
+        double i_rlo = t_rlo, i_rhi = t_rhi, i_pp = t_pp, i_pm = t_pm;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double a1 = __shfl_up_sync(full, i_rlo, o), a2 = __shfl_up_sync(full, i_rhi, o);
+            const double a3 = __shfl_up_sync(full, i_pp, o), a4 = __shfl_up_sync(full, i_pm, o);
+            if (lane >= o) { i_rlo += a1; i_rhi += a2; i_pp += a3; i_pm += a4; }
+        }
+        const double o_rlo = i_rlo - t_rlo, o_rhi = i_rhi - t_rhi, o_pp = i_pp - t_pp, o_pm = i_pm - t_pm;
+        // suffix sums of min(cmin, 0): the trivial bound on the cost-to-go
+        double suf[4], t_tail = 0.0;
+#pragma unroll
+        for (int i = 3; i >= 0; --i) { t_tail += v_cmin[i] < 0.0 ? v_cmin[i] : 0.0; suf[i] = t_tail; }
+        double i_tail = t_tail;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const double a1 = __shfl_down_sync(full, i_tail, o); if (lane + o < 32) i_tail += a1; }
+        const double o_tail = i_tail - t_tail;
+        // band clamped to what is reachable, minus the slew; running min / max over the stages up to k
+        double x_lo[4], x_hi[4], pp_[4], pm_[4], rl_[4], rh_[4];
+        double r_mn = INFINITY, r_mx = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int k = lane * CH + i;
+            const bool in = i < CH && k < Nt;
+            rl_[i] = o_rlo + e_rlo[i]; rh_[i] = o_rhi + e_rhi[i]; pp_[i] = o_pp + e_pp[i]; pm_[i] = o_pm + e_pm[i];
+            if (in) c.tailmin[k] = o_tail + suf[i];
+            const double lo_c = fmin(fmax(v_lo[i], rl_[i]), rh_[i]), hi_c = fmax(fmin(v_hi[i], rh_[i]), rl_[i]);
+            r_mn = in ? fmin(r_mn, lo_c - pp_[i]) : r_mn; r_mx = in ? fmax(r_mx, hi_c - pm_[i]) : r_mx;
+            x_lo[i] = r_mn; x_hi[i] = r_mx;                       // inclusive within the lane
+        }
+        double i_mn = r_mn, i_mx = r_mx;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double a1 = __shfl_up_sync(full, i_mn, o), a2 = __shfl_up_sync(full, i_mx, o);
+            if (lane >= o) { i_mn = fmin(i_mn, a1); i_mx = fmax(i_mx, a2); }
+        }
+        double p_mn = __shfl_up_sync(full, i_mn, 1), p_mx = __shfl_up_sync(full, i_mx, 1);      // lanes before this one
+        if (lane == 0) { p_mn = INFINITY; p_mx = -INFINITY; }
+        double a0[4], Wmax = 0.0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int k = lane * CH + i;
+            const bool in = i < CH && k < Nt;
+            const double env_lo = pp_[i] + fmin(p_mn, x_lo[i]), env_hi = pm_[i] + fmax(p_mx, x_hi[i]);
+            a0[i] = fmax(fmin(env_lo, env_hi) - 2.0 * margin, rl_[i] - 0.01 * margin);
+            double b0 = fmin(fmax(env_lo, env_hi) + margin, rh_[i] + 0.01 * margin);
+            if (!(b0 > a0[i])) b0 = a0[i];
+            if (in) Wmax = fmax(Wmax, b0 - a0[i]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) Wmax = fmax(Wmax, __shfl_xor_sync(full, Wmax, o));
+        // every stage has the same width: the widest of them, at least 5.4 shifts
+        double W = fmax(Wmax, 5.4 * margin * (1.0 + 16.0 / (double)c.G));
+        if (!(W > 0.0) || !isfinite(W)) W = 1.0;
+        const double w = W / (double)c.G, invw = 1.0 / w;
+        int off_last = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int k = lane * CH + i;
+            if (i < CH && k < Nt) {
+                const int o_ = (int)fmax(fmin(floor(a0[i] * invw), 1.0e9), -1.0e9);
+                c.off[k] = o_;
+                if (k == Nt - 1) off_last = o_;
+            }
+        }
+        off_last = __shfl_sync(full, off_last, (Nt - 1) / CH);
+        if (lane == 0) {
+            c.tailmin[Nt] = 0.0;
+            c.misc[MISC_W] = w; c.misc[MISC_INVW] = invw; c.misc[MISC_SIMPLE] = 1.0;
             c.loinf[Nt] = 0.0; c.hiinf[Nt] = 0.0;
+            c.off[Nt] = off_last; c.off[Nt + 1] = off_last;
         }
     }
-    __syncthreads();
-    if (tid < Nt) {
-        const double invw = c.misc[MISC_INVW];
-        c.off[tid] = (int)fmax(fmin(floor(s_lo[tid] * invw), 1.0e9), -1.0e9);
-    }
-    __syncthreads();
-    if (tid == 0) { c.off[Nt] = c.off[Nt - 1]; c.off[Nt + 1] = c.off[Nt - 1]; }
     __syncthreads();
 }
 
@@ -694,7 +741,6 @@ template <int NC, int NACT, int FMT, int MINB>
 __global__ void __launch_bounds__(kTableBlock, MINB) stage_dp_table_kernel(const DpArgs A) {
     typedef typename Cell<FMT>::T TT;
     extern __shared__ __align__(16) unsigned char smem[];
-    __shared__ double s_kins[kTableBlock / 32];
     __shared__ SearchShared sh_search;
     const int b = blockIdx.x;
     const int nthr = kTableBlock;
@@ -845,25 +891,20 @@ __global__ void __launch_bounds__(kTableBlock, MINB) stage_dp_table_kernel(const
             if (!(fl & 2) || (fl & 4) || mask == 0) lin_ok = false;
         }
     }
-    {   // executed FP64-pipe instructions of the sweep (for the roofline): per cell 4 (two compares, two adds) without
-        // and 5 + 3 NC with penalty arithmetic on the hand-tuned path; the other paths at their mix per action
+    if (helper) {
+        // executed FP64-pipe instructions of the sweep (for the roofline): per cell 4 (two compares, two adds) without
+        // and 5 + 3 NC with penalty arithmetic on the hand-tuned path; the other paths at their mix per action.  The
+        // helper warp adds them up on its own (nobody needs the number before the search tail).
         double kins = 0.0;
-        for (int k = 1 + tid; k < Nt; k += nthr) {
+        for (int k = 1 + lane; k < Nt; k += 32) {
             const int zc = c.sc_z[2 * k + 1] - c.sc_z[2 * k];
             const int fl = c.sc_flags[k];
             if (FMT == FMT_LIN) kins += (double)G * (22.0 + 4.0 * nc);
             else if ((fl & 1) && (fl & 2) && nact == 2) kins += 4.0 * zc + (5.0 + 3.0 * nc) * (G - zc);
             else kins += (double)G * nact * (3.0 + 3.0 * nc);
         }
-        if (warp < (Nt + 31) / 32) { kins = warp_sum(kins); if (lane == 0) s_kins[warp] = kins; }
-        __syncthreads();
-        if (tid == 0) {
-            double tot = 0.0;
-            for (int wv = 0; wv < (Nt + 31) / 32; ++wv) tot += s_kins[wv];
-            c.misc[MISC_KINS] = tot;
-            c.misc[MISC_LINOK] = lin_ok ? 1.0 : 0.0;
-        }
-        __syncthreads();
+        kins = warp_sum(kins);
+        if (lane == 0) { c.misc[MISC_KINS] = kins; c.misc[MISC_LINOK] = lin_ok ? 1.0 : 0.0; }
     }
     const bool bad_agent = c.misc[MISC_FLAG] != 0.0;
     if (bad_agent) {
