@@ -724,7 +724,7 @@ struct Node { double s, cost, bound; unsigned long long p0, p1; int k, pad; };
 struct SearchShared {
     double best, T, root_lb, delta, open_lb;
     unsigned long long bp0, bp1;
-    int sp, nodes, improvements, cut_by_T, limit, defer, pass_done, cap;
+    int sp, nodes, improvements, cut_by_T, limit, defer, pass, cap;
     double cand[kTableBlock / 32];
     unsigned long long cp0[kTableBlock / 32], cp1[kTableBlock / 32];
     int cnt[kTableBlock / 32];
@@ -732,7 +732,7 @@ struct SearchShared {
 
 template <bool SOLO>
 __device__ bool dp_search(const DpArgs& A, const DpCtx& c, int b, Node* stack, int cap, double* ptraj, SearchShared* sh,
-                          int W, int budget);
+                          int W, int budget, bool resume = false);
 
 // MINB = 1: the register budget of one CTA per SM (small batches: the step time is one agent's latency);  MINB = 2: half
 // the registers (a few spills outside the hot loops) so that two CTAs share an SM and hide each other's latencies -- 24 %
@@ -1094,7 +1094,7 @@ __global__ void __launch_bounds__(kTableBlock, MINB) stage_dp_table_kernel(const
         if (warp == 0) done = dp_search<true>(A, c, b, stack, cap, ptraj, &sh_search, 1, (c.Nt + A.D - 1) / A.D + kSoloTail);
         done = __syncthreads_or(done);
         // ... and the whole CTA takes over what is left
-        if (!done) done = dp_search<false>(A, c, b, stack, cap, ptraj, &sh_search, kTableBlock / 32, kTailBudget);
+        if (!done) done = dp_search<false>(A, c, b, stack, cap, ptraj, &sh_search, kTableBlock / 32, kTailBudget, true);
         if (done) return;
         __syncthreads();
     }
@@ -1225,9 +1225,11 @@ __device__ __forceinline__ bool expand_simple(const DpCtx& c, const TabRef& tr, 
 //   dive   : when the stack could not hold the siblings of a first descent, a greedy dive (warp 0, nothing pushed)
 //            produces an incumbent first; the same dive is the best effort of a search that hit its limits without one.
 // Returns false when `budget` expansions were not enough: the incumbent goes to misc[] for whoever continues.
+// `resume`: continue the search another team left unfinished in this very shared memory (stack, threshold, pass and
+// incumbent as they are in *sh) instead of starting over from the root with its incumbent.
 template <bool SOLO>
 __device__ bool dp_search(const DpArgs& A, const DpCtx& c, int b, Node* stack, int cap, double* ptraj, SearchShared* sh,
-                          int W, int budget) {
+                          int W, int budget, bool resume) {
     const int Nt = c.Nt, nb = c.nb, nc = c.nc, nv = c.nv, nact = c.nact;
     const int tid = SOLO ? (int)(threadIdx.x & 31) : (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nthreads = SOLO ? 32 : (int)blockDim.x;
@@ -1240,7 +1242,7 @@ __device__ bool dp_search(const DpArgs& A, const DpCtx& c, int b, Node* stack, i
     tr.linok = c.misc[MISC_LINOK] != 0.0;
     tr.tab = reinterpret_cast<const unsigned char*>(A.table) + (int64_t)b * A.nstore * c.G * fmt_bytes(A.fmt);
     const int D = A.D;
-    const int nodes_in = (int)c.misc[MISC_NODES0];
+    const int nodes_in = resume ? sh->nodes : (int)c.misc[MISC_NODES0];
 
     const bool simple21 = c.misc[MISC_SIMPLE] != 0.0 && nb == 1 && nc == 2 && D == 5;
     // evaluate lane's action sequence below node (k0, s, cost, path); returns ok, and (k1, s, cost, path, bd)
@@ -1285,7 +1287,8 @@ __device__ bool dp_search(const DpArgs& A, const DpCtx& c, int b, Node* stack, i
         }
     };
 
-    if (tid == 0) {
+    if (tid == 0 && resume) { sh->defer = 0; sh->open_lb = INFINITY; }
+    if (tid == 0 && !resume) {
         sh->best = c.misc[MISC_INC_OBJ];
         sh->bp0 = (unsigned long long)__double_as_longlong(c.misc[MISC_INC_P0]);
         sh->bp1 = (unsigned long long)__double_as_longlong(c.misc[MISC_INC_P1]);
@@ -1296,16 +1299,18 @@ __device__ bool dp_search(const DpArgs& A, const DpCtx& c, int b, Node* stack, i
     bar();
     const int fan = (1 << (nb * D)) - 1;
     const int reserve = ((Nt + D - 1) / D) * fan;                 // growth of a sequential descent from any open node
-    if (reserve + 64 > cap && !isfinite(sh->best)) {
+    if (!resume && reserve + 64 > cap && !isfinite(sh->best)) {
         if (warp == 0) greedy_dive();
         bar();
     }
     // ---- exact search, pass by pass
-    for (int pass = 0; pass < 200; ++pass) {
-        if (tid == 0) {
+    const int pass0 = resume ? sh->pass : 0;
+    bar();
+    for (int pass = pass0; pass < 200; ++pass) {
+        if (tid == 0 && !(resume && pass == pass0)) {
             Node r; r.s = 0.0; r.cost = 0.0; r.bound = pass == 0 ? -INFINITY : sh->root_lb; r.p0 = r.p1 = 0; r.k = 0; r.pad = 0;
             stack[0] = r;
-            sh->sp = 1; sh->cut_by_T = 0; sh->pass_done = 0;
+            sh->sp = 1; sh->cut_by_T = 0; sh->pass = pass;
         }
         bar();
         while (true) {
@@ -1341,7 +1346,10 @@ __device__ bool dp_search(const DpArgs& A, const DpCtx& c, int b, Node* stack, i
                 if (nd.k == 0 && pass == 0) {
                     // the root's children fix the first threshold: a hair above the best of their bounds
                     const double rl = warp_min(bd);
-                    const double dl = fmax(1e-3 * fmax(1.0, fabs(rl)), 1e-9);
+                    double dl = fmax(1e-3 * fmax(1.0, fabs(rl)), 1e-9);
+                    // a search that starts with an incumbent (handed over by the one-warp leg) knows the scale of the
+                    // gap: a quarter of it per pass, so the tree is descended twice at most instead of once per factor 4
+                    if (isfinite(best) && best > rl) dl = fmax(dl, 0.25 * (best - rl));
                     if (lane == 0) { sh->root_lb = rl; sh->delta = dl; sh->T = rl + dl; }
                     ok = ok && bd < rl + dl;
                 }
@@ -1412,6 +1420,8 @@ __device__ bool dp_search(const DpArgs& A, const DpCtx& c, int b, Node* stack, i
         if (finished) break;                                     // nothing was held back by the threshold: done
         if (tid == 0) {
             sh->delta *= 4.0;
+            // with an incumbent the scale of the gap is known: at least a quarter of it per pass
+            if (isfinite(sh->best) && sh->best > sh->root_lb) sh->delta = fmax(sh->delta, 0.25 * (sh->best - sh->root_lb));
             double Tn = sh->root_lb + sh->delta;
             sh->T = isfinite(Tn) ? Tn : INFINITY;
         }
