@@ -501,3 +501,52 @@ def test_stage_dp_fuzz_against_branch_and_cut(cuda_device):
         assert rel.max() <= 1e-6, (seed, float(rel.max()), int(np.argmax(rel)))
         checked += int(both.sum())
     assert checked > 800
+
+
+def test_stage_dp_team_search_forms_agree(cuda_device):
+    """Robust constraint sets (256 DEWHs x 32 demand scenarios over the whole horizon, N_p = 48) need 10^2..10^4
+    expansions for some agents, so every leg of the search runs: one warp first, then the team -- resumed in place in
+    the fused tail (fuse_search = 1), restarted from the incumbent in the wide kernel (fuse_search = 0).  Both forms
+    and both table bounds must prove the same optima bit for bit; a node budget below the tree size must return an
+    incumbent that is no better than the optimum, with status 2 and a certified gap that covers the difference."""
+    import torch
+    from pyhybridcontrol_b200 import cabi
+    from pyhybridcontrol_b200.batch import BatchMpc
+    from pyhybridcontrol_b200.examples.residential_mg_with_pv_and_dewhs import synthetic as syn
+    dev = cuda_device
+    B, N_p, S = 256, 48, 32
+    Nt = N_p + 1
+    rng = np.random.default_rng(1048)
+    wl = syn.dewh_batch(B, N_p, seed=5)
+    scen = wl["omega"][:, :, None] * rng.uniform(0.5, 1.8, size=(B, Nt, S))
+    cost = np.zeros((B, Nt, 3)); cost[:, :, 0] = wl["q_u"]; cost[:, :, 1:] = wl["q_mu"][:, None, :]
+    x0 = torch.as_tensor(wl["x0"]).to(dev); om = torch.as_tensor(wl["omega"]).to(dev)
+    sc = torch.as_tensor(scen).to(dev); cst = torch.as_tensor(cost.reshape(B, -1)).to(dev)
+
+    def run(bound, fuse, max_nodes=4000000):
+        bm = BatchMpc(wl["mats"], N_p, nu_l=1, device=dev, dp_bound=bound)
+        bm.dp_opts.fuse_search = fuse
+        bm.dp_opts.max_nodes = max_nodes
+        bm.build(want=("H_x", "H_v", "H_omega", "H_5"))
+        res = bm.solve(x0, om, cost_v=cst, scenarios=sc)
+        return {k: res[k].cpu().numpy() for k in ("obj", "status", "stats", "v")}
+
+    ref = run("constant", 1)
+    assert (ref["status"] == 0).all()
+    assert ref["stats"][:, 0].max() > 200            # the team search is really exercised
+    for bound, fuse in (("constant", 0), ("linear", 1), ("linear", 0)):
+        r = run(bound, fuse)
+        assert (r["status"] == 0).all(), (bound, fuse)
+        assert np.array_equal(r["obj"], ref["obj"]), (bound, fuse)
+    # the returned point reproduces the objective
+    np.testing.assert_allclose((cost.reshape(B, -1) * ref["v"]).sum(axis=1), ref["obj"], rtol=1e-9)
+    # a node budget below the size of the hard trees
+    for fuse in (1, 0):
+        r = run("constant", fuse, max_nodes=150)
+        lim = r["status"] == 2
+        assert lim.any() and ((r["status"] == 0) | lim).all()
+        assert np.array_equal(r["obj"][~lim], ref["obj"][~lim])
+        assert np.isfinite(r["obj"][lim]).all() and (r["obj"][lim] >= ref["obj"][lim] * (1 - 1e-12)).all()
+        gap = r["stats"][lim, 6] * 1e-9
+        true_gap = (r["obj"][lim] - ref["obj"][lim]) / np.abs(r["obj"][lim])
+        assert (gap + 1e-9 >= true_gap).all(), (fuse, float((true_gap - gap).max()))
