@@ -329,9 +329,11 @@ def main_ours(args):
         cost = np.zeros((B, Nt, 3))
         cost[:, :, 0] = wl["q_u"]
         cost[:, :, 1:] = wl["q_mu"][:, None, :]
-        steps_in.append(dict(
-            x0=torch.as_tensor(wl["x0"]).to(dev), omega=torch.as_tensor(wl["omega"]).to(dev),
-            cost=torch.as_tensor(cost.reshape(B, -1)).to(dev), host=wl, host_cost=cost.reshape(B, -1)))
+        # one packed block per instant [x0 | omega | cost]: a new instant reaches the step's static buffers in ONE copy
+        packed = torch.cat([torch.as_tensor(wl["x0"]).reshape(-1), torch.as_tensor(wl["omega"]).reshape(-1),
+                            torch.as_tensor(cost).reshape(-1)]).to(dev)
+        steps_in.append(dict(packed=packed, x0=packed[:B].view(B, 1), omega=packed[B:B + B * Nt].view(B, Nt),
+                             cost=packed[B + B * Nt:].view(B, -1), host=wl, host_cost=cost.reshape(B, -1)))
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
     names = ("condense", "rhs", "solve", "sim", "aggregate")
     use_dp = args.solver == "stage_dp" or (args.solver == "auto" and fleet.batch.stage_dp_ok)
@@ -339,6 +341,7 @@ def main_ours(args):
     kernel_ms = {k: 0.0 for k in names}
     solve_stats, statuses = [], []
     fleet.build()                                  # K1 once: the models do not change between the control instants
+    sim_stream = torch.cuda.Stream()
 
     def one_step(inp, timed_events=None):
         ev = timed_events
@@ -361,9 +364,17 @@ def main_ours(args):
         if ev:
             ev[3].record()
         u = v.view(B, Nt, 3)[:, :, 0]
-        T1, cons = fleet.sim_step(inp["x0"][:, 0].contiguous(), u[:, 0].contiguous(), inp["omega"][:, 0].contiguous())
+        # K5 and K6 both consume the solution and nothing of each other: K5 runs on a side stream next to K6 (in the
+        # breakdown pass, which times them one by one, they stay in line)
+        main_s = torch.cuda.current_stream()
         if ev:
+            T1, cons = fleet.sim_step(inp["x0"][:, 0].contiguous(), u[:, 0].contiguous(), inp["omega"][:, 0].contiguous())
             ev[4].record()
+        else:
+            sim_stream.wait_stream(main_s)
+            with torch.cuda.stream(sim_stream):
+                T1, cons = fleet.sim_step(inp["x0"][:, 0].contiguous(), u[:, 0].contiguous(),
+                                          inp["omega"][:, 0].contiguous())
         if peer_ex is not None:
             # K6 with the exchange fused in: the reduction's last pass stores this rank's sums into every rank's window
             # over NVLink; the same launch adds the world's contributions of the step four publishes back (pipelined: a
@@ -374,6 +385,8 @@ def main_ours(args):
             p_agg = cabi.aggregate_power(u, fleet.P_nom)      # this rank's agents; ranks are summed by exchange()
         if ev:
             ev[5].record()
+        else:
+            main_s.wait_stream(sim_stream)
         return v, obj, status, stats, T1, p_agg
 
     # K6 across ranks: NCCL all-reduce of the [Nt] aggregate power.  Nothing in the NEXT control step depends on it
@@ -434,11 +447,12 @@ def main_ours(args):
     sampler = ClockSampler(local_rank, enabled=(rank == 0))   # one NVML poller per box: queries contend with launches
     # ---- the step as ONE CUDA graph over static input buffers (the per-step inputs are copied in, device to
     #      device, inside the timed region); --no-graph launches the kernels one by one instead
-    static = {k: torch.empty_like(steps_in[0][k]) for k in ("x0", "omega", "cost")}
+    static_packed = torch.empty_like(steps_in[0]["packed"])
+    static = dict(x0=static_packed[:B].view(B, 1), omega=static_packed[B:B + B * Nt].view(B, Nt),
+                  cost=static_packed[B + B * Nt:].view(B, -1))
 
     def load_inputs(inp):
-        for k in static:
-            static[k].copy_(inp[k])
+        static_packed.copy_(inp["packed"])
 
     for s in range(W):
         flush.fill_(float(s))
