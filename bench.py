@@ -560,7 +560,9 @@ def main_ours(args):
     if peer_ex is not None:
         assert peer_ex.error() == 0, "peer exchange: a rank never published step %d" % peer_ex.error()
         assert bool(torch.isfinite(p_total_prev).all())
-    launches_per_step = (1 if args.recondense else 0) + 1 + (2 if use_dp else 1) + 1 + 2  # [K1], K2, K3/K4, K5, K6 (two launches)
+    # [K1], K2, K3/K4 (stage-DP: one fused launch up to 296 agents, else three), K5, K6 (two launches)
+    launches_per_step = ((1 if args.recondense else 0) + 1 + (cabi.stage_dp_launches(B, dp_opts.fuse_search) if use_dp else 1)
+                         + 1 + 2)
     launches = launches_per_step * K if graph is not None else cabi.launch_count - launches0
     if graph is not None:
         step_ms = [e[0].elapsed_time(e[1]) - flush_one_ms for e in evs.values()]

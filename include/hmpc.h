@@ -191,8 +191,9 @@ typedef struct {
                               cell (16 bytes), exact where slack penalties make the cost-to-go steep (full-horizon
                               robust constraint sets); DEWH shape only, other agents get constant lines; the cell
                               count must fit shared memory (hmpc_stage_dp_max_cells)                             */
-    int32_t fuse_search;   /* -1 (default): the table kernel's tail searches the agent itself when B <= 296;
-                              0 / 1: never / always                                                             */
+    int32_t fuse_search;   /* -1 (default): the table kernel's tail searches the agent itself, to the end, when
+                              B <= 296 (ONE launch per solve); else the table kernel is followed by a one-warp
+                              search kernel and a team-search kernel for what that leaves;  0 / 1: never / always */
     int32_t reserved;
 } hmpc_stage_dp_opts;
 enum { HMPC_DP_BOUND_CONSTANT = 0, HMPC_DP_BOUND_LINEAR = 1 };

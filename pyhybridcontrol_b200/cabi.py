@@ -417,6 +417,13 @@ def _stage_terms(d, terms, dev):
     return st, keep
 
 
+def stage_dp_launches(B, fuse_search=-1):
+    """kernels one hmpc_stage_dp_solve_f64 call launches: the table kernel alone when the search is its tail (up to 296
+    agents by default), else table + one-warp search + team search"""
+    fused = (int(B) <= 296) if int(fuse_search) < 0 else bool(fuse_search)
+    return 1 if fused else 3
+
+
 def stage_dp_solve(d, mats, rhs, cost_v, lb, ub, is_bin, opts=None, terms=None):
     """K3s/K4s.  mats as for condense(); rhs [B, nc*Nt]; cost_v [B|1, nv*Nt]; lb/ub [nv*Nt]; is_bin uint8 [nv*Nt];
     terms: optional convex state / slack terms (see hmpc_stage_terms) -> an MIQP."""
@@ -438,7 +445,7 @@ def stage_dp_solve(d, mats, rhs, cost_v, lb, ub, is_bin, opts=None, terms=None):
                                         C.byref(st) if st is not None else None, C.byref(o),
                                         C.c_void_p(ws.data_ptr()), nbytes, _ptr(v), _ptr(obj), _ptr(status),
                                         _ptr(stats), _stream()), "hmpc_stage_dp_solve_f64")
-    launch_count += 2
+    launch_count += stage_dp_launches(d.B, o.fuse_search)
     return v, obj, status, stats
 
 
@@ -740,7 +747,7 @@ class StepPlan(object):
                                            self._out_ptrs[2], self._out_ptrs[3], self.timing),
                "hmpc_mpc_step_host_f64")
         self.last_solver = ("bnc", "stage_dp")[max(0, _lib.hmpc_step_plan_last_solver(self._h))]
-        launch_count += (1 if recondense else 0) + 1 + (2 if self.last_solver == "stage_dp" else 1)
+        launch_count += (1 if recondense else 0) + 1 + (stage_dp_launches(d.B) if self.last_solver == "stage_dp" else 1)
         return self.v, self.obj, self.status, self.stats, tuple(self.timing)
 
     def close(self):

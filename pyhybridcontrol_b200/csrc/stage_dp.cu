@@ -56,7 +56,6 @@ constexpr int kSoloStack = 896;       // ... per warp in the one-warp search ker
 constexpr int kSoloWarps = 4;         // agents per CTA in the one-warp search kernel
 constexpr int kSoloTail = 48;         // expansions beyond one descent that warp 0 spends alone in the fused tail before the CTA joins in
 constexpr int kSoloBudget = 128;      // ... and a warp of the one-warp kernel before it hands the agent to the wide kernel
-constexpr int kTailBudget = 20000;    // expansions the fused tail search may spend before deferring to the wide kernel
 constexpr int kPending = -1;          // status of an agent that kernel 2 still has to search
 constexpr double kEdgeEps = 1e-9;     // cell-boundary guard (fraction of a cell)
 constexpr double kLinSlop = 4e-15;    // relative floating-point slop subtracted per stage from a linear cell
@@ -1093,8 +1092,8 @@ __global__ void __launch_bounds__(kTableBlock, MINB) stage_dp_table_kernel(const
         int done = 0;
         if (warp == 0) done = dp_search<true>(A, c, b, stack, cap, ptraj, &sh_search, 1, (c.Nt + A.D - 1) / A.D + kSoloTail);
         done = __syncthreads_or(done);
-        // ... and the whole CTA takes over what is left
-        if (!done) done = dp_search<false>(A, c, b, stack, cap, ptraj, &sh_search, kTableBlock / 32, kTailBudget, true);
+        // ... and the whole CTA takes over what is left, to the end: a fused launch has no second kernel
+        if (!done) done = dp_search<false>(A, c, b, stack, cap, ptraj, &sh_search, kTableBlock / 32, INT_MAX, true);
         if (done) return;
         __syncthreads();
     }
@@ -1680,9 +1679,9 @@ extern "C" int hmpc_stage_dp_solve_f64(const hmpc_dims* dims, const double* cons
         HMPC_CUDA_TRY(cudaFuncSetAttribute(stage_dp_solo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_solo));
         stage_dp_solo_kernel<<<(dims->B + kSoloWarps - 1) / kSoloWarps, kSoloWarps * 32, smem_solo, s>>>(a);
         HMPC_LAUNCH_CHECK("stage_dp_solo_kernel");
+        stage_dp_search_kernel<<<dims->B, kSearchWarps * 32, smem2, s>>>(a);
+        HMPC_LAUNCH_CHECK("stage_dp_search_kernel");
     }
-    stage_dp_search_kernel<<<dims->B, kSearchWarps * 32, smem2, s>>>(a);
-    HMPC_LAUNCH_CHECK("stage_dp_search_kernel");
     return HMPC_OK;
 }
 
