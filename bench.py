@@ -712,8 +712,8 @@ def main_ours(args):
                       "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
                       "frac": achieved_tf / fp64_peak if fp64_peak else None,
                       # DRAM bytes of ONE launch from the round's `ncu --set full` capture of this very configuration
-                      # (profiles/r2_final_table_ncu_full_summary.csv: 388,352 B read + 159,488 B written); null elsewhere
-                      "traffic": (547840 if (B, N_p, int(dp_opts.cells)) == (100, 48, 4096) else None),
+                      # (profiles/r2_final_table_ncu_full_summary.csv: 386,560 B read + 308,992 B written); null elsewhere
+                      "traffic": (695552 if (B, N_p, int(dp_opts.cells)) == (100, 48, 4096) else None),
                       "traffic_source": "profiles/r2_final_table_ncu_full_summary.csv (dram__bytes_read.sum + "
                                         "dram__bytes_write.sum, one launch; the table itself stays in L2)",
                       "table_bytes_leaving_sm": table_bytes,
