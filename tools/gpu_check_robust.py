@@ -54,6 +54,8 @@ for N_p in horizons:
     for name, bound in (("nominal_constant", "constant"), ("constant", "constant"), ("linear", "linear")):
         bm = BatchMpc(mats, N_p, nu_l=1, device=dev, dp_bound=bound)
         bm.dp_opts.max_nodes = max_nodes
+        if os.environ.get("ROBUST_CELLS"):
+            bm.dp_opts.cells = min(int(os.environ["ROBUST_CELLS"]), cabi.stage_dp_max_cells(bm.dims, bm.dp_opts))
         bm.dp_opts.mip_rel_gap = gap
         bm.build(want=("H_x", "H_v", "H_omega", "H_5"))
         if name.startswith("nominal"):
