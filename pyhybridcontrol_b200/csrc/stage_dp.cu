@@ -25,15 +25,17 @@
 //     cell.  Two cell formats: a constant per cell (default), or a LINE per cell (value at the left and right edge,
 //     cells need not agree at their common edge) built from the lower convex hull of the translated pieces -- exact
 //     where slack penalties make the cost-to-go steep (full-horizon robust constraint sets), and never below the
-//     constant-cell bound.  Two stage buffers live in shared memory between guard cells that hold the semi-infinite
-//     bounds; only the stages the search can read (k = D, 2D, ...: the depth of one search expansion) leave the SM,
-//     each through one TMA bulk copy.
-//   * search (one warp per agent; the tail of kernel 1 when the batch is small, else / for the hard agents kernel 2):
-//     exact depth-first search over the binary sequence in time order -- states and costs are exact FP64 -- pruned by
-//     cost so far + table bound >= min(incumbent, T), where the threshold T starts just above the root bound and
-//     grows geometrically whenever the tree below it is exhausted without a solution (iterative deepening on the
-//     bound: a poor first dive can no longer trap the search in a bad subtree).  The unit of work is the depth-D
-//     subtree under an open node (32 lanes = 32 action sequences, one table read each).
+//     constant-cell bound.  The two stage buffers are exactly 2 G cells of shared memory (no guard cells: the two
+//     semi-infinite bounds of a stage are computed by a helper warp next to the sweep); only the stages the search can
+//     read (k = D, 2D, ...: the depth of one search expansion) leave the SM, each through one TMA bulk copy.
+//   * search: exact depth-first search over the binary sequence in time order -- states and costs are exact FP64 --
+//     pruned by cost so far + table bound >= min(incumbent, T), where the threshold T starts just above the root bound
+//     and grows whenever the tree below it is exhausted without a solution (iterative deepening on the bound: a poor
+//     first dive can no longer trap the search in a bad subtree).  The unit of work is the depth-D subtree under an
+//     open node (32 lanes = 32 action sequences, one table read each).  One warp searches an agent first (a descent is
+//     sequential); what that leaves is searched by a team of warps, several open nodes per round.  Up to 296 agents
+//     all of it is the tail of kernel 1 (ONE launch per solve); above, kernel 1 is followed by stage_dp_solo_kernel
+//     (one warp per agent) and stage_dp_search_kernel (one 16-warp CTA per agent still pending).
 // Optional convex stage terms (quadratic / L1 atoms on the state, outputs and slacks) make the problem an MIQP; they
 // run through the general loops of both kernels.
 #include <limits.h>
