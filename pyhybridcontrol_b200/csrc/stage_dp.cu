@@ -1387,6 +1387,32 @@ __device__ bool dp_search(const DpArgs& A, const DpCtx& c, int b, Node* stack, i
                     win = npush > 1 ? warp_argmin(ok, bd) : (npush ? __ffs(pm) - 1 : -1);
                 }
             }
+            if (SOLO) {
+                // one warp: the outcome of the expansion is already in every lane's registers -- no exchange through
+                // shared memory, one warp barrier per round
+                const int base = sp - 1;
+                if (live) {
+                    if (base + npush > cap) {           // the children do not fit: stop with what is known
+                        if (lane == 0) { sh->limit = 1; sh->sp = base; sh->open_lb = fmin(sh->open_lb, sh->root_lb); }
+                        __syncwarp();
+                        break;
+                    }
+                    if (!leaf && ok) {
+                        int pos = __popc(pm & ((1u << lane) - 1u));           // rank among the survivors
+                        if (lane == win) pos = npush - 1;                     // (the best one goes on top)
+                        else if (lane > win) pos -= 1;
+                        Node ch; ch.s = s; ch.cost = cost; ch.bound = bd; ch.k = nd.k + D; ch.pad = 0; ch.p0 = q0; ch.p1 = q1;
+                        stack[base + pos] = ch;
+                    }
+                    if (leaf && win >= 0 && cand < best && lane == win) {
+                        sh->best = cand; sh->bp0 = q0; sh->bp1 = q1; sh->improvements += 1;
+                    }
+                    if (lane == 0) sh->nodes = nodes + 1;
+                }
+                if (lane == 0) sh->sp = base + npush;
+                __syncwarp();
+                continue;
+            }
             if (mine && lane == 0) {
                 sh->cand[warp] = cand; sh->cnt[warp] = npush;
                 if (live) atomicAdd(&sh->nodes, 1);
