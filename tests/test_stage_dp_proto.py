@@ -94,3 +94,49 @@ def test_search_with_the_piecewise_linear_bound_is_exact(N_p, cells):
         st, oref, vref = osv.solve_milp(prob, polish=True)
         assert st == osv.OPTIMAL and abs(obj + prob.c0 - oref) <= 1e-6 * max(1.0, abs(oref)), (b, obj, oref, nodes)
         assert np.array_equal(u, np.round(vref[prob.is_bin]))
+
+
+# ---- round 2: moving window, semi-infinite cells, linear cells, threshold passes, split search (tools/stage_dp_mw_proto.py)
+from stage_dp_mw_proto import StageDpMw  # noqa: E402
+
+
+@pytest.mark.parametrize("lin", [False, True])
+@pytest.mark.parametrize("cells,x0_shift", [(64, 0.0), (64, -12.0), (512, 14.0)])
+def test_moving_window_tables_are_lower_bounds(lin, cells, x0_shift):
+    """constant and linear cells over the moving window, and the cells beyond the window: never above the exact
+    cost-to-go, for every state a plan can reach and for random states inside and outside the window"""
+    N_p = 9
+    wl = syn.dewh_batch(3, N_p, seed=17)
+    wl["x0"] = wl["x0"] + x0_shift
+    rng = np.random.default_rng(cells + int(lin))
+    for b in range(3):
+        mats, prob = _problem(wl, b)
+        dp = StageDpMw(*from_dewh_problem(mats, prob, wl["Nt"]), cells=cells, lin=lin)
+        for k in range(1, wl["Nt"]):
+            reach = {0.0}
+            for j in range(k):
+                reach |= {s + dp.shift[j] for s in reach}
+            lo = dp.o[k] * dp.w
+            states = list(reach)[:64] + list(lo + rng.uniform(-0.5, 1.5, size=12) * dp.G * dp.w)
+            for s in states:
+                lb, true = dp.bound(k, s), dp.cost_to_go_exact(k, s)
+                assert lb <= true + 1e-9 * max(1.0, abs(true)), (b, k, s, lb, true)
+
+
+@pytest.mark.parametrize("N_p,cells,lin", [(24, 256, False), (24, 1024, True), (48, 2048, False)])
+def test_threshold_search_and_split_search_are_exact(N_p, cells, lin):
+    """iterative deepening on the bound returns the HiGHS optimum and plan; dealing the root's 32 subtrees to eight
+    parts by bound rank (the team kernel's split) returns the same optimum, every subtree being searched exactly once"""
+    wl = syn.dewh_batch(3, N_p, seed=23)
+    for b in range(3):
+        mats, prob = _problem(wl, b)
+        dp = StageDpMw(*from_dewh_problem(mats, prob, wl["Nt"]), cells=cells, lin=lin)
+        obj, u, nodes = dp.solve_ida()
+        st, oref, vref = osv.solve_milp(prob, polish=True)
+        assert st == osv.OPTIMAL and abs(obj + prob.c0 - oref) <= 1e-6 * max(1.0, abs(oref)), (b, obj, oref, nodes)
+        assert np.array_equal(u, np.round(vref[prob.is_bin]))
+        for nparts in (1, 3, 8):
+            obj2, u2, nodes2 = dp.solve_split(nparts=nparts)
+            assert abs(obj2 - obj) <= 1e-11 * max(1.0, abs(obj)), (b, nparts, obj2, obj)
+            assert np.array_equal(u2, u), (b, nparts)
+            assert nodes2 < 50 * max(nodes, 100)

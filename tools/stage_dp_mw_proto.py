@@ -239,3 +239,67 @@ class StageDpMw(StageDp):
             delta *= grow
         self.passes = passes
         return best, best_u, nodes
+
+    # -- the team kernel's split of one hard agent over several CTAs (csrc/stage_dp.cu, dp_search with part / nparts):
+    #    the depth-`depth` prefixes below the root (the 32 "children" one expansion produces) are ranked by their
+    #    bounds and dealt to `nparts` parts, rank r to part r mod nparts; every part searches its own subtrees with the
+    #    threshold passes of solve_ida -- steps of at least a quarter of the known gap once an incumbent exists --
+    #    and prunes with the best plan ANY part has found.  On the GPU the parts run side by side and exchange the
+    #    incumbent through one atomic key; here they run one after the other, which is one of the orders the GPU may
+    #    produce.  Returns (best, plan, expansions).
+    def solve_split(self, nparts=8, depth=5, max_nodes=2000000, delta0=1e-3, grow=4.0):
+        Nt = self.Nt
+        D = min(depth, Nt)
+        kids = []
+        for code in range(1 << D):
+            s, cost, acts = 0.0, 0.0, []
+            for t in range(D):
+                act = float(code >> t & 1)
+                cost += self.stage_cost(t, self.ak[t] * s, act)
+                s += self.shift[t] * act
+                acts.append(act)
+            kids.append((cost + self.bound(D, s), code, s, cost, acts))
+        order = sorted(range(len(kids)), key=lambda i: (kids[i][0], i))
+        root_lb = min(kd[0] for kd in kids)
+        best, best_u, nodes = np.inf, None, 0
+        for part in range(nparts):
+            mine = [kids[i] for r, i in enumerate(order) if r % nparts == part]
+            delta = max(delta0 * max(1.0, abs(root_lb)), 1e-9)
+            while nodes < max_nodes:
+                if np.isfinite(best) and best > root_lb:
+                    delta = max(delta, 0.25 * (best - root_lb))
+                T = root_lb + delta
+                u = np.zeros(Nt)
+                cutoff_hit = False
+                stack = [(D, s, cost, acts, bd) for bd, code, s, cost, acts in sorted(mine, key=lambda kd: -kd[0])]
+                while stack and nodes < max_nodes:
+                    k, s, cost, setter, bd = stack.pop()
+                    tol = 1e-11 * max(1.0, abs(best)) if np.isfinite(best) else 0.0
+                    if bd >= min(best - tol, T):
+                        if bd < best - tol:
+                            cutoff_hit = True
+                        continue
+                    if isinstance(setter, list):
+                        u[:k] = setter
+                    else:
+                        u[k - 1] = setter
+                    nodes += 1
+                    if k == Nt:
+                        best, best_u = cost, u.copy()
+                        continue
+                    p = self.ak[k] * s
+                    nxt = []
+                    for act in (0.0, 1.0):
+                        c2 = cost + self.stage_cost(k, p, act)
+                        s2 = s + self.shift[k] * act
+                        b2 = c2 + self.bound(k + 1, s2)
+                        if b2 < min(best - tol, T):
+                            nxt.append((b2, k + 1, s2, c2, act))
+                        elif b2 < best - tol:
+                            cutoff_hit = True
+                    for b2, k2, s2, c2, act in sorted(nxt, key=lambda t_: -t_[0]):
+                        stack.append((k2, s2, c2, act, b2))
+                if not cutoff_hit or (np.isfinite(best) and best <= T):
+                    break
+                delta *= grow
+        return best, best_u, nodes
